@@ -1,0 +1,1063 @@
+// TEST INFRASTRUCTURE — CPU oracle (see oracle.h for scope, pinning and the
+// citation tags). Plain C++14, single-threaded unless stated, compiled with
+// -ffp-contract=off so that its arithmetic is the written IEEE sequence.
+#include "oracle.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <random>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef MTG_ORACLE_NO_RPOLY
+extern "C" void mtg_ref_rpoly(double* coefficients_decreasing, int* degree,
+                              double* roots_real, double* roots_imag);
+#endif
+
+namespace {
+
+// ---------------------------------------------------------------- P2 table
+// POLY_C:145-161: row 0 all ones; row n = (i-(n-1)) * row n-1  ==> i!/(i-n)!.
+struct BaseTable {
+  double v[MTGO_MAX_CONV][MTGO_MAX_CONV];
+  BaseTable() {
+    const int n_tab = MTGO_MAX_CONV;
+    for (int n = 0; n < n_tab; ++n)
+      for (int i = 0; i < n_tab; ++i) v[n][i] = 0.0;
+    for (int i = 0; i < n_tab; ++i) v[0][i] = 1.0;
+    const int deg = n_tab - 1;
+    int order = deg;
+    for (int n = 1; n < n_tab; ++n) {
+      for (int i = deg - order; i < n_tab; ++i)
+        v[n][i] = static_cast<double>(order - deg + i) * v[n - 1][i];
+      --order;
+    }
+  }
+};
+const BaseTable kBase;
+inline double Bc(int derivative, int j) { return kBase.v[derivative][j]; }
+
+// ------------------------------------------------------- small dense algebra
+typedef std::vector<double> Vec;
+
+// C = A(m x k) * B(k x n), row-major, inner index ascending.
+void matmul(const double* A, const double* B, double* C, int m, int k, int n) {
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < n; ++j) {
+      double s = 0.0;
+      for (int p = 0; p < k; ++p) s += A[i * k + p] * B[p * n + j];
+      C[i * n + j] = s;
+    }
+}
+
+// Partial-pivot Gauss-Jordan inverse (what Eigen's fixed-size inverse() does
+// for sizes > 4, up to rounding order). Returns false if singular.
+bool general_inverse(int n, const double* M, double* Minv) {
+  Vec a(M, M + n * n);
+  Vec b(static_cast<size_t>(n) * n, 0.0);
+  for (int i = 0; i < n; ++i) b[i * n + i] = 1.0;
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    double best = std::fabs(a[c * n + c]);
+    for (int r = c + 1; r < n; ++r)
+      if (std::fabs(a[r * n + c]) > best) {
+        best = std::fabs(a[r * n + c]);
+        piv = r;
+      }
+    if (best == 0.0) return false;
+    if (piv != c)
+      for (int j = 0; j < n; ++j) {
+        std::swap(a[c * n + j], a[piv * n + j]);
+        std::swap(b[c * n + j], b[piv * n + j]);
+      }
+    const double inv = 1.0 / a[c * n + c];
+    for (int j = 0; j < n; ++j) {
+      a[c * n + j] *= inv;
+      b[c * n + j] *= inv;
+    }
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const double f = a[r * n + c];
+      if (f == 0.0) continue;
+      for (int j = 0; j < n; ++j) {
+        a[r * n + j] -= f * a[c * n + j];
+        b[r * n + j] -= f * b[c * n + j];
+      }
+    }
+  }
+  std::memcpy(Minv, b.data(), sizeof(double) * n * n);
+  return true;
+}
+
+// Dense Householder QR solve of the square system M x = rhs (n_rhs columns,
+// rhs row-major [n][n_rhs]); the closest dense stand-in for the reference's
+// Eigen::SparseQR factor/solve (LIN_I:364-374).
+bool qr_solve(int n, const double* M, int n_rhs, double* rhs) {
+  Vec a(M, M + n * n);
+  Vec v(n);
+  for (int c = 0; c < n; ++c) {
+    double norm = 0.0;
+    for (int r = c; r < n; ++r) norm += a[r * n + c] * a[r * n + c];
+    norm = std::sqrt(norm);
+    if (norm == 0.0) return false;
+    const double alpha = (a[c * n + c] > 0.0) ? -norm : norm;
+    for (int r = c; r < n; ++r) v[r] = a[r * n + c];
+    v[c] -= alpha;
+    double vtv = 0.0;
+    for (int r = c; r < n; ++r) vtv += v[r] * v[r];
+    if (vtv == 0.0) continue;
+    const double beta = 2.0 / vtv;
+    for (int j = c; j < n; ++j) {
+      double s = 0.0;
+      for (int r = c; r < n; ++r) s += v[r] * a[r * n + j];
+      s *= beta;
+      for (int r = c; r < n; ++r) a[r * n + j] -= s * v[r];
+    }
+    for (int j = 0; j < n_rhs; ++j) {
+      double s = 0.0;
+      for (int r = c; r < n; ++r) s += v[r] * rhs[r * n_rhs + j];
+      s *= beta;
+      for (int r = c; r < n; ++r) rhs[r * n_rhs + j] -= s * v[r];
+    }
+  }
+  for (int j = 0; j < n_rhs; ++j)
+    for (int r = n - 1; r >= 0; --r) {
+      double s = rhs[r * n_rhs + j];
+      for (int c = r + 1; c < n; ++c) s -= a[r * n + c] * rhs[c * n_rhs + j];
+      if (a[r * n + r] == 0.0) return false;
+      rhs[r * n_rhs + j] = s / a[r * n + r];
+    }
+  return true;
+}
+
+bool cholesky_solve(int n, const double* M, int n_rhs, double* rhs) {
+  Vec l(static_cast<size_t>(n) * n, 0.0);
+  for (int j = 0; j < n; ++j) {
+    double d = M[j * n + j];
+    for (int k = 0; k < j; ++k) d -= l[j * n + k] * l[j * n + k];
+    if (!(d > 0.0)) return false;
+    const double ljj = std::sqrt(d);
+    l[j * n + j] = ljj;
+    for (int i = j + 1; i < n; ++i) {
+      // symmetrise: the reference's R_pp is symmetric only up to rounding
+      double s = 0.5 * (M[i * n + j] + M[j * n + i]);
+      for (int k = 0; k < j; ++k) s -= l[i * n + k] * l[j * n + k];
+      l[i * n + j] = s / ljj;
+    }
+  }
+  for (int c = 0; c < n_rhs; ++c) {
+    for (int i = 0; i < n; ++i) {
+      double s = rhs[i * n_rhs + c];
+      for (int k = 0; k < i; ++k) s -= l[i * n + k] * rhs[k * n_rhs + c];
+      rhs[i * n_rhs + c] = s / l[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      double s = rhs[i * n_rhs + c];
+      for (int k = i + 1; k < n; ++k) s -= l[k * n + i] * rhs[k * n_rhs + c];
+      rhs[i * n_rhs + c] = s / l[i * n + i];
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------- P3, P4, P5
+void quadratic_cost_jacobian(int N, int derivative, double t, double* Q) {
+  for (int i = 0; i < N * N; ++i) Q[i] = 0.0;
+  for (int col = 0; col < N - derivative; ++col)
+    for (int row = 0; row < N - derivative; ++row) {
+      const double exponent = (N - 1 - derivative) * 2 + 1 - row - col;
+      Q[(N - 1 - row) * N + (N - 1 - col)] =
+          Bc(derivative, N - 1 - row) * Bc(derivative, N - 1 - col) *
+          std::pow(t, exponent) * 2.0 / exponent;
+    }
+}
+
+void base_coeffs_with_time(int N, int derivative, double t, double* out) {
+  for (int j = 0; j < N; ++j) out[j] = 0.0;
+  out[derivative] = Bc(derivative, derivative);
+  if (std::fabs(t) < std::numeric_limits<double>::epsilon()) return;
+  double t_power = t;
+  for (int j = derivative + 1; j < N; ++j) {
+    out[j] = Bc(derivative, j) * t_power;
+    t_power = t_power * t;
+  }
+}
+
+void setup_mapping_matrix(int N, double t, double* A) {
+  const int h = N / 2;
+  for (int i = 0; i < h; ++i) {
+    base_coeffs_with_time(N, i, 0.0, A + i * N);
+    base_coeffs_with_time(N, i, t, A + (i + h) * N);
+  }
+}
+
+void invert_mapping_matrix(int N, const double* A, double* Ainv) {
+  const int h = N / 2;
+  Vec a_inv(static_cast<size_t>(h) * h, 0.0), c(h * h), d(h * h), d_inv(h * h);
+  for (int i = 0; i < h; ++i) a_inv[i * h + i] = 1.0 / A[i * N + i];
+  for (int i = 0; i < h; ++i)
+    for (int j = 0; j < h; ++j) {
+      c[i * h + j] = A[(i + h) * N + j];
+      d[i * h + j] = A[(i + h) * N + (j + h)];
+    }
+  general_inverse(h, d.data(), d_inv.data());
+  Vec neg(h * h), t1(h * h), t2(h * h);
+  for (int i = 0; i < h * h; ++i) neg[i] = -d_inv[i];
+  matmul(neg.data(), c.data(), t1.data(), h, h, h);      // (-D^-1) C
+  matmul(t1.data(), a_inv.data(), t2.data(), h, h, h);   // ... diag^-1
+  for (int i = 0; i < h; ++i)
+    for (int j = 0; j < h; ++j) {
+      Ainv[i * N + j] = a_inv[i * h + j];
+      Ainv[i * N + (j + h)] = 0.0;
+      Ainv[(i + h) * N + j] = t2[i * h + j];
+      Ainv[(i + h) * N + (j + h)] = d_inv[i * h + j];
+    }
+}
+
+// -------------------------------------------------- the optimisation object
+struct Problem {
+  int N, D, K, derivative, h;
+  const double* times;
+  const uint8_t* mask;    // [(K+1)][h]
+  const double* values;   // [(K+1)][h][D]
+  // state
+  int n_all, n_fixed, n_free;
+  std::vector<int> col_of_row;      // reordering matrix C, one 1 per row
+  Vec d_f;                          // [D][n_fixed]
+  Vec d_p;                          // [D][n_free]
+  Vec Q, Ainv;                      // [K][N][N]
+};
+
+bool has_constraint(const Problem& p, int v, int k) {
+  return p.mask[v * p.h + k] != 0;
+}
+
+// P6 LIN_I:277-304 (debug prints of :287-292 excluded)
+int update_segment_times(Problem& p, const double* times) {
+  const int N = p.N;
+  p.Q.resize(static_cast<size_t>(p.K) * N * N);
+  p.Ainv.resize(static_cast<size_t>(p.K) * N * N);
+  Vec A(static_cast<size_t>(N) * N);
+  for (int i = 0; i < p.K; ++i) {
+    const double T = times[i];
+    if (!(T > 0.0)) return -3;  // CHECK_GT(segment_time, 0)
+    quadratic_cost_jacobian(N, p.derivative, T, &p.Q[static_cast<size_t>(i) * N * N]);
+    setup_mapping_matrix(N, T, A.data());
+    invert_mapping_matrix(N, A.data(), &p.Ainv[static_cast<size_t>(i) * N * N]);
+  }
+  return 0;
+}
+
+// P7 LIN_I:171-252
+void setup_constraint_reordering(Problem& p) {
+  struct Key { int v, k; };
+  std::vector<Key> all, fixed, free_;
+  const int n_vertices = p.K + 1;
+  for (int v = 0; v < n_vertices; ++v) {
+    const int occ = (v == 0 || v == p.K) ? 1 : 2;
+    for (int co = 0; co < occ; ++co)
+      for (int k = 0; k < p.h; ++k) {
+        all.push_back(Key{v, k});
+        // std::set insert: unique, ordered by (vertex_idx, constraint_idx).
+        // Enumeration is already in that order, so "insert if new" == append
+        // on first occurrence.
+        if (co == 0) (has_constraint(p, v, k) ? fixed : free_).push_back(Key{v, k});
+      }
+  }
+  p.n_all = static_cast<int>(all.size());
+  p.n_fixed = static_cast<int>(fixed.size());
+  p.n_free = static_cast<int>(free_.size());
+  p.col_of_row.assign(p.n_all, -1);
+  p.d_f.assign(static_cast<size_t>(p.D) * p.n_fixed, 0.0);
+  int row = 0;
+  for (const Key& ca : all) {
+    int col = 0;
+    for (const Key& cf : fixed) {
+      if (ca.v == cf.v && ca.k == cf.k) {
+        p.col_of_row[row] = col;
+        for (int d = 0; d < p.D; ++d)
+          p.d_f[static_cast<size_t>(d) * p.n_fixed + col] =
+              p.values[(static_cast<size_t>(cf.v) * p.h + cf.k) * p.D + d];
+      }
+      ++col;
+    }
+    for (const Key& cp : free_) {
+      if (ca.v == cp.v && ca.k == cp.k) p.col_of_row[row] = col;
+      ++col;
+    }
+    ++row;
+  }
+}
+
+// P8a LIN_I:306-335 : H_i = Ainv^T Q Ainv ; R = C^T H C (scatter-add)
+void construct_R(const Problem& p, Vec* R) {
+  const int N = p.N, n = p.n_fixed + p.n_free;
+  R->assign(static_cast<size_t>(n) * n, 0.0);
+  Vec At(N * N), t1(N * N), H(N * N);
+  for (int i = 0; i < p.K; ++i) {
+    const double* Ai = &p.Ainv[static_cast<size_t>(i) * N * N];
+    const double* Q = &p.Q[static_cast<size_t>(i) * N * N];
+    for (int r = 0; r < N; ++r)
+      for (int c = 0; c < N; ++c) At[r * N + c] = Ai[c * N + r];
+    matmul(At.data(), Q, t1.data(), N, N, N);
+    matmul(t1.data(), Ai, H.data(), N, N, N);
+    for (int r = 0; r < N; ++r)
+      for (int c = 0; c < N; ++c)
+        (*R)[static_cast<size_t>(p.col_of_row[i * N + r]) * n + p.col_of_row[i * N + c]] +=
+            H[r * N + c];
+  }
+}
+
+// P8c LIN_I:254-275
+void update_segments_from_compact(const Problem& p, double* coeffs) {
+  const int N = p.N;
+  Vec d_all(p.n_fixed + p.n_free), new_d(N);
+  for (int dim = 0; dim < p.D; ++dim) {
+    for (int c = 0; c < p.n_fixed; ++c) d_all[c] = p.d_f[static_cast<size_t>(dim) * p.n_fixed + c];
+    for (int c = 0; c < p.n_free; ++c)
+      d_all[p.n_fixed + c] = p.d_p[static_cast<size_t>(dim) * p.n_free + c];
+    for (int i = 0; i < p.K; ++i) {
+      for (int r = 0; r < N; ++r) new_d[r] = d_all[p.col_of_row[i * N + r]];
+      const double* Ai = &p.Ainv[static_cast<size_t>(i) * N * N];
+      double* out = coeffs + (static_cast<size_t>(i) * p.D + dim) * N;
+      for (int r = 0; r < N; ++r) {
+        double s = 0.0;
+        for (int c = 0; c < N; ++c) s += Ai[r * N + c] * new_d[c];
+        out[r] = s;
+      }
+    }
+  }
+}
+
+// P8d LIN_I:113-130
+double compute_cost(const Problem& p, const double* coeffs) {
+  const int N = p.N;
+  double cost = 0.0;
+  Vec tmp(N);
+  for (int i = 0; i < p.K; ++i) {
+    const double* Q = &p.Q[static_cast<size_t>(i) * N * N];
+    for (int dim = 0; dim < p.D; ++dim) {
+      const double* c = coeffs + (static_cast<size_t>(i) * p.D + dim) * N;
+      for (int col = 0; col < N; ++col) {  // (c^T Q)
+        double s = 0.0;
+        for (int r = 0; r < N; ++r) s += c[r] * Q[r * N + col];
+        tmp[col] = s;
+      }
+      double partial = 0.0;
+      for (int r = 0; r < N; ++r) partial += tmp[r] * c[r];
+      cost += partial;
+    }
+  }
+  return 0.5 * cost;
+}
+
+// P1 LIN_I:46-99 (validation + state) ; constraints above N/2-1 cannot be
+// represented in mask[][h] and are dropped by the caller like LIN_I:74-95.
+int setup_problem(Problem& p, int N, int D, int K, int derivative,
+                  const double* times, const uint8_t* mask,
+                  const double* values) {
+  if (N < 2 || N > MTGO_MAX_N || (N % 2) != 0) return -1;
+  if (derivative < 0 || derivative > N / 2 - 1) return -2;
+  if (K < 1 || D < 1) return -1;
+  p.N = N; p.D = D; p.K = K; p.derivative = derivative; p.h = N / 2;
+  p.times = times; p.mask = mask; p.values = values;
+  const int rc = update_segment_times(p, times);
+  if (rc) return rc;
+  setup_constraint_reordering(p);
+  return 0;
+}
+
+// P8b LIN_I:337-379
+int solve_linear(Problem& p, int solver, double* coeffs, Vec* R_keep) {
+  p.d_p.assign(static_cast<size_t>(p.D) * p.n_free, 0.0);
+  if (p.n_free == 0) {  // fully constrained shortcut LIN_I:342-348
+    update_segments_from_compact(p, coeffs);
+    if (R_keep) construct_R(p, R_keep);
+    return 0;
+  }
+  Vec R;
+  construct_R(p, &R);
+  const int nf = p.n_fixed, np = p.n_free, n = nf + np;
+  Vec Rpp(static_cast<size_t>(np) * np), rhs(static_cast<size_t>(np) * p.D);
+  for (int r = 0; r < np; ++r)
+    for (int c = 0; c < np; ++c) Rpp[static_cast<size_t>(r) * np + c] = R[static_cast<size_t>(nf + r) * n + nf + c];
+  for (int dim = 0; dim < p.D; ++dim)
+    for (int r = 0; r < np; ++r) {
+      double s = 0.0;  // (-Rpf) * d_f
+      for (int c = 0; c < nf; ++c)
+        s += (-R[static_cast<size_t>(nf + r) * n + c]) * p.d_f[static_cast<size_t>(dim) * nf + c];
+      rhs[static_cast<size_t>(r) * p.D + dim] = s;
+    }
+  const bool ok = (solver == 1) ? cholesky_solve(np, Rpp.data(), p.D, rhs.data())
+                                : qr_solve(np, Rpp.data(), p.D, rhs.data());
+  if (!ok) return -4;
+  for (int dim = 0; dim < p.D; ++dim)
+    for (int r = 0; r < np; ++r)
+      p.d_p[static_cast<size_t>(dim) * np + r] = rhs[static_cast<size_t>(r) * p.D + dim];
+  update_segments_from_compact(p, coeffs);
+  if (R_keep) R_keep->swap(R);
+  return 0;
+}
+
+// NL_I:1537-1606 : J_d summed over dimensions (no 1/2)
+double cost_derivative(const Problem& p) {
+  Vec R;
+  construct_R(p, &R);
+  const int nf = p.n_fixed, np = p.n_free, n = nf + np;
+  double J = 0.0;
+  for (int dim = 0; dim < p.D; ++dim) {
+    const double* df = &p.d_f[static_cast<size_t>(dim) * nf];
+    const double* dp = np ? &p.d_p[static_cast<size_t>(dim) * np] : nullptr;
+    double t_ff = 0.0, t_fp = 0.0, t_pf = 0.0, t_pp = 0.0;
+    for (int r = 0; r < nf; ++r) {
+      double s = 0.0;
+      for (int c = 0; c < nf; ++c) s += R[static_cast<size_t>(r) * n + c] * df[c];
+      t_ff += df[r] * s;
+    }
+    for (int r = 0; r < np; ++r) {
+      double s = 0.0, s2 = 0.0;
+      for (int c = 0; c < nf; ++c) s += R[static_cast<size_t>(nf + r) * n + c] * df[c];
+      for (int c = 0; c < np; ++c) s2 += R[static_cast<size_t>(nf + r) * n + nf + c] * dp[c];
+      t_pf += dp[r] * s;
+      t_pp += dp[r] * s2;
+    }
+    t_fp = t_pf;  // d_f^T R_pf^T d_p is the transpose of the same scalar
+    J += t_ff + t_fp + t_pf + t_pp;
+  }
+  return J;
+}
+
+// ------------------------------------------------------------- E1..E4
+double poly_evaluate(int N, const double* c, double t, int derivative) {
+  if (derivative >= N) return 0.0;
+  const int top = N - 1;
+  double result = Bc(derivative, top) * c[top];
+  for (int j = top - 1; j >= derivative; --j) {
+    result *= t;
+    result += Bc(derivative, j) * c[j];
+  }
+  return result;
+}
+
+void segment_evaluate(int N, int D, const double* seg_coeffs, double t,
+                      int derivative, double* out) {
+  for (int d = 0; d < D; ++d) out[d] = poly_evaluate(N, seg_coeffs + d * N, t, derivative);
+}
+
+int traj_evaluate(int N, int D, int K, const double* coeffs, const double* times,
+                  double t, int derivative, double* out) {
+  double accumulated = 0.0;
+  int i = 0;
+  for (i = 0; i < K; ++i) {
+    accumulated += times[i];
+    if (accumulated > t) break;
+  }
+  if (t > accumulated) {
+    for (int d = 0; d < D; ++d) out[d] = 0.0;
+    return -1;
+  }
+  if (i >= K) i = K - 1;
+  accumulated -= times[i];
+  segment_evaluate(N, D, coeffs + static_cast<size_t>(i) * D * N, t - accumulated, derivative, out);
+  return i;
+}
+
+double norm_d(const double* v, int D) {
+  double s = 0.0;
+  for (int d = 0; d < D; ++d) s += v[d] * v[d];
+  return std::sqrt(s);
+}
+
+// ------------------------------------------------------------- R1 wrapper
+int find_roots_jt(const double* inc, int n, double* re, double* im, int* n_roots) {
+  *n_roots = 0;
+#ifdef MTG_ORACLE_NO_RPOLY
+  (void)inc; (void)n; (void)re; (void)im;
+  return -2;
+#else
+  // RPOLY_C:57-68 strip high-order zeros (|c| >= DBL_MIN counts as non-zero)
+  int last = -1;
+  for (int i = n - 1; i != -1; --i)
+    if (std::fabs(inc[i]) >= std::numeric_limits<double>::min()) { last = i; break; }
+  if (last == -1) return 1;      // all-zero polynomial: no roots, success
+  const int n_coeff = last + 1;
+  if (n_coeff < 2) return 1;     // constant: no roots, success
+  int degree = n_coeff - 1;
+  double poly[101], rr[100], ri[100];
+  for (int i = 0; i < n_coeff; ++i) poly[i] = inc[last - i];  // decreasing powers
+  mtg_ref_rpoly(poly, &degree, rr, ri);
+  if (degree > 0) {
+    *n_roots = degree;
+    for (int i = 0; i < degree; ++i) { re[i] = rr[i]; im[i] = ri[i]; }
+    return 1;
+  }
+  return 0;
+#endif
+}
+
+// POLY_C:32-63
+int select_candidates_from_roots(double t_start, double t_end, const double* re,
+                                 const double* im, int n_roots, double* cand) {
+  if (t_start > t_end) return -1;
+  int n = 0;
+  cand[n++] = t_start;
+  cand[n++] = t_end;
+  for (int i = 0; i < n_roots; ++i) {
+    if (std::fabs(im[i]) > std::numeric_limits<double>::epsilon()) continue;
+    const double c = re[i];
+    if (c < t_start || c > t_end) continue;
+    cand[n++] = c;
+  }
+  return n;
+}
+
+void derivative_coefficients(int N, const double* c, int derivative, double* out) {
+  if (derivative == 0) {
+    for (int j = 0; j < N; ++j) out[j] = c[j];
+    return;
+  }
+  for (int j = 0; j < N; ++j) out[j] = 0.0;
+  for (int j = 0; j < N - derivative; ++j) out[j] = c[j + derivative] * Bc(derivative, j + derivative);
+}
+
+void convolve(const double* data, int nd, const double* kernel, int nk, double* out) {
+  const int len = nd + nk - 1;
+  for (int i = 0; i < len; ++i) {
+    out[i] = 0.0;
+    const int data_idx = i - nk + 1;
+    const int lower = std::max(0, -data_idx);
+    const int upper = std::min(nk, nd - data_idx);
+    for (int k = lower; k < upper; ++k) out[i] += kernel[nk - 1 - k] * data[data_idx + k];
+  }
+}
+
+// POLY_C:65-83 on a polynomial with n_c coefficients: roots of derivative+1.
+int poly_min_max_candidates(int n_c, const double* c, double t_start, double t_end,
+                            int derivative, double* cand) {
+  if (n_c - derivative - 1 < 0) return -1;
+  double dc[MTGO_MAX_CONV + 2];
+  derivative_coefficients(n_c, c, derivative + 1, dc);
+  double re[100], im[100];
+  int n_roots = 0;
+  find_roots_jt(dc, n_c, re, im, &n_roots);  // failure only logged (POLY_C:75-78)
+  return select_candidates_from_roots(t_start, t_end, re, im, n_roots, cand);
+}
+
+// SEG_C:82-133
+int segment_candidate_times(int N, int D, const double* seg, int derivative,
+                            double t_start, double t_end, const int* dims,
+                            int n_dims, double* cand) {
+  if (n_dims <= 0) return -1;
+  if (n_dims > 1) {
+    const int n_d = N - derivative, n_dd = n_d - 1;
+    if (n_dd < 1) return -1;
+    const int len = n_d + n_dd - 1;
+    double conv[MTGO_MAX_CONV + 2], tmp[MTGO_MAX_CONV + 2], d[MTGO_MAX_N], dd[MTGO_MAX_N];
+    for (int i = 0; i < len; ++i) conv[i] = 0.0;
+    for (int q = 0; q < n_dims; ++q) {
+      const int dim = dims[q];
+      if (dim < 0 || dim >= D) return -1;
+      derivative_coefficients(N, seg + dim * N, derivative, d);
+      derivative_coefficients(N, seg + dim * N, derivative + 1, dd);
+      convolve(d, n_d, dd, n_dd, tmp);
+      for (int i = 0; i < len; ++i) conv[i] += tmp[i];
+    }
+    return poly_min_max_candidates(len, conv, t_start, t_end, -1, cand);
+  }
+  return poly_min_max_candidates(N, seg + dims[0] * N, t_start, t_end, derivative, cand);
+}
+
+double segment_magnitude(int N, const double* seg, double t, int derivative,
+                         const int* dims, int n_dims) {
+  double m = 0.0;
+  for (int q = 0; q < n_dims; ++q) {
+    const double v = poly_evaluate(N, seg + dims[q] * N, t, derivative);
+    m += std::pow(v, 2);
+  }
+  return std::sqrt(m);
+}
+
+// ------------------------------------------------------------- T1 geometry
+struct TubeSeg {
+  double A[9], b[3], n[3], p_start[3], p_end[3], r_tube, r_sphere, pad[1];
+};
+static_assert(sizeof(TubeSeg) == 24 * sizeof(double), "geom layout");
+
+void tube_geometry(int K, const double* pos, const double* radii, TubeSeg* g) {
+  for (int i = 0; i < K; ++i) {
+    const double* s = pos + 3 * i;
+    const double* e = pos + 3 * (i + 1);
+    double v[3] = {e[0] - s[0], e[1] - s[1], e[2] - s[2]};
+    const double nrm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    for (int k = 0; k < 3; ++k) v[k] = v[k] / nrm;
+    const double nx = v[0], ny = v[1], nz = v[2];
+    const double px = s[0], py = s[1], pz = s[2];
+    TubeSeg& t = g[i];
+    const double A[9] = {1 - std::pow(nx, 2), -nx * ny, -nx * nz,
+                         -nx * ny, 1 - std::pow(ny, 2), -ny * nz,
+                         -nx * nz, -ny * nz, 1 - std::pow(nz, 2)};
+    for (int k = 0; k < 9; ++k) t.A[k] = (A[k] > -0.000001 && A[k] < 0.000001) ? 0.0 : A[k];
+    const double b[3] = {(std::pow(nx, 2) - 1) * px + nx * ny * py + nx * nz * pz,
+                         nx * ny * px + (std::pow(ny, 2) - 1) * py + ny * nz * pz,
+                         nx * nz * px + ny * nz * py + (std::pow(nz, 2) - 1) * pz};
+    for (int k = 0; k < 3; ++k) t.b[k] = (b[k] > -0.000001 && b[k] < 0.000001) ? 0.0 : b[k];
+    const double r_start = (i == 0) ? radii[0] : radii[2 * (i - 1) + 1];
+    const double r_end = radii[2 * i + 1];
+    for (int k = 0; k < 3; ++k) {
+      t.n[k] = v[k];
+      t.p_start[k] = s[k] + (-v[k]) * r_start;
+      t.p_end[k] = e[k] + v[k] * r_end;
+    }
+    t.r_tube = radii[2 * i];
+    t.r_sphere = radii[2 * i + 1];
+    t.pad[0] = 0.0;
+  }
+}
+
+int tube_flags(const TubeSeg& t, const double* vertex_end, const double* x) {
+  double q = 0.0;
+  for (int r = 0; r < 3; ++r) {
+    const double y = t.A[3 * r] * x[0] + t.A[3 * r + 1] * x[1] + t.A[3 * r + 2] * x[2] + t.b[r];
+    q += y * y;
+  }
+  const bool in_cyl = (q - t.r_tube * t.r_tube) <= 0.0;
+  double cs = 0.0, ce = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    cs += (-t.n[k]) * (x[k] - t.p_start[k]);
+    ce += t.n[k] * (x[k] - t.p_end[k]);
+  }
+  const bool in_caps = (cs <= 0.0) && (ce <= 0.0);
+  double sq = 0.0;
+  for (int k = 0; k < 3; ++k) sq += (x[k] - vertex_end[k]) * (x[k] - vertex_end[k]);
+  const bool in_sphere = (sq - t.r_sphere * t.r_sphere) <= 0.0;
+  return (in_cyl && in_caps ? 1 : 0) | (in_sphere ? 2 : 0);
+}
+
+}  // namespace
+
+// =========================================================== C entry points
+extern "C" {
+
+void mtgo_base_coefficients(double* out) {
+  for (int n = 0; n < MTGO_MAX_CONV; ++n)
+    for (int i = 0; i < MTGO_MAX_CONV; ++i) out[n * MTGO_MAX_CONV + i] = kBase.v[n][i];
+}
+void mtgo_quadratic_cost_jacobian(int N, int derivative, double t, double* Q) {
+  quadratic_cost_jacobian(N, derivative, t, Q);
+}
+void mtgo_base_coeffs_with_time(int N, int derivative, double t, double* out) {
+  base_coeffs_with_time(N, derivative, t, out);
+}
+void mtgo_setup_mapping_matrix(int N, double t, double* A) { setup_mapping_matrix(N, t, A); }
+void mtgo_invert_mapping_matrix(int N, const double* A, double* Ainv) {
+  invert_mapping_matrix(N, A, Ainv);
+}
+int mtgo_general_inverse(int n, const double* M, double* Minv) {
+  return general_inverse(n, M, Minv) ? 0 : -1;
+}
+
+int mtgo_create_random_vertices(int maximum_derivative, int n_segments, int D,
+                                const double* pos_min, const double* pos_max,
+                                uint64_t seed, int half_n, uint8_t* mask,
+                                double* values) {
+  if (n_segments < 1 || maximum_derivative <= 0) return -1;  // VTX_C:31-34
+  std::mt19937 generator(seed);
+  std::vector<std::uniform_real_distribution<double> > dist(D);
+  for (int i = 0; i < D; ++i) dist[i] = std::uniform_real_distribution<double>(pos_min[i], pos_max[i]);
+  const double min_distance = 0.2;
+  const int n_vertices = n_segments + 1;
+  std::memset(mask, 0, static_cast<size_t>(n_vertices) * half_n);
+  for (size_t i = 0; i < static_cast<size_t>(n_vertices) * half_n * D; ++i) values[i] = 0.0;
+  Vec last(D), pos(D);
+  for (int i = 0; i < D; ++i) last[i] = dist[i](generator);
+  auto set_pos = [&](int v, const Vec& p) {
+    mask[v * half_n + 0] = 1;
+    for (int d = 0; d < D; ++d) values[(static_cast<size_t>(v) * half_n + 0) * D + d] = p[d];
+  };
+  auto make_start_or_end = [&](int v, const Vec& p) {  // VTX_C:147-153
+    set_pos(v, p);
+    for (int k = 1; k <= maximum_derivative && k < half_n; ++k) mask[v * half_n + k] = 1;
+  };
+  make_start_or_end(0, last);
+  for (int v = 1; v < n_vertices; ++v) {
+    while (true) {
+      for (int d = 0; d < D; ++d) pos[d] = dist[d](generator);
+      double s = 0.0;
+      for (int d = 0; d < D; ++d) s += (pos[d] - last[d]) * (pos[d] - last[d]);
+      if (std::sqrt(s) > min_distance) break;
+    }
+    set_pos(v, pos);
+    last = pos;
+  }
+  make_start_or_end(n_vertices - 1, last);
+  return n_vertices;
+}
+
+void mtgo_estimate_segment_times_nfabian(int K, int D, const double* positions,
+                                         double v_max, double a_max,
+                                         double magic, double* times) {
+  for (int i = 0; i < K; ++i) {
+    double s = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double e = positions[(i + 1) * D + d] - positions[i * D + d];
+      s += e * e;
+    }
+    const double distance = std::sqrt(s);
+    times[i] = distance / v_max * 2 *
+               (1.0 + magic * v_max / a_max * std::exp(-distance / v_max * 2));
+  }
+}
+
+void mtgo_estimate_segment_times_velocity_ramp(int K, int D, const double* positions,
+                                               double v_max, double a_max,
+                                               double* times) {
+  for (int i = 0; i < K; ++i) {
+    double s = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double e = positions[i * D + d] - positions[(i + 1) * D + d];
+      s += e * e;
+    }
+    const double distance = std::sqrt(s);
+    const double acc_time = v_max / a_max;
+    const double acc_distance = 0.5 * v_max * acc_time;
+    times[i] = (distance < 2.0 * acc_distance)
+                   ? 2.0 * std::sqrt(distance / a_max)
+                   : 2.0 * acc_time + (distance - 2.0 * acc_distance) / v_max;
+  }
+}
+
+int mtgo_solve(int N, int D, int K, int derivative, const double* times,
+               const uint8_t* mask, const double* values, int solver,
+               double* coeffs, double* cost, int* counts, double* d_f,
+               double* d_p, double* R_out, int* col_of_row) {
+  Problem p;
+  int rc = setup_problem(p, N, D, K, derivative, times, mask, values);
+  if (rc) return rc;
+  Vec R;
+  rc = solve_linear(p, solver, coeffs, R_out ? &R : nullptr);
+  if (rc) return rc;
+  if (cost) *cost = compute_cost(p, coeffs);
+  if (counts) { counts[0] = p.n_all; counts[1] = p.n_fixed; counts[2] = p.n_free; }
+  if (d_f) std::copy(p.d_f.begin(), p.d_f.end(), d_f);
+  if (d_p) std::copy(p.d_p.begin(), p.d_p.end(), d_p);
+  if (R_out) std::copy(R.begin(), R.end(), R_out);
+  if (col_of_row) std::copy(p.col_of_row.begin(), p.col_of_row.end(), col_of_row);
+  return 0;
+}
+
+int mtgo_solve_canonical_batch(int B, int N, int D, int K, int derivative,
+                               const double* positions, const double* times,
+                               int solver, int n_threads, double* coeffs,
+                               double* cost) {
+  const int h = N / 2;
+  int bad = 0;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(n_threads > 0 ? n_threads : 1) schedule(static) reduction(+ : bad)
+#else
+  (void)n_threads;
+#endif
+  for (int b = 0; b < B; ++b) {
+    std::vector<uint8_t> mask(static_cast<size_t>(K + 1) * h, 0);
+    Vec values(static_cast<size_t>(K + 1) * h * D, 0.0);
+    for (int v = 0; v <= K; ++v) {
+      mask[v * h] = 1;
+      for (int d = 0; d < D; ++d)
+        values[(static_cast<size_t>(v) * h) * D + d] = positions[(static_cast<size_t>(b) * (K + 1) + v) * D + d];
+    }
+    for (int k = 1; k < h; ++k) mask[k] = mask[K * h + k] = 1;
+    double c = 0.0;
+    const int rc = mtgo_solve(N, D, K, derivative, times + static_cast<size_t>(b) * K, mask.data(),
+                              values.data(), solver, coeffs + static_cast<size_t>(b) * K * D * N, &c,
+                              nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc) ++bad;
+    if (cost) cost[b] = c;
+  }
+  return bad ? -1 : 0;
+}
+
+int mtgo_coeffs_from_free_constraints(int N, int D, int K, const double* times,
+                                      const uint8_t* mask, const double* values,
+                                      const double* d_p, double* coeffs) {
+  Problem p;
+  const int rc = setup_problem(p, N, D, K, N / 2 - 1, times, mask, values);
+  if (rc) return rc;
+  p.d_p.assign(d_p, d_p + static_cast<size_t>(D) * p.n_free);
+  update_segments_from_compact(p, coeffs);
+  return 0;
+}
+
+int mtgo_cost_time_fd(int N, int D, int K, int derivative, const double* times,
+                      const uint8_t* mask, const double* values,
+                      const double* d_p, double increment_time, int central,
+                      double* J_nominal, double* J_plus, double* J_minus,
+                      double* grad_d) {
+  Problem p;
+  int rc = setup_problem(p, N, D, K, derivative, times, mask, values);
+  if (rc) return rc;
+  p.d_p.assign(d_p, d_p + static_cast<size_t>(D) * p.n_free);
+  const double J0 = cost_derivative(p);
+  if (J_nominal) *J_nominal = J0;
+  Vec t(K);
+  for (int n = 0; n < K; ++n) {
+    double J_small = 0.0;
+    if (central) {
+      for (int i = 0; i < K; ++i) t[i] = times[i];
+      t[n] = t[n] <= 0.1 ? 0.1 : t[n] - increment_time;
+      rc = update_segment_times(p, t.data());
+      if (rc) return rc;
+      J_small = cost_derivative(p);
+      if (J_minus) J_minus[n] = J_small;
+    }
+    for (int i = 0; i < K; ++i) t[i] = times[i];
+    t[n] = t[n] <= 0.1 ? 0.1 : t[n] + increment_time;
+    rc = update_segment_times(p, t.data());
+    if (rc) return rc;
+    const double J_big = cost_derivative(p);
+    if (J_plus) J_plus[n] = J_big;
+    if (grad_d)
+      grad_d[n] = central ? (J_big - J_small) / (2.0 * increment_time)
+                          : (J_big - J0) / (increment_time);
+  }
+  return 0;
+}
+
+double mtgo_poly_evaluate(int N, const double* c, double t, int derivative) {
+  return poly_evaluate(N, c, t, derivative);
+}
+void mtgo_poly_derivative_coefficients(int N, const double* c, int derivative, double* out) {
+  derivative_coefficients(N, c, derivative, out);
+}
+void mtgo_convolve(const double* data, int n_data, const double* kernel, int n_kernel, double* out) {
+  convolve(data, n_data, kernel, n_kernel, out);
+}
+int mtgo_traj_evaluate(int N, int D, int K, const double* coeffs, const double* times,
+                       double t, int derivative, double* out) {
+  return traj_evaluate(N, D, K, coeffs, times, t, derivative, out);
+}
+
+int mtgo_traj_evaluate_range(int N, int D, int K, const double* coeffs,
+                             const double* times, double t_start, double t_end,
+                             double dt, int derivative, int cap, double* out,
+                             double* sampling_times, int32_t* segment_idx) {
+  double accumulated = 0.0;
+  int i = 0;
+  for (i = 0; i < K; ++i) {
+    accumulated += times[i];
+    if (accumulated > t_start) break;
+  }
+  if (t_start > accumulated) return -1;
+  if (i >= K) return -1;  // t_start == max_time: reference indexes segments_[K] (UB)
+  accumulated -= times[i];
+  double tau = t_start - accumulated;
+  int n = 0;
+  while (accumulated < t_end) {
+    if (tau > times[i]) {
+      tau = tau - times[i];
+      ++i;
+      if (i >= K) break;
+      continue;
+    }
+    if (n >= cap) return n;
+    if (out) segment_evaluate(N, D, coeffs + static_cast<size_t>(i) * D * N, tau, derivative, out + static_cast<size_t>(n) * D);
+    if (sampling_times) sampling_times[n] = accumulated;
+    if (segment_idx) segment_idx[n] = i;
+    ++n;
+    tau += dt;
+    accumulated += dt;
+  }
+  return n;
+}
+
+int mtgo_find_roots_jenkins_traub(const double* inc, int n, double* re, double* im, int* n_roots) {
+  return find_roots_jt(inc, n, re, im, n_roots);
+}
+int mtgo_select_min_max_candidates_from_roots(double t_start, double t_end, const double* re,
+                                              const double* im, int n_roots, double* cand) {
+  return select_candidates_from_roots(t_start, t_end, re, im, n_roots, cand);
+}
+
+int mtgo_poly_compute_min_max(int N, const double* c, double t_start, double t_end,
+                              int derivative, double* min_t, double* min_v,
+                              double* max_t, double* max_v) {
+  double cand[128];
+  const int n = poly_min_max_candidates(N, c, t_start, t_end, derivative, cand);
+  if (n <= 0) return -1;
+  *min_t = cand[0]; *min_v = std::numeric_limits<double>::max();
+  *max_t = cand[0]; *max_v = std::numeric_limits<double>::lowest();
+  for (int i = 0; i < n; ++i) {  // POLY_C:116-143
+    const double v = poly_evaluate(N, c, cand[i], derivative);
+    if (v < *min_v) { *min_t = cand[i]; *min_v = v; }
+    if (v > *max_v) { *max_t = cand[i]; *max_v = v; }
+  }
+  return 0;
+}
+
+int mtgo_segment_candidate_times(int N, int D, const double* seg, int derivative,
+                                 double t_start, double t_end, const int* dims,
+                                 int n_dims, double* cand, int cap) {
+  double tmp[128];
+  const int n = segment_candidate_times(N, D, seg, derivative, t_start, t_end, dims, n_dims, tmp);
+  for (int i = 0; i < n && i < cap; ++i) cand[i] = tmp[i];
+  return n;
+}
+
+int mtgo_traj_min_max_magnitude(int N, int D, int K, const double* coeffs,
+                                const double* times, int derivative,
+                                const int* dims, int n_dims, double* min_time,
+                                double* min_value, int* min_seg,
+                                double* max_time, double* max_value, int* max_seg) {
+  double mn_v = std::numeric_limits<double>::max(), mx_v = std::numeric_limits<double>::lowest();
+  double mn_t = 0.0, mx_t = 0.0;
+  int mn_s = 0, mx_s = 0;
+  for (int s = 0; s < K; ++s) {
+    const double* seg = coeffs + static_cast<size_t>(s) * D * N;
+    double cand[128];
+    // SEG_C:135-158: the bool of the candidate-time search is ignored there.
+    int n = segment_candidate_times(N, D, seg, derivative, 0.0, times[s], dims, n_dims, cand);
+    if (n < 0) n = 0;
+    // SEG_C:160-184
+    if (0.0 > times[s]) return -1;
+    double smn_v = std::numeric_limits<double>::max(), smx_v = std::numeric_limits<double>::lowest();
+    double smn_t = 0.0, smx_t = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double t = cand[i];
+      if (t < 0.0 || t > times[s]) continue;
+      const double m = segment_magnitude(N, seg, t, derivative, dims, n_dims);
+      if (smx_v < m) { smx_v = m; smx_t = t; }   // std::max keeps first on ties
+      if (m < smn_v) { smn_v = m; smn_t = t; }   // std::min keeps first on ties
+    }
+    if (smn_v < mn_v) { mn_v = smn_v; mn_t = smn_t; mn_s = s; }
+    if (smx_v > mx_v) { mx_v = smx_v; mx_t = smx_t; mx_s = s; }
+  }
+  *min_time = mn_t; *min_value = mn_v; *min_seg = mn_s;
+  *max_time = mx_t; *max_value = mx_v; *max_seg = mx_s;
+  return 0;
+}
+
+int mtgo_opt_max_magnitude(int N, int D, int K, const double* coeffs,
+                           const double* times, int derivative,
+                           double* max_time, double* max_value, int* max_seg) {
+  if (!(N - derivative - 1 > 0)) return -1;  // LIN_I:401
+  std::vector<int> dims(D);
+  for (int d = 0; d < D; ++d) dims[d] = d;
+  double e_t = 0.0, e_v = 0.0;  // Extremum() default
+  int e_s = 0;
+  Vec val(D);
+  for (int s = 0; s < K; ++s) {
+    const double* seg = coeffs + static_cast<size_t>(s) * D * N;
+    double cand[128];
+    int n = segment_candidate_times(N, D, seg, derivative, 0.0, times[s], dims.data(), D, cand);
+    if (n < 0) n = 0;  // the pushed 0.0 is cleared by the callee (SEG_C:87)
+    for (int i = 0; i < n; ++i) {
+      segment_evaluate(N, D, seg, cand[i], derivative, val.data());
+      const double m = norm_d(val.data(), D);
+      if (e_v < m) { e_v = m; e_t = cand[i]; e_s = s; }
+    }
+  }
+  const double* seg = coeffs + static_cast<size_t>(K - 1) * D * N;
+  segment_evaluate(N, D, seg, times[K - 1], derivative, val.data());
+  const double m = norm_d(val.data(), D);
+  if (e_v < m) { e_v = m; e_t = times[K - 1]; e_s = K - 1; }
+  *max_time = e_t; *max_value = e_v; *max_seg = e_s;
+  return 0;
+}
+
+double mtgo_sampled_maximum_magnitude(int N, int D, int K, const double* coeffs,
+                                      const double* times, int derivative, double dt) {
+  double max_time = 0.0;
+  for (int i = 0; i < K; ++i) max_time += times[i];
+  double maximum = -1e9;
+  Vec v(D);
+  for (double ts = 0; ts < max_time; ts += dt) {
+    traj_evaluate(N, D, K, coeffs, times, ts, derivative, v.data());
+    const double cur = norm_d(v.data(), D);
+    if (cur > maximum) maximum = cur;
+  }
+  return maximum;
+}
+
+double mtgo_cost_numeric(int N, int D, int K, const double* coeffs,
+                         const double* times, int derivative, double dt) {
+  double max_time = 0.0;
+  for (int i = 0; i < K; ++i) max_time += times[i];
+  double cost = 0.0;
+  Vec v(D);
+  for (double ts = 0; ts < max_time; ts += dt) {
+    traj_evaluate(N, D, K, coeffs, times, ts, derivative, v.data());
+    double s = 0.0;
+    for (int d = 0; d < D; ++d) s += v[d] * v[d];
+    cost += s * dt;
+  }
+  return cost;
+}
+
+void mtgo_tube_geometry(int K, const double* positions, const double* radii, double* geom) {
+  tube_geometry(K, positions, radii, reinterpret_cast<TubeSeg*>(geom));
+}
+int mtgo_tube_flags(const double* geom_seg, const double* vertex_end, const double* x) {
+  return tube_flags(*reinterpret_cast<const TubeSeg*>(geom_seg), vertex_end, x);
+}
+
+int mtgo_feasibility_sweep(int N, int K, const double* coeffs, const double* times,
+                           const double* positions, const double* radii,
+                           double v_max, double a_max, double t_start,
+                           double t_end, double dt, int cap, double* pos_out,
+                           uint8_t* flags, double* max_v, double* max_a) {
+  const int D = 3;
+  std::vector<TubeSeg> geom;
+  if (radii) { geom.resize(K); tube_geometry(K, positions, radii, geom.data()); }
+  double accumulated = 0.0;
+  int i = 0;
+  for (i = 0; i < K; ++i) {
+    accumulated += times[i];
+    if (accumulated > t_start) break;
+  }
+  if (t_start > accumulated || i >= K) return -1;
+  accumulated -= times[i];
+  double tau = t_start - accumulated;
+  int n = 0;
+  double mv = 0.0, ma = 0.0;
+  while (accumulated < t_end) {
+    if (tau > times[i]) {
+      tau = tau - times[i];
+      ++i;
+      if (i >= K) break;
+      continue;
+    }
+    if (n >= cap) break;
+    const double* seg = coeffs + static_cast<size_t>(i) * D * N;
+    double x[3], v[3], a[3];
+    segment_evaluate(N, D, seg, tau, 0, x);
+    segment_evaluate(N, D, seg, tau, 1, v);
+    segment_evaluate(N, D, seg, tau, 2, a);
+    const double nv = norm_d(v, 3), na = norm_d(a, 3);
+    if (nv > mv) mv = nv;
+    if (na > ma) ma = na;
+    int f = (nv <= v_max ? 1 : 0) | (na <= a_max ? 2 : 0);
+    if (radii) f |= (tube_flags(geom[i], positions + 3 * (i + 1), x) & 1) ? 4 : 0;
+    if (pos_out) for (int d = 0; d < 3; ++d) pos_out[static_cast<size_t>(n) * 3 + d] = x[d];
+    if (flags) flags[n] = static_cast<uint8_t>(f);
+    ++n;
+    tau += dt;
+    accumulated += dt;
+  }
+  if (max_v) *max_v = mv;
+  if (max_a) *max_a = ma;
+  return n;
+}
+
+int mtgo_has_reference_rpoly(void) {
+#ifdef MTG_ORACLE_NO_RPOLY
+  return 0;
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+"""TEST INFRASTRUCTURE — ctypes front-end of the CPU oracle (oracle/liboracle.so).
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may import
+this module. It is the checker of the CUDA path, never part of it. See
+``oracle/oracle.h`` for what each function restates (reference file:line) and
+for which rows are pinned / unpinned.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so (and oracle/_ref when /root/reference exists)."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.mtgo_poly_evaluate.restype = C.c_double
+        _lib.mtgo_sampled_maximum_magnitude.restype = C.c_double
+        _lib.mtgo_cost_numeric.restype = C.c_double
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def has_reference_rpoly() -> bool:
+    return bool(lib().mtgo_has_reference_rpoly())
+
+
+# ----------------------------------------------------------------- matrices
+def base_coefficients() -> np.ndarray:
+    out = np.empty((22, 22))
+    lib().mtgo_base_coefficients(_d(out))
+    return out
+
+
+def quadratic_cost_jacobian(N: int, derivative: int, t: float) -> np.ndarray:
+    Q = np.empty((N, N))
+    lib().mtgo_quadratic_cost_jacobian(N, derivative, C.c_double(t), _d(Q))
+    return Q
+
+
+def setup_mapping_matrix(N: int, t: float) -> np.ndarray:
+    A = np.empty((N, N))
+    lib().mtgo_setup_mapping_matrix(N, C.c_double(t), _d(A))
+    return A
+
+
+def invert_mapping_matrix(A: np.ndarray) -> np.ndarray:
+    A = _f64(A)
+    out = np.empty_like(A)
+    lib().mtgo_invert_mapping_matrix(A.shape[0], _d(A), _d(out))
+    return out
+
+
+def general_inverse(M: np.ndarray) -> np.ndarray:
+    M = _f64(M)
+    out = np.empty_like(M)
+    rc = lib().mtgo_general_inverse(M.shape[0], _d(M), _d(out))
+    if rc:
+        raise ValueError("singular")
+    return out
+
+
+# --------------------------------------------------------------- generators
+def create_random_vertices(maximum_derivative: int, n_segments: int, pos_min, pos_max,
+                           seed: int, N: int = 10):
+    """VTX_C:27-82. Returns (mask[(K+1),N/2] uint8, values[(K+1),N/2,D])."""
+    pos_min = _f64(np.atleast_1d(pos_min))
+    pos_max = _f64(np.atleast_1d(pos_max))
+    D = pos_min.size
+    h = N // 2
+    mask = np.zeros((n_segments + 1, h), dtype=np.uint8)
+    values = np.zeros((n_segments + 1, h, D))
+    rc = lib().mtgo_create_random_vertices(maximum_derivative, n_segments, D, _d(pos_min),
+                                           _d(pos_max), C.c_uint64(seed), h,
+                                           mask.ctypes.data_as(_u8p), _d(values))
+    if rc < 0:
+        raise ValueError("createRandomVertices: invalid arguments")
+    return mask, values
+
+
+def estimate_segment_times_nfabian(positions, v_max, a_max, magic=6.5) -> np.ndarray:
+    positions = _f64(positions)
+    K = positions.shape[0] - 1
+    D = positions.shape[1]
+    out = np.empty(K)
+    lib().mtgo_estimate_segment_times_nfabian(K, D, _d(positions), C.c_double(v_max),
+                                              C.c_double(a_max), C.c_double(magic), _d(out))
+    return out
+
+
+def estimate_segment_times_velocity_ramp(positions, v_max, a_max) -> np.ndarray:
+    positions = _f64(positions)
+    K = positions.shape[0] - 1
+    D = positions.shape[1]
+    out = np.empty(K)
+    lib().mtgo_estimate_segment_times_velocity_ramp(K, D, _d(positions), C.c_double(v_max),
+                                                    C.c_double(a_max), _d(out))
+    return out
+
+
+# -------------------------------------------------------------------- solve
+class Solution:
+    __slots__ = ("coeffs", "cost", "n_all", "n_fixed", "n_free", "d_f", "d_p", "R", "col_of_row")
+
+
+def solve(N, derivative, times, mask, values, solver: int = 0, want_R: bool = True) -> Solution:
+    """P1..P8: mask[(K+1),N/2], values[(K+1),N/2,D], times[K] -> Solution."""
+    times = _f64(times)
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    values = _f64(values)
+    K = times.size
+    h = N // 2
+    D = values.shape[2]
+    assert mask.shape == (K + 1, h) and values.shape == (K + 1, h, D)
+    n_all = K * N
+    coeffs = np.zeros((K, D, N))
+    cost = C.c_double(0.0)
+    counts = (C.c_int * 3)()
+    d_f = np.zeros((D, n_all))
+    d_p = np.zeros((D, n_all))
+    R = np.zeros((n_all, n_all)) if want_R else None
+    col = np.zeros(n_all, dtype=np.int32)
+    rc = lib().mtgo_solve(N, D, K, derivative, _d(times), mask.ctypes.data_as(_u8p), _d(values),
+                          solver, _d(coeffs), C.byref(cost), counts, _d(d_f), _d(d_p),
+                          _d(R) if want_R else None, col.ctypes.data_as(_ip))
+    if rc:
+        raise ValueError(f"oracle solve failed rc={rc}")
+    s = Solution()
+    s.coeffs, s.cost = coeffs, cost.value
+    s.n_all, s.n_fixed, s.n_free = counts[0], counts[1], counts[2]
+    s.d_f = d_f.reshape(-1)[: D * s.n_fixed].reshape(D, s.n_fixed).copy()
+    s.d_p = d_p.reshape(-1)[: D * s.n_free].reshape(D, s.n_free).copy()
+    n = s.n_fixed + s.n_free
+    s.R = R.reshape(-1)[: n * n].reshape(n, n).copy() if want_R else None
+    s.col_of_row = col[: s.n_all].copy()
+    return s
+
+
+def solve_canonical_batch(positions, times, N=10, derivative=4, solver=0, n_threads=1):
+    """positions [B,K+1,D], times [B,K] -> coeffs [B,K,D,N], cost [B]."""
+    positions = _f64(positions)
+    times = _f64(times)
+    B, Kp1, D = positions.shape
+    K = Kp1 - 1
+    coeffs = np.empty((B, K, D, N))
+    cost = np.empty(B)
+    rc = lib().mtgo_solve_canonical_batch(B, N, D, K, derivative, _d(positions), _d(times),
+                                          solver, n_threads, _d(coeffs), _d(cost))
+    if rc:
+        raise ValueError("oracle batch solve failed")
+    return coeffs, cost
+
+
+def canonical_mask_values(positions, N=10):
+    """mask/values of the createRandomVertices pattern for given positions [K+1,D]."""
+    positions = _f64(positions)
+    Kp1, D = positions.shape
+    h = N // 2
+    mask = np.zeros((Kp1, h), dtype=np.uint8)
+    values = np.zeros((Kp1, h, D))
+    mask[:, 0] = 1
+    values[:, 0, :] = positions
+    mask[0, :] = 1
+    mask[-1, :] = 1
+    return mask, values
+
+
+def coeffs_from_free_constraints(N, times, mask, values, d_p) -> np.ndarray:
+    times = _f64(times)
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    values = _f64(values)
+    d_p = _f64(d_p)
+    K = times.size
+    D = values.shape[2]
+    coeffs = np.zeros((K, D, N))
+    rc = lib().mtgo_coeffs_from_free_constraints(N, D, K, _d(times), mask.ctypes.data_as(_u8p),
+                                                 _d(values), _d(d_p), _d(coeffs))
+    if rc:
+        raise ValueError(rc)
+    return coeffs
+
+
+def cost_time_fd(N, derivative, times, mask, values, d_p, increment_time, central: bool):
+    """P9. Returns (J_nominal, J_plus[K], J_minus[K] or None, grad_d[K])."""
+    times = _f64(times)
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    values = _f64(values)
+    d_p = _f64(d_p)
+    K = times.size
+    D = values.shape[2]
+    J0 = C.c_double(0.0)
+    Jp = np.zeros(K)
+    Jm = np.zeros(K)
+    g = np.zeros(K)
+    rc = lib().mtgo_cost_time_fd(N, D, K, derivative, _d(times), mask.ctypes.data_as(_u8p),
+                                 _d(values), _d(d_p), C.c_double(increment_time),
+                                 1 if central else 0, C.byref(J0), _d(Jp), _d(Jm), _d(g))
+    if rc:
+        raise ValueError(rc)
+    return J0.value, Jp, (Jm if central else None), g
+
+
+# --------------------------------------------------------------- evaluation
+def poly_evaluate(c, t: float, derivative: int) -> float:
+    c = _f64(c)
+    return lib().mtgo_poly_evaluate(c.size, _d(c), C.c_double(t), derivative)
+
+
+def poly_derivative_coefficients(c, derivative: int) -> np.ndarray:
+    c = _f64(c)
+    out = np.empty_like(c)
+    lib().mtgo_poly_derivative_coefficients(c.size, _d(c), derivative, _d(out))
+    return out
+
+
+def convolve(data, kernel) -> np.ndarray:
+    data = _f64(data)
+    kernel = _f64(kernel)
+    out = np.empty(data.size + kernel.size - 1)
+    lib().mtgo_convolve(_d(data), data.size, _d(kernel), kernel.size, _d(out))
+    return out
+
+
+def traj_evaluate(coeffs, times, t: float, derivative: int):
+    coeffs = _f64(coeffs)
+    times = _f64(times)
+    K, D, N = coeffs.shape
+    out = np.zeros(D)
+    seg = lib().mtgo_traj_evaluate(N, D, K, _d(coeffs), _d(times), C.c_double(t), derivative, _d(out))
+    return out, seg
+
+
+def traj_evaluate_range(coeffs, times, t_start, t_end, dt, derivative, cap=None):
+    """E4. Returns (samples[n,D], sampling_times[n], segment_idx[n]) or None if out of range."""
+    coeffs = _f64(coeffs)
+    times = _f64(times)
+    K, D, N = coeffs.shape
+    if cap is None:
+        # the reference's loop counter restarts at the start of the segment that
+        # holds t_start (TRAJ_C:110-114), so size by t_end, not t_end - t_start
+        cap = int(max(0.0, t_end) / dt) + 8
+    out = np.zeros((cap, D))
+    st = np.zeros(cap)
+    seg = np.zeros(cap, dtype=np.int32)
+    n = lib().mtgo_traj_evaluate_range(N, D, K, _d(coeffs), _d(times), C.c_double(t_start),
+                                       C.c_double(t_end), C.c_double(dt), derivative, cap,
+                                       _d(out), _d(st), seg.ctypes.data_as(_i32p))
+    if n < 0:
+        return None
+    return out[:n].copy(), st[:n].copy(), seg[:n].copy()
+
+
+# ------------------------------------------------------------------ extrema
+def find_roots_jenkins_traub(coeffs_increasing):
+    c = _f64(coeffs_increasing)
+    re = np.zeros(128)
+    im = np.zeros(128)
+    n = C.c_int(0)
+    ok = lib().mtgo_find_roots_jenkins_traub(_d(c), c.size, _d(re), _d(im), C.byref(n))
+    if ok == -2:
+        raise RuntimeError("oracle built without the reference rpoly (oracle/_ref missing)")
+    return bool(ok), re[: n.value] + 1j * im[: n.value]
+
+
+def poly_compute_min_max(c, t_start, t_end, derivative):
+    c = _f64(c)
+    v = [C.c_double(0.0) for _ in range(4)]
+    rc = lib().mtgo_poly_compute_min_max(c.size, _d(c), C.c_double(t_start), C.c_double(t_end),
+                                         derivative, *[C.byref(x) for x in v])
+    if rc:
+        return None
+    return (v[0].value, v[1].value), (v[2].value, v[3].value)
+
+
+def segment_candidate_times(seg_coeffs, derivative, t_start, t_end, dims=None):
+    seg = _f64(seg_coeffs)
+    D, N = seg.shape
+    dims = np.arange(D, dtype=np.int32) if dims is None else np.ascontiguousarray(dims, dtype=np.int32)
+    cand = np.zeros(128)
+    n = lib().mtgo_segment_candidate_times(N, D, _d(seg), derivative, C.c_double(t_start),
+                                           C.c_double(t_end), dims.ctypes.data_as(_ip), dims.size,
+                                           _d(cand), 128)
+    return None if n < 0 else cand[:n].copy()
+
+
+def traj_min_max_magnitude(coeffs, times, derivative, dims=None):
+    coeffs = _f64(coeffs)
+    times = _f64(times)
+    K, D, N = coeffs.shape
+    dims = np.arange(D, dtype=np.int32) if dims is None else np.ascontiguousarray(dims, dtype=np.int32)
+    mt, mv, Mt, Mv = (C.c_double(0.0) for _ in range(4))
+    ms, Ms = C.c_int(0), C.c_int(0)
+    rc = lib().mtgo_traj_min_max_magnitude(N, D, K, _d(coeffs), _d(times), derivative,
+                                           dims.ctypes.data_as(_ip), dims.size, C.byref(mt),
+                                           C.byref(mv), C.byref(ms), C.byref(Mt), C.byref(Mv),
+                                           C.byref(Ms))
+    if rc:
+        return None
+    return (mt.value, mv.value, ms.value), (Mt.value, Mv.value, Ms.value)
+
+
+def opt_max_magnitude(coeffs, times, derivative):
+    coeffs = _f64(coeffs)
+    times = _f64(times)
+    K, D, N = coeffs.shape
+    t, v, s = C.c_double(0.0), C.c_double(0.0), C.c_int(0)
+    rc = lib().mtgo_opt_max_magnitude(N, D, K, _d(coeffs), _d(times), derivative, C.byref(t),
+                                      C.byref(v), C.byref(s))
+    if rc:
+        return None
+    return t.value, v.value, s.value
+
+
+def sampled_maximum_magnitude(coeffs, times, derivative, dt=0.01) -> float:
+    coeffs = _f64(coeffs)
+    times = _f64(times)
+    K, D, N = coeffs.shape
+    return lib().mtgo_sampled_maximum_magnitude(N, D, K, _d(coeffs), _d(times), derivative,
+                                                C.c_double(dt))
+
+
+def cost_numeric(coeffs, times, derivative, dt=0.001) -> float:
+    coeffs = _f64(coeffs)
+    times = _f64(times)
+    K, D, N = coeffs.shape
+    return lib().mtgo_cost_numeric(N, D, K, _d(coeffs), _d(times), derivative, C.c_double(dt))
+
+
+# --------------------------------------------------------------------- tube
+def tube_geometry(positions, radii) -> np.ndarray:
+    positions = _f64(positions)
+    radii = _f64(radii)
+    K = positions.shape[0] - 1
+    geom = np.zeros((K, 24))
+    lib().mtgo_tube_geometry(K, _d(positions), _d(radii), _d(geom))
+    return geom
+
+
+def tube_flags(geom_seg, vertex_end, x) -> int:
+    g = _f64(geom_seg)
+    return lib().mtgo_tube_flags(_d(g), _d(_f64(vertex_end)), _d(_f64(x)))
+
+
+def feasibility_sweep(coeffs, times, positions, radii, v_max, a_max, t_start, t_end, dt, cap=None):
+    coeffs = _f64(coeffs)
+    times = _f64(times)
+    positions = _f64(positions)
+    K, D, N = coeffs.shape
+    assert D == 3
+    if cap is None:
+        cap = int(max(0.0, t_end) / dt) + 8
+    pos = np.zeros((cap, 3))
+    flags = np.zeros(cap, dtype=np.uint8)
+    mv, ma = C.c_double(0.0), C.c_double(0.0)
+    rad = _f64(radii) if radii is not None else None
+    n = lib().mtgo_feasibility_sweep(N, K, _d(coeffs), _d(times), _d(positions),
+                                     _d(rad) if rad is not None else None, C.c_double(v_max),
+                                     C.c_double(a_max), C.c_double(t_start), C.c_double(t_end),
+                                     C.c_double(dt), cap, _d(pos), flags.ctypes.data_as(_u8p),
+                                     C.byref(mv), C.byref(ma))
+    if n < 0:
+        return None
+    return pos[:n].copy(), flags[:n].copy(), mv.value, ma.value

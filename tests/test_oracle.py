@@ -1,0 +1,498 @@
+"""CPU tests that PIN THE ORACLE (oracle/) against the reference's own golden
+vectors, known-answer tests and invariants, against the
+unmodified reference Jenkins-Traub build (oracle/_ref) and against a 60-digit
+mpmath solve. These restate test/test_polynomial_optimization.cpp and
+test/test_polynomial.cpp of the reference (cited per test).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE_PARAMS, make_reference_problem, normwise_error
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+N = 10
+
+SMALL = [n for n, p in REFERENCE_PARAMS.items() if p[2] <= 10]
+
+
+def seg_eval(po, coeffs, seg, t, derivative):
+    return np.array([po.poly_evaluate(coeffs[seg, d], t, derivative) for d in range(coeffs.shape[1])])
+
+
+def check_path(po, prob, coeffs, tol=1e-6):
+    """checkPath, TEST_OPT:113-195."""
+    mask, values, times = prob["mask"], prob["values"], prob["times"]
+    K = len(times)
+    for i in range(K):
+        for k in range(5):
+            if mask[i, k]:
+                assert np.abs(seg_eval(po, coeffs, i, 0.0, k) - values[i, k]).max() < tol
+            if mask[i + 1, k]:
+                assert np.abs(seg_eval(po, coeffs, i, times[i], k) - values[i + 1, k]).max() < tol
+        if i > 0:
+            for k in range(N // 2):
+                a = seg_eval(po, coeffs, i - 1, times[i - 1], k)
+                b = seg_eval(po, coeffs, i, 0.0, k)
+                assert np.abs(a - b).max() < tol
+
+
+# ----------------------------------------------------------------- P2..P5
+def test_base_coefficients_are_falling_factorials(po):
+    B = po.base_coefficients()
+    import math
+
+    for n in range(22):
+        for i in range(22):
+            want = math.factorial(i) // math.factorial(i - n) if i >= n else 0
+            assert B[n, i] == float(want)
+
+
+def test_a_matrix_inversion(po):
+    """AMatrixInversion TEST_OPT:695-705: Schur inverse == dense inverse, 1e-10, T=1..60."""
+    for t in range(1, 61):
+        A = po.setup_mapping_matrix(N, float(t))
+        Ai = po.invert_mapping_matrix(A)
+        Ai_dense = po.general_inverse(A)
+        assert np.abs(Ai - Ai_dense).max() < 1.0e-10, t
+        # LAPACK pivots differently; entries reach 1e2..1e3, so compare relatively
+        assert np.abs(Ai - np.linalg.inv(A)).max() < 1.0e-11 * np.abs(Ai).max(), t
+
+
+def test_mapping_matrix_rows_are_derivative_bases(po):
+    T = 2.5
+    A = po.setup_mapping_matrix(N, T)
+    c = np.random.RandomState(0).randn(N)
+    for k in range(5):
+        assert A[k] @ c == pytest.approx(po.poly_evaluate(c, 0.0, k), rel=1e-14, abs=1e-14)
+        assert A[5 + k] @ c == pytest.approx(po.poly_evaluate(c, T, k), rel=1e-12)
+
+
+def test_cost_jacobian_matches_numeric_integral(po):
+    """Q is twice the Hessian of the integral of the squared derivative (LIN_I:557-573)."""
+    T, d = 1.7, 4
+    Q = po.quadratic_cost_jacobian(N, d, T)
+    c = np.random.RandomState(1).randn(N)
+    ts = np.linspace(0, T, 20001)
+    vals = np.array([po.poly_evaluate(c, t, d) for t in ts]) ** 2
+    integral = np.trapezoid(vals, ts)
+    assert 0.5 * c @ Q @ c == pytest.approx(integral, rel=1e-6)
+
+
+# ------------------------------------------------------------ golden vector
+def test_two_vertices_setup_golden(po):
+    """TwoVerticesSetup TEST_OPT:707-751, Matlab coefficients :741-744."""
+    g = np.load(os.path.join(GOLD, "two_vertices_setup.npz"))
+    s = po.solve(int(g["N"]), int(g["derivative"]), g["times"], g["mask"], g["values"])
+    assert (s.n_all, s.n_fixed, s.n_free) == (10, 10, 0)
+    # the Matlab literals carry ~4e-15 (low orders) .. 1.5e-14 (c5) of noise
+    assert np.abs(s.coeffs[0, 0] - g["matlab_coeffs"]).max() < 5e-14
+    exact = np.array([0, 0, 0, 0, 0, 0.2016, -0.1344, 0.03456, -0.004032, 0.0001792])
+    assert np.abs(s.coeffs[0, 0] - exact).max() < 5e-14   # cond(A(5)) ~ 1e8 noise of the reference order
+    prob = dict(mask=g["mask"], values=g["values"], times=g["times"])
+    check_path(po, prob, s.coeffs)
+
+
+def test_convolution_golden(po):
+    """PolynomialTest.Convolution TEST_POLY:68-79."""
+    g = np.load(os.path.join(GOLD, "convolution.npz"))
+    assert np.array_equal(po.convolve(g["data"], g["kernel"]), g["expected"])
+    rng = np.random.RandomState(3)
+    for _ in range(20):
+        a, b = rng.randn(rng.randint(1, 12)), rng.randn(rng.randint(1, 12))
+        assert np.allclose(po.convolve(a, b), np.convolve(a, b), rtol=1e-13, atol=1e-13)
+
+
+# ------------------------------------------------------------- generators
+@pytest.mark.parametrize("name", list(REFERENCE_PARAMS))
+def test_vertex_generation(po, name):
+    """VertexGeneration TEST_OPT:249-268."""
+    D, der, K, seed, box, v, a = REFERENCE_PARAMS[name]
+    mask, values = po.create_random_vertices(4, K, [-box] * D, [box] * D, seed)
+    assert mask[0].sum() == 5 and mask[-1].sum() == 5
+    assert np.all(mask[:, 0] == 1)
+    assert np.all(mask[1:-1, 1:] == 0)
+    assert np.all(values[:, 0, :] <= box) and np.all(values[:, 0, :] >= -box)
+    dist = np.linalg.norm(np.diff(values[:, 0, :], axis=0), axis=1)
+    assert np.all(dist > 0.2)
+
+
+def test_mt19937_generator_matches_numpy_stream(po):
+    """createRandomVertices draws generate_canonical<double,53>(mt19937): two 32-bit
+    words per double, low word first (libstdc++). numpy's MT19937 yields the same
+    raw 32-bit stream for the same integer seed."""
+    seed, D, K = 105, 3, 10
+    # std::mt19937(seed) uses the Knuth-style init_genrand, as numpy's legacy seeding does
+    rs = np.random.RandomState(seed)
+    raw = rs.randint(0, 2 ** 32, size=2 * D * (K + 1) + 64, dtype=np.uint64)
+    mask, values = po.create_random_vertices(4, K, [-10.0] * D, [10.0] * D, seed)
+    got = values[:, 0, :].reshape(-1)
+    # no rejection happens for seed 105 (checked by the distance assertion below)
+    want = []
+    for i in range(D * (K + 1)):
+        lo, hi = float(raw[2 * i]), float(raw[2 * i + 1])
+        canon = (lo + hi * 4294967296.0) / 18446744073709551616.0
+        want.append(canon * 20.0 + -10.0)
+    assert np.array_equal(got, np.array(want))
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_time_allocation(po, name):
+    """TimeAllocation TEST_OPT:572-613 (times in (0,1e5); resulting v/a < 2.5x)."""
+    prob = make_reference_problem(name)
+    pos = prob["values"][:, 0, :]
+    ramp = po.estimate_segment_times_velocity_ramp(pos, prob["v_max"], prob["a_max"])
+    nf = po.estimate_segment_times_nfabian(pos, prob["v_max"], prob["a_max"])
+    assert ramp.shape == nf.shape == (prob["K"],)
+    assert np.all(ramp > 0) and np.all(nf > 0) and np.all(ramp < 1e5) and np.all(nf < 1e5)
+    if not po.has_reference_rpoly():
+        pytest.skip("oracle/_ref missing")
+    for times in (ramp, nf):
+        s = po.solve(N, prob["derivative"], times, prob["mask"], prob["values"])
+        v_ext = po.traj_min_max_magnitude(s.coeffs, times, 1)[1]
+        a_ext = po.traj_min_max_magnitude(s.coeffs, times, 2)[1]
+        assert v_ext[1] < prob["v_max"] * 2.5
+        assert a_ext[1] < prob["a_max"] * 2.5
+
+
+# -------------------------------------------------------------------- solve
+@pytest.mark.parametrize("name", SMALL)
+def test_unconstrained_linear(po, name):
+    """UnconstrainedLinearEstimateSegmentTimes TEST_OPT:270-305."""
+    prob = make_reference_problem(name)
+    s = po.solve(N, prob["derivative"], prob["times"], prob["mask"], prob["values"])
+    check_path(po, prob, s.coeffs)
+    v = po.sampled_maximum_magnitude(s.coeffs, prob["times"], 1)
+    a = po.sampled_maximum_magnitude(s.coeffs, prob["times"], 2)
+    assert v < prob["v_max"] * 2.5 and a < prob["a_max"] * 2.5
+    cost_numeric = po.cost_numeric(s.coeffs, prob["times"], prob["derivative"], 0.001)
+    assert abs(cost_numeric - s.cost) <= cost_numeric * 0.1
+    # the Riemann sum is in fact much closer than the reference's 10 %
+    assert abs(cost_numeric - s.cost) <= cost_numeric * 5e-3
+
+
+def test_counts_of_config_c(po):
+    prob = make_reference_problem("segment_10_dim_3")
+    s = po.solve(N, 4, prob["times"], prob["mask"], prob["values"])
+    assert (s.n_all, s.n_fixed, s.n_free) == (100, 19, 36)
+    # appendix A index algebra of SURVEY.md
+    col = s.col_of_row
+    K = 10
+    for i in range(K):
+        for k in range(5):
+            start = col[i * N + k]
+            end = col[i * N + 5 + k]
+            if i == 0:
+                assert start == k
+            elif k == 0:
+                assert start == 4 + i
+            else:
+                assert start == 19 + 4 * (i - 1) + (k - 1)
+            if i == K - 1:
+                assert end == K + 4 + k
+            elif k == 0:
+                assert end == 4 + (i + 1)
+            else:
+                assert end == 19 + 4 * i + (k - 1)
+    Rpp = s.R[19:, 19:]
+    nz = np.abs(Rpp) > 0
+    assert nz.sum() == 400
+    r, c = np.nonzero(nz)
+    assert np.abs(r - c).max() == 7
+
+
+@pytest.mark.parametrize("name", ["segment_10_dim_3", "segment_10_dim_1", "jerk_5_dim_3",
+                                  "accel_5_dim_3", "segment_1_dim_3"])
+def test_oracle_vs_mpmath(po, name):
+    """The dense-QR restatement against the 60-digit solution of the same equations:
+    within 2e-10 (norm-wise per polynomial) for min-snap (the benchmarked config C);
+    the reference evaluation order itself (A^-1 with cond ~1e9, then A^-T Q A^-1) is
+    noisier for min-acceleration / min-jerk costs, up to ~1.5e-9, which the CUDA
+    path's 1e-9 parity budget cannot share: those cases are arbitrated by mpmath."""
+    from exact_solver import exact_solve
+
+    prob = make_reference_problem(name)
+    s = po.solve(N, prob["derivative"], prob["times"], prob["mask"], prob["values"])
+    ce, cost_e, dp_e = exact_solve(N, prob["derivative"], prob["times"], prob["mask"], prob["values"])
+    tol = 2e-10 if prob["derivative"] == 4 else 5e-9
+    assert normwise_error(s.coeffs, ce) < tol
+    assert abs(s.cost - cost_e) <= tol * abs(cost_e)
+    if s.n_free:
+        assert np.abs(s.d_p - dp_e).max() <= tol * np.abs(dp_e).max()
+
+
+def test_golden_fixture_is_reproduced(po):
+    """The committed fixtures (tests/golden/make_golden.py) replay bit-exactly."""
+    g = np.load(os.path.join(GOLD, "reference_params.npz"))
+    for name in g["names"]:
+        s = po.solve(N, int(g[f"{name}/derivative"]), g[f"{name}/times"], g[f"{name}/mask"],
+                     g[f"{name}/values"])
+        assert np.array_equal(s.coeffs, g[f"{name}/oracle_coeffs"]), name
+        assert s.cost == float(g[f"{name}/oracle_cost"])
+        tol = 5e-10 if int(g[f"{name}/derivative"]) == 4 else 5e-9
+        assert normwise_error(s.coeffs, g[f"{name}/exact_coeffs"]) < tol, name
+
+
+def test_constraint_packing(po):
+    """ConstraintPacking TEST_OPT:511-570: [d_f;d_p] -> p = A^-1 M d -> A p -> M^+ -> [d_f;d_p]."""
+    D, K = 3, 10
+    for i in range(10):
+        mask, values = po.create_random_vertices(4, K, [-50.0] * D, [50.0] * D, 12345 + i)
+        times = po.estimate_segment_times_nfabian(values[:, 0, :], 3.0, 5.0)
+        s = po.solve(N, 4, times, mask, values)
+        n = s.n_fixed + s.n_free
+        M = np.zeros((s.n_all, n))
+        M[np.arange(s.n_all), s.col_of_row] = 1.0
+        Mpinv = M.T / M.T.sum(axis=1, keepdims=True)          # LIN_I:546-555
+        A = np.zeros((K * N, K * N))
+        Ainv = np.zeros_like(A)
+        for j in range(K):
+            Aj = po.setup_mapping_matrix(N, times[j])
+            A[j * N:(j + 1) * N, j * N:(j + 1) * N] = Aj
+            Ainv[j * N:(j + 1) * N, j * N:(j + 1) * N] = po.invert_mapping_matrix(Aj)
+        for dim in range(D):
+            d_all = np.concatenate([s.d_f[dim], s.d_p[dim]])
+            p = Ainv @ M @ d_all
+            d_re = Mpinv @ (A @ p)
+            assert np.abs(d_all - d_re).max() < 1e-6
+            for j in range(K):
+                assert np.abs(s.coeffs[j, dim] - p[j * N:(j + 1) * N]).max() < 1e-6
+
+
+def test_set_free_constraints_round_trip(po):
+    prob = make_reference_problem("segment_10_dim_3")
+    s = po.solve(N, 4, prob["times"], prob["mask"], prob["values"])
+    c2 = po.coeffs_from_free_constraints(N, prob["times"], prob["mask"], prob["values"], s.d_p)
+    assert np.array_equal(c2, s.coeffs)
+
+
+def test_invalid_inputs_are_rejected(po):
+    prob = make_reference_problem("segment_1_dim_1")
+    with pytest.raises(ValueError):   # CHECK derivative <= N/2-1  (LIN_I:50-55)
+        po.solve(N, 5, prob["times"], prob["mask"], prob["values"])
+    with pytest.raises(ValueError):   # CHECK_GT(segment_time, 0)   (LIN_I:296)
+        po.solve(N, 4, [0.0], prob["mask"], prob["values"])
+
+
+# ------------------------------------------------------------------- P9
+def test_cost_time_fd(po):
+    prob = make_reference_problem("segment_10_dim_3")
+    s = po.solve(N, 4, prob["times"], prob["mask"], prob["values"])
+    J0, Jp, Jm, g = po.cost_time_fd(N, 4, prob["times"], prob["mask"], prob["values"], s.d_p, 1e-3, True)
+    # J_d has no 1/2 (NL_I:1585-1588) whereas computeCost has (LIN_I:129). The
+    # reference's d^T R d on its rounding-noisy R cancels ~2 digits: 1e-8 agreement.
+    assert J0 == pytest.approx(2.0 * s.cost, rel=5e-8)
+    assert np.allclose(g, (Jp - Jm) / 2e-3)
+    J0f, Jpf, _, gf = po.cost_time_fd(N, 4, prob["times"], prob["mask"], prob["values"], s.d_p, 1e-3, False)
+    assert J0f == J0 and np.array_equal(Jpf, Jp)
+    assert np.allclose(gf, (Jp - J0) / 1e-3)
+    # shortening any segment with d_p fixed raises the snap cost
+    assert np.all(g < 0)
+    # floor: a segment at <= 0.1 s is perturbed to exactly 0.1 on both sides -> zero central slope
+    t2 = prob["times"].copy()
+    t2[3] = 0.05
+    _, Jp2, Jm2, g2 = po.cost_time_fd(N, 4, t2, prob["mask"], prob["values"], s.d_p, 1e-3, True)
+    assert Jp2[3] == Jm2[3] and g2[3] == 0.0
+
+
+# -------------------------------------------------------------- evaluation
+def test_trajectory_evaluate_semantics(po):
+    """TRAJ_C:41-72: vertex time -> right-hand segment; t == max -> last segment; beyond -> zeros."""
+    prob = make_reference_problem("segment_10_dim_3")
+    s = po.solve(N, 4, prob["times"], prob["mask"], prob["values"])
+    T = prob["times"]
+    out, seg = po.traj_evaluate(s.coeffs, T, 0.0, 0)
+    assert seg == 0 and np.allclose(out, prob["values"][0, 0])
+    acc = 0.0
+    acc += T[0]
+    out, seg = po.traj_evaluate(s.coeffs, T, acc, 0)
+    assert seg == 1
+    assert np.allclose(out, prob["values"][1, 0], atol=1e-9)
+    total = 0.0
+    for t in T:
+        total += t
+    out, seg = po.traj_evaluate(s.coeffs, T, total, 0)
+    assert seg == 9 and np.allclose(out, prob["values"][10, 0], atol=1e-6)
+    out, seg = po.traj_evaluate(s.coeffs, T, total + 1.0, 0)
+    assert seg == -1 and np.all(out == 0.0)
+
+
+def test_evaluate_range_recurrence(po):
+    """TRAJ_C:74-134: serial acc += dt / tau += dt recurrence, strict '>' crossing."""
+    prob = make_reference_problem("segment_10_dim_3")
+    s = po.solve(N, 4, prob["times"], prob["mask"], prob["values"])
+    T = prob["times"]
+    total = 0.0
+    for t in T:
+        total += t
+    dt = total / 1000
+    samples, st, seg = po.traj_evaluate_range(s.coeffs, T, 0.0, total, dt, 0)
+    assert samples.shape[0] in (1000, 1001)
+    # python replay of the same recurrence
+    acc, i, tau, k = 0.0, 0, 0.0, 0
+    while acc < total:
+        if tau > T[i]:
+            tau = tau - T[i]
+            i += 1
+            if i >= len(T):
+                break
+            continue
+        assert st[k] == acc and seg[k] == i
+        want = seg_eval(po, s.coeffs, i, tau, 0)
+        assert np.array_equal(samples[k], want)
+        k += 1
+        tau += dt
+        acc += dt
+    assert k == samples.shape[0]
+    assert po.traj_evaluate_range(s.coeffs, T, total + 1.0, total + 2.0, dt, 0) is None
+    # empty range at a segment start
+    r = po.traj_evaluate_range(s.coeffs, T, 0.0, 0.0, dt, 0)
+    assert r[0].shape[0] == 0
+    # reference quirk (TRAJ_C:110-114): the loop counter restarts at the START of the
+    # segment holding t_start, so a start inside a segment yields samples for
+    # tau = t_start, t_start+dt, ... while the reported time runs from the segment
+    # start to t_end: the window is shifted, not clipped.
+    r = po.traj_evaluate_range(s.coeffs, T, 1.0, 1.0, dt, 0)
+    n_shift = r[0].shape[0]
+    assert n_shift > 0 and r[1][0] == 0.0 and np.all(r[1] < 1.0)
+    assert np.array_equal(r[0][0], seg_eval(po, s.coeffs, 0, 1.0, 0))
+
+
+# ------------------------------------------------------------------ extrema
+needs_ref = pytest.mark.skipif(
+    not os.path.exists(os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "librpoly_ref.so")),
+    reason="oracle/_ref/librpoly_ref.so missing")
+
+
+@needs_ref
+def test_rpoly_wrapper_matches_reference_wrapper(po):
+    """The restated wrapper (RPOLY_C:57-117) against the reference's own wrapper
+    compiled from /root/reference through the include shim."""
+    ref = C.CDLL(os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "librpoly_ref.so"))
+    rng = np.random.RandomState(7)
+    cases = [np.array([-6.0, 11.0, -6.0, 1.0]), np.zeros(5), np.array([3.0]),
+             np.array([1.0, 2.0, 0.0, 0.0]), np.array([0.0, 0.0, 1.0, -3.0, 2.0])]
+    cases += [rng.uniform(-100, 100, size=rng.randint(2, 19)) for _ in range(50)]
+    for c in cases:
+        c = np.ascontiguousarray(c)
+        re, im = np.zeros(128), np.zeros(128)
+        n = C.c_int(0)
+        ok_ref = ref.mtg_ref_find_roots_jenkins_traub(c.ctypes.data_as(C.POINTER(C.c_double)), c.size,
+                                                      re.ctypes.data_as(C.POINTER(C.c_double)),
+                                                      im.ctypes.data_as(C.POINTER(C.c_double)),
+                                                      C.byref(n))
+        ok, roots = po.find_roots_jenkins_traub(c)
+        assert ok == bool(ok_ref)
+        assert roots.size == n.value
+        assert np.array_equal(roots.real, re[: n.value]) and np.array_equal(roots.imag, im[: n.value])
+
+
+@needs_ref
+def test_rpoly_known_answers(po):
+    g = np.load(os.path.join(GOLD, "rpoly_kat.npz"))
+    for p, r in zip(g["polys"], g["roots"]):
+        n = int(np.max(np.nonzero(p)[0])) + 1
+        ok, roots = po.find_roots_jenkins_traub(p[:n])
+        want = r[~np.isnan(r.real)]
+        assert ok and np.array_equal(roots, want)
+        # and they are roots
+        for z in roots:
+            val = np.polyval(p[:n][::-1], z)
+            scale = np.polyval(np.abs(p[:n][::-1]), abs(z))
+            assert abs(val) <= 1e-9 * scale
+
+
+@needs_ref
+def test_find_min_max(po):
+    """PolynomialTest.FindMinMax TEST_POLY:81-137 (1e-3 sampling vs rpoly, tol 1e-2)."""
+    rng = np.random.RandomState(1234567)
+    for _ in range(60):
+        n = rng.randint(2, 13)
+        c = rng.uniform(-1, 1, size=n)
+        t0, t1 = sorted(rng.uniform(-2, 2, size=2))
+        for der in range(0, min(3, n - 1)):
+            r = po.poly_compute_min_max(c, t0, t1, der)
+            assert r is not None
+            (tmin, vmin), (tmax, vmax) = r
+            ts = np.append(np.arange(t0, t1, 1e-3), t1)
+            vals = np.array([po.poly_evaluate(c, t, der) for t in ts])
+            slope = np.abs([po.poly_evaluate(c, t, der + 1) for t in ts]).max()
+            assert vmin <= vals.min() + 1e-9 and vmax >= vals.max() - 1e-9
+            # sampling at 1e-3 can miss the extremum by at most ~slope * dt
+            assert vmin >= vals.min() - 2e-3 * slope - 1e-9
+            assert vmax <= vals.max() + 2e-3 * slope + 1e-9
+            assert t0 <= tmin <= t1 and t0 <= tmax <= t1
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["segment_10_dim_3", "segment_1_dim_3", "segment_10_dim_1",
+                                  "jerk_5_dim_3"])
+def test_extrema_of_magnitude(po, name):
+    """ExtremaOfMagnitude TEST_OPT:307-406: analytic max == sampled max (0.01), both
+    via computeMaximumOfMagnitude and Trajectory::computeMinMaxMagnitude."""
+    prob = make_reference_problem(name)
+    s = po.solve(N, prob["derivative"], prob["times"], prob["mask"], prob["values"])
+    for der in (1, 2):
+        ref = po.sampled_maximum_magnitude(s.coeffs, prob["times"], der)
+        t, v, seg = po.opt_max_magnitude(s.coeffs, prob["times"], der)
+        (_, _, _), (t2, v2, seg2) = po.traj_min_max_magnitude(s.coeffs, prob["times"], der)
+        assert v == pytest.approx(ref, abs=0.01)
+        assert v2 == pytest.approx(ref, abs=0.01)
+        assert v >= ref - 1e-12 and v2 >= ref - 1e-12
+        assert seg == seg2 and t == pytest.approx(t2, abs=1e-9)
+
+
+# --------------------------------------------------------------------- tube
+def test_tube_geometry_and_predicate(po):
+    """T1 (QC_I:357-474), parity unpinned by the reference: geometric self-checks."""
+    prob = make_reference_problem("segment_10_dim_3")
+    pos = prob["values"][:, 0, :]
+    K = 10
+    radii = np.full((K, 2), 0.15)
+    geom = po.tube_geometry(pos, radii)
+    for i in range(K):
+        n = (pos[i + 1] - pos[i]) / np.linalg.norm(pos[i + 1] - pos[i])
+        A = geom[i, :9].reshape(3, 3)
+        assert np.allclose(A, np.eye(3) - np.outer(n, n), atol=1e-6)
+        mid = 0.5 * (pos[i] + pos[i + 1])
+        assert po.tube_flags(geom[i], pos[i + 1], mid) & 1
+        # orthogonal offset inside / outside the radius
+        o = np.cross(n, [1.0, 0.3, -0.2])
+        o /= np.linalg.norm(o)
+        assert po.tube_flags(geom[i], pos[i + 1], mid + 0.149 * o) & 1
+        assert not (po.tube_flags(geom[i], pos[i + 1], mid + 0.151 * o) & 1)
+        # end caps: 0.15 beyond either vertex along the axis is in, 0.16 is out
+        assert po.tube_flags(geom[i], pos[i + 1], pos[i] - 0.149 * n) & 1
+        assert not (po.tube_flags(geom[i], pos[i + 1], pos[i] - 0.151 * n) & 1)
+        assert po.tube_flags(geom[i], pos[i + 1], pos[i + 1] + 0.149 * n) & 1
+        assert not (po.tube_flags(geom[i], pos[i + 1], pos[i + 1] + 0.151 * n) & 1)
+        assert po.tube_flags(geom[i], pos[i + 1], pos[i + 1] + 0.149 * o) & 2
+        assert not (po.tube_flags(geom[i], pos[i + 1], pos[i + 1] + 0.151 * o) & 2)
+
+
+def test_feasibility_sweep_consistency(po):
+    prob = make_reference_problem("segment_10_dim_3")
+    s = po.solve(N, 4, prob["times"], prob["mask"], prob["values"])
+    T = prob["times"]
+    pos = prob["values"][:, 0, :]
+    total = 0.0
+    for t in T:
+        total += t
+    dt = total / 1000
+    radii = np.full((10, 2), 0.15)
+    p, flags, mv, ma = po.feasibility_sweep(s.coeffs, T, pos, radii, 3.0, 5.0, 0.0, total, dt)
+    samples, st, seg = po.traj_evaluate_range(s.coeffs, T, 0.0, total, dt, 0)
+    assert np.array_equal(p, samples)
+    v, _, _ = po.traj_evaluate_range(s.coeffs, T, 0.0, total, dt, 1)
+    a, _, _ = po.traj_evaluate_range(s.coeffs, T, 0.0, total, dt, 2)
+    nv = np.sqrt((v ** 2).sum(axis=1))
+    na = np.sqrt((a ** 2).sum(axis=1))
+    assert mv == pytest.approx(nv.max(), rel=1e-15) and ma == pytest.approx(na.max(), rel=1e-15)
+    assert np.array_equal((flags & 1) != 0, nv <= 3.0)
+    assert np.array_equal((flags & 2) != 0, na <= 5.0)
+    # a min-snap trajectory through random waypoints leaves a 15 cm tube somewhere,
+    # but every sample exactly at a vertex start is inside
+    assert (flags[0] & 4) != 0
+    assert not np.all(flags & 4)
