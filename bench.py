@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the batched min-snap hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): a batch of 65,536 random 3-D, 10-segment,
+N = 10 min-snap problems per GPU (random vertices in a +-10 m box, Nfabian
+segment times v_max = 3, a_max = 5 — the reference's createRandomVertices +
+estimateSegmentTimes recipe, vectorised with numpy's RNG). One "step" = one
+mtg_solve_batch over that batch: Q/A/R construction, the R_pp solve, all 300
+coefficients and the cost of every trajectory.
+
+  value : trajectories solved / s, whole job, inputs resident in HBM (CUDA events)
+  e2e   : the same through the C ABI with PINNED HOST buffers (H2D + kernel + D2H
+          inside the timed region, staged by the library)
+  roofline    : algorithmic bytes (2,752 B / trajectory) / kernel time vs measured HBM peak
+  cpu_baseline: the oracle (a port of the reference algorithm; Eigen is not on the image)
+                on all host cores over a bounded sample
+`--impl reference` times that CPU port alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_SEG, DIM, NCOEF, DERIV = 10, 3, 10, 4
+BATCH_PER_GPU = 65536
+BYTES_IN = ((K_SEG + 1) * DIM + K_SEG) * 8          # 344
+BYTES_OUT = (K_SEG * DIM * NCOEF + 1) * 8           # 2,408
+BYTES_PER_TRAJ = BYTES_IN + BYTES_OUT               # 2,752  
+FLOP_PER_TRAJ_REF = 8.8e4                           # reference formulation
+N_ROTATE = 4                                        # rotating buffer sets: 4 x 180 MB > L2 (126 MB)
+METRIC = "min-snap trajectories solved/sec (N=10, 10 seg, 3D)"
+
+
+def make_workload(batch, seed):
+    """positions [K+1,D,B], times [K,B] (SoA, batch innermost), float64."""
+    rng = np.random.RandomState(seed)
+    pos = rng.uniform(-10.0, 10.0, size=(K_SEG + 1, DIM, batch))
+    # resample vertices closer than 0.2 m to their predecessor (vertex.cpp:65-72)
+    for v in range(1, K_SEG + 1):
+        while True:
+            d = np.sqrt(((pos[v] - pos[v - 1]) ** 2).sum(axis=0))
+            bad = d <= 0.2
+            if not bad.any():
+                break
+            pos[v][:, bad] = rng.uniform(-10.0, 10.0, size=(DIM, int(bad.sum())))
+    dist = np.sqrt((np.diff(pos, axis=0) ** 2).sum(axis=1))
+    v_max, a_max = 3.0, 5.0
+    times = dist / v_max * 2 * (1.0 + 6.5 * v_max / a_max * np.exp(-dist / v_max * 2))
+    return np.ascontiguousarray(pos), np.ascontiguousarray(times)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.06)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_port_rate(batch_sample, threads, reps=1, seed=12345):
+    """Oracle (port of the reference algorithm) solves/s over a bounded sample."""
+    from oracle import pyoracle as po
+
+    pos, times = make_workload(batch_sample, seed)
+    pos_aos = np.ascontiguousarray(np.moveaxis(pos, -1, 0))
+    times_aos = np.ascontiguousarray(np.moveaxis(times, -1, 0))
+    po.solve_canonical_batch(pos_aos[:256], times_aos[:256], n_threads=threads)  # warm
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        po.solve_canonical_batch(pos_aos, times_aos, N=NCOEF, derivative=DERIV, n_threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return batch_sample / best, best
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path. Eigen/glog are not on this image, so the
+    reference itself cannot be compiled; the oracle port of its algorithm is timed instead
+    (kind = "port"), single process, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 8192
+    from oracle import pyoracle as po
+
+    pos, times = make_workload(sample, 777)
+    pos_aos = np.ascontiguousarray(np.moveaxis(pos, -1, 0))
+    times_aos = np.ascontiguousarray(np.moveaxis(times, -1, 0))
+    for _ in range(args.warmup):
+        po.solve_canonical_batch(pos_aos, times_aos, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        po.solve_canonical_batch(pos_aos, times_aos, n_threads=threads)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "trajectories/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} solves per step x {args.steps} steps of the same workload, "
+                                   "OpenMP over the batch; oracle restatement of the reference algorithm "
+                                   "(dense QR for SparseQR), debug prints excluded; Eigen absent so the "
+                                   "reference itself cannot be built here"},
+        "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: batch of 65,536 random 3-D 10-segment min-snap (N=10) solves per GPU",
+            "batch_per_gpu": BATCH_PER_GPU, "segments": K_SEG, "dims": DIM, "N": NCOEF,
+            "derivative_to_optimize": DERIV, "global_batch": BATCH_PER_GPU * n_gpus,
+            "parallelism": f"batch sharded over {n_gpus} GPU(s), no data-path collective",
+            "l2": f"inputs+outputs rotate over {N_ROTATE} buffer sets of 180 MB (> 126 MB L2)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help=argparse.SUPPRESS)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import mav_tube_trajectory_generation_b200 as m
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = m.Context(local_rank)
+    B = args.batch
+
+    # ---- synthetic inputs: N_ROTATE distinct sets resident in HBM + one pinned host set
+    dev_in, dev_out = [], []
+    for i in range(N_ROTATE):
+        pos, times = make_workload(B, seed=1000 * rank + i)
+        dev_in.append((torch.from_numpy(pos).cuda(), torch.from_numpy(times).cuda()))
+        dev_out.append({"coeffs": torch.empty((K_SEG, DIM, NCOEF, B), dtype=torch.float64, device="cuda"),
+                        "cost": torch.empty((B,), dtype=torch.float64, device="cuda"),
+                        "status": torch.empty((B,), dtype=torch.int32, device="cuda")})
+    host_pos = torch.from_numpy(pos).pin_memory()
+    host_times = torch.from_numpy(times).pin_memory()
+    host_out = {"coeffs": torch.empty((K_SEG, DIM, NCOEF, B), dtype=torch.float64).pin_memory(),
+                "cost": torch.empty((B,), dtype=torch.float64).pin_memory(),
+                "status": torch.empty((B,), dtype=torch.int32).pin_memory()}
+
+    def step(i):
+        p, t = dev_in[i % N_ROTATE]
+        ctx.solve_batch(p, t, N=NCOEF, derivative=DERIV, out=dev_out[i % N_ROTATE])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput (CUDA events on the launching stream)
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    n0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    launches = ctx.launch_count - n0
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    bad = int(sum(int(o["status"].max().item()) for o in dev_out))
+    ms_t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ctx.solve_batch(host_pos, host_times, N=NCOEF, derivative=DERIV, out=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.solve_batch(host_pos, host_times, N=NCOEF, derivative=DERIV, out=host_out)
+        _ = float(host_out["cost"][0])      # the step's result is read on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(e2e_t.item())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        kernel_s = ms_per_step * 1e-3                 # one kernel launch per step
+        achieved = BYTES_PER_TRAJ * B / kernel_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world), "gpu_launches": int(launches),
+            "status_nonzero": bad,
+            "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": BYTES_IN * B,
+                    "d2h_bytes_per_step": (BYTES_OUT + 4) * B, "steps": e2e_steps,
+                    "note": "mtg_solve_batch(MTG_MEM_HOST) on pinned buffers: chunked H2D/kernel/D2H "
+                            "pipeline inside the call; wall clock between device synchronisations"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "solve_canonical_kernel<5,3>",
+                         "algorithmic_bytes_per_trajectory": BYTES_PER_TRAJ,
+                         "fp64_gflops_reference_formulation": FLOP_PER_TRAJ_REF * B / kernel_s / 1e9},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = 32768
+            rate, secs = cpu_port_rate(sample, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "trajectories/s", "cores": threads,
+                                    "kind": "port",
+                                    "sample": f"{sample} solves of the same workload in {secs:.2f} s wall, "
+                                              "OpenMP over the batch (oracle port, dense QR, prints excluded)"}
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,118 @@
+/* mtg_cuda.h — C ABI of libmtg_cuda.so, the B200 (sm_100a) batched implementation
+ * of the unconstrained polynomial-trajectory hot path of
+ * NilsFunk/mav_tube_trajectory_generation.
+ *
+ * The reference has NO plugin/FFI boundary: its boundary is the C++ class API
+ * (Vertex / Polynomial / Segment / Trajectory / PolynomialOptimization<N>).
+ * include/mav_tube_trajectory_generation/*.h in this repo re-creates that class
+ * API on top of these entry points (B = 1 per object); batched callers (bench,
+ * sweeps) call them directly. Every entry point cites the reference interface
+ * it replaces (paths relative to the reference root;
+ * LIN_I = include/mav_tube_trajectory_generation/impl/polynomial_optimization_linear_impl.h).
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no C++/torch types. `stream` is a cudaStream_t
+ *    passed as void* (NULL = default stream).
+ *  - return value: 0 = MTG_OK, negative = call-level error (bad argument, CUDA
+ *    error; text via mtg_last_error). Reference programmer-error CHECKs
+ *    (process abort there) become negative return codes here.
+ *  - per-item problems never abort: they set bits in status[b] (MTG_ST_*).
+ *  - there is NO CPU fallback: without a CUDA device mtg_create fails.
+ *  - memory: desc.memory says whether ALL data pointers of the call are device
+ *    pointers (MTG_MEM_DEVICE; nothing is copied, the call only enqueues work
+ *    on `stream`) or host pointers (MTG_MEM_HOST; the library stages H2D/D2H
+ *    itself in pipelined chunks and returns when the outputs are in place).
+ *  - layout: struct-of-arrays with the BATCH INNERMOST, leading dimension
+ *    desc.B. A tensor written below as [K][D][N][B] has element (k,d,n,b) at
+ *    ((k*D + d)*N + n)*B + b. With B = 1 this degenerates to the reference's
+ *    natural per-object order.
+ */
+#ifndef MTG_CUDA_H_
+#define MTG_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTG_ABI_VERSION 1
+
+#define MTG_OK 0
+#define MTG_ERR_INVALID_ARGUMENT (-1) /* reference: glog CHECK abort            */
+#define MTG_ERR_CUDA (-2)             /* CUDA runtime error, see mtg_last_error  */
+#define MTG_ERR_NO_DEVICE (-3)        /* no CUDA device: the library has no CPU path */
+#define MTG_ERR_UNSUPPORTED (-4)
+#define MTG_ERR_NCCL (-5)
+
+/* per-item status bits */
+#define MTG_ST_OK 0u
+#define MTG_ST_BAD_TIME 1u      /* a segment time <= 0 or non-finite (LIN_I:296 CHECK_GT) */
+#define MTG_ST_NOT_SPD 2u       /* R_pp pivot <= 0: ill-scaled problem                      */
+#define MTG_ST_OUT_OF_RANGE 4u  /* evaluation time outside the trajectory (TRAJ_C:58-61,104-107) */
+#define MTG_ST_TRUNCATED 8u     /* more samples than max_samples                            */
+#define MTG_ST_NO_CONVERGENCE 16u /* root iteration hit its cap (RPOLY_C:372-377)          */
+
+#define MTG_MEM_DEVICE 0
+#define MTG_MEM_HOST 1
+
+#define MTG_MAX_N 12 /* Polynomial::kMaxN, polynomial.h:45 */
+
+typedef struct mtg_ctx mtg_ctx;
+
+/* Shape of one batch. Mirrors the reference's "config" (ctor/setup arguments):
+ * PolynomialOptimization<N>(dimension) + setupFromVertices(vertices, times,
+ * derivative_to_optimize)  [polynomial_optimization_linear.h:57,67-69]. */
+typedef struct mtg_problem_desc {
+  int32_t B;                      /* trajectories in the batch (leading dimension) */
+  int32_t K;                      /* segments per trajectory (vertices = K+1)      */
+  int32_t D;                      /* dimensions (1..4)                             */
+  int32_t N;                      /* coefficients per polynomial, even, <= 12      */
+  int32_t derivative_to_optimize; /* 0 .. N/2-1                                    */
+  int32_t memory;                 /* MTG_MEM_DEVICE / MTG_MEM_HOST                 */
+} mtg_problem_desc;
+
+/* ------------------------------------------------------------------ context */
+int mtg_abi_version(void);
+int mtg_create(int device, mtg_ctx** ctx);
+void mtg_destroy(mtg_ctx* ctx);
+const char* mtg_last_error(const mtg_ctx* ctx);
+/* number of kernels this context has launched so far (bench "gpu_launches") */
+uint64_t mtg_launch_count(const mtg_ctx* ctx);
+int mtg_sync(mtg_ctx* ctx, void* stream);
+
+/* Constant tables of (N, derivative): H1 = A(1)^-T Q(1) A(1)^-1 and A(1)^-1,
+ * row-major N x N, computed in binary128 on the host and rounded once. These
+ * replace computeQuadraticCostJacobian / setupMappingMatrix /
+ * invertMappingMatrix [LIN_I:557-573, 101-111, 132-169] through
+ * H(T) = T^(1-2d) S H1 S,  A(T)^-1 = diag(T^-j) A(1)^-1 S,  S = diag(T^alpha). */
+int mtg_get_tables(int N, int derivative, double* H1, double* Ainv1);
+
+/* ------------------------------------------------------ P1..P8: linear solve
+ * Replaces, per trajectory: setupFromVertices + updateSegmentTimes +
+ * setupConstraintReorderingMatrix + constructR + solveLinear +
+ * updateSegmentsFromCompactConstraints + computeCost
+ * [LIN_I:46-99, 277-304, 171-252, 306-335, 337-379, 254-275, 113-130]
+ * for the constraint pattern createRandomVertices produces [src/vertex.cpp:27-82]:
+ * first and last vertex fix derivatives 0..N/2-1, interior vertices fix position.
+ *
+ *  positions        [K+1][D][B]      in
+ *  end_derivatives  [2][N/2-1][D][B] in, derivatives 1..N/2-1 at the first ([0]) and
+ *                                    last ([1]) vertex; NULL = all zero (makeStartOrEnd,
+ *                                    src/vertex.cpp:147-153)
+ *  seg_times        [K][B]           in
+ *  coeffs           [K][D][N][B]     out, increasing powers (polynomial.h:35-36)
+ *  cost             [B]              out or NULL, computeCost() = 0.5 sum c^T Q c
+ *  free_constraints [K-1][N/2-1][D][B] out or NULL, d_p (getFreeConstraints order:
+ *                                    vertex-major, derivative 1.. within a vertex)
+ *  status           [B] uint32       out or NULL                                   */
+int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc,
+                    const double* positions, const double* end_derivatives,
+                    const double* seg_times, double* coeffs, double* cost,
+                    double* free_constraints, uint32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTG_CUDA_H_ */

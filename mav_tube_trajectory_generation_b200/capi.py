@@ -1,0 +1,183 @@
+"""ctypes binding of libmtg_cuda.so (include/mtg_cuda.h) — the only way Python
+reaches the product path. There is no CPU fallback: if the library is missing or
+no CUDA device is present this module raises.
+
+Tensors are struct-of-arrays with the batch innermost (see mtg_cuda.h). A
+``torch`` CUDA tensor selects MTG_MEM_DEVICE (nothing is copied; work is
+enqueued on torch's current stream); a numpy array or CPU torch tensor selects
+MTG_MEM_HOST (the library stages H2D/D2H itself).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+MTG_MEM_DEVICE = 0
+MTG_MEM_HOST = 1
+
+ST_BAD_TIME = 1
+ST_NOT_SPD = 2
+ST_OUT_OF_RANGE = 4
+ST_TRUNCATED = 8
+ST_NO_CONVERGENCE = 16
+
+
+class MtgError(RuntimeError):
+    pass
+
+
+class ProblemDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("D", C.c_int32), ("N", C.c_int32),
+                ("derivative_to_optimize", C.c_int32), ("memory", C.c_int32)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.LIB):
+        raise MtgError(f"{_build.LIB} is missing: run __graft_entry__.build() "
+                       "(python -m mav_tube_trajectory_generation_b200._build). "
+                       "There is no CPU fallback.")
+    lib = C.CDLL(_build.LIB)
+    vp, dp, u32p = C.c_void_p, C.c_void_p, C.c_void_p
+    lib.mtg_abi_version.restype = C.c_int
+    lib.mtg_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.mtg_destroy.argtypes = [vp]
+    lib.mtg_destroy.restype = None
+    lib.mtg_last_error.argtypes = [vp]
+    lib.mtg_last_error.restype = C.c_char_p
+    lib.mtg_launch_count.argtypes = [vp]
+    lib.mtg_launch_count.restype = C.c_uint64
+    lib.mtg_sync.argtypes = [vp, vp]
+    lib.mtg_get_tables.argtypes = [C.c_int, C.c_int, dp, dp]
+    lib.mtg_solve_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, u32p, vp]
+    _lib = lib
+    return lib
+
+
+def get_tables(N: int, derivative: int):
+    """H1 and A(1)^-1 (host computation, no device needed)."""
+    lib = load()
+    H1 = np.zeros((N, N))
+    Ai = np.zeros((N, N))
+    rc = lib.mtg_get_tables(N, derivative, H1.ctypes.data, Ai.ctypes.data)
+    if rc:
+        raise MtgError("invalid (N, derivative)")
+    return H1, Ai
+
+
+def _is_torch(x) -> bool:
+    return hasattr(x, "data_ptr")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+class Context:
+    """One mtg_ctx on one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        h = C.c_void_p()
+        rc = self._lib.mtg_create(device, C.byref(h))
+        if rc == -3:
+            raise MtgError("no CUDA device: libmtg_cuda.so has no CPU path")
+        if rc:
+            raise MtgError(f"mtg_create failed rc={rc}")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mtg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ utils
+    def _check(self, rc: int, what: str):
+        if rc:
+            raise MtgError(f"{what} failed rc={rc}: {self._lib.mtg_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mtg_launch_count(self._h))
+
+    def _mode(self, x) -> int:
+        return MTG_MEM_DEVICE if (_is_torch(x) and x.is_cuda) else MTG_MEM_HOST
+
+    def _stream(self, mode, stream):
+        if stream is not None:
+            return C.c_void_p(int(stream))
+        if mode == MTG_MEM_DEVICE:
+            import torch
+
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(0)
+
+    def _empty(self, like, shape, dtype="f8"):
+        if _is_torch(like):
+            import torch
+
+            tdt = {"f8": torch.float64, "u4": torch.int32, "u1": torch.uint8, "i4": torch.int32}[dtype]
+            pin = (not like.is_cuda) and like.is_pinned()
+            return torch.empty(shape, dtype=tdt, device=like.device, pin_memory=pin)
+        return np.empty(shape, dtype={"f8": np.float64, "u4": np.uint32, "u1": np.uint8,
+                                      "i4": np.int32}[dtype])
+
+    @staticmethod
+    def _contig(x, name):
+        ok = x.is_contiguous() if _is_torch(x) else x.flags["C_CONTIGUOUS"]
+        if not ok:
+            raise MtgError(f"{name} must be contiguous (SoA, batch innermost)")
+
+    # ------------------------------------------------------------------ solve
+    def solve_batch(self, positions, seg_times, end_derivatives=None, N: int = 10,
+                    derivative: int = 4, want_cost=True, want_free=False, want_status=True,
+                    out=None, stream=None):
+        """mtg_solve_batch. positions [K+1,D,B], seg_times [K,B], end_derivatives
+        [2,N/2-1,D,B] or None. Returns dict(coeffs [K,D,N,B], cost [B], free
+        [K-1,N/2-1,D,B], status [B])."""
+        Kp1, D, B = positions.shape
+        K = Kp1 - 1
+        assert tuple(seg_times.shape) == (K, B)
+        for nm, x in (("positions", positions), ("seg_times", seg_times)):
+            self._contig(x, nm)
+        mode = self._mode(positions)
+        desc = ProblemDesc(B, K, D, N, derivative, mode)
+        out = out or {}
+        coeffs = out.get("coeffs")
+        if coeffs is None:
+            coeffs = self._empty(positions, (K, D, N, B))
+        cost = out.get("cost") if want_cost else None
+        if want_cost and cost is None:
+            cost = self._empty(positions, (B,))
+        free = out.get("free") if want_free else None
+        if want_free and free is None:
+            free = self._empty(positions, (max(K - 1, 0), N // 2 - 1, D, B))
+        status = out.get("status") if want_status else None
+        if want_status and status is None:
+            status = self._empty(positions, (B,), "u4")
+        rc = self._lib.mtg_solve_batch(self._h, C.byref(desc), _ptr(positions), _ptr(end_derivatives),
+                                       _ptr(seg_times), _ptr(coeffs), _ptr(cost), _ptr(free),
+                                       _ptr(status), self._stream(mode, stream))
+        self._check(rc, "mtg_solve_batch")
+        return dict(coeffs=coeffs, cost=cost, free=free, status=status)

@@ -1,0 +1,25 @@
+// Device-side constant tables shared by all kernels of libmtg_cuda.so.
+#ifndef MTG_DEVICE_TABLES_CUH_
+#define MTG_DEVICE_TABLES_CUH_
+
+#include "tables.h"
+
+namespace mtg {
+
+struct DevTables {
+  double H1[MTG_TAB_LD * MTG_TAB_LD];
+  double Ainv1[MTG_TAB_LD * MTG_TAB_LD];
+  double base[MTG_BASE_LD * MTG_BASE_LD];
+  double inv_factorial[MTG_TAB_LD];  // 1/B(j,j) = 1/j!  (the A(0) diagonal inverse, LIN_I:152-155)
+  int N;
+  int derivative;
+};
+
+#ifdef __CUDACC__
+// libmtg_cuda.so is ONE CUDA translation unit (mtg_cuda.cu #includes every kernel
+// header), so the table is defined here, once, without relocatable device code.
+__constant__ DevTables c_tab;
+#endif
+
+}  // namespace mtg
+#endif

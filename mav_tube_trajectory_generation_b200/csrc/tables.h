@@ -1,0 +1,21 @@
+#ifndef MTG_TABLES_H_
+#define MTG_TABLES_H_
+
+#define MTG_TAB_LD 12   // Polynomial::kMaxN (reference polynomial.h:45)
+#define MTG_BASE_LD 22  // Polynomial::kMaxConvolutionSize (reference polynomial.h:48)
+
+namespace mtg {
+
+struct Tables {
+  int N;
+  int derivative;
+  double H1[MTG_TAB_LD * MTG_TAB_LD];     // row-major, leading dimension MTG_TAB_LD
+  double Ainv1[MTG_TAB_LD * MTG_TAB_LD];
+  double base[MTG_BASE_LD * MTG_BASE_LD]; // base_coefficients_: B(n,i) = i!/(i-n)!
+};
+
+// false on invalid (N, derivative)
+bool compute_tables(int N, int derivative, Tables* out);
+
+}  // namespace mtg
+#endif
