@@ -22,10 +22,10 @@
  *    pointers (MTG_MEM_DEVICE; nothing is copied, the call only enqueues work
  *    on `stream`) or host pointers (MTG_MEM_HOST; the library stages H2D/D2H
  *    itself in pipelined chunks and returns when the outputs are in place).
- *  - layout: struct-of-arrays with the BATCH INNERMOST, leading dimension
- *    desc.B. A tensor written below as [K][D][N][B] has element (k,d,n,b) at
- *    ((k*D + d)*N + n)*B + b. With B = 1 this degenerates to the reference's
- *    natural per-object order.
+ *  - layout: see MTG_LAYOUT_* below. Tensors are documented by the element
+ *    order inside one trajectory's record, e.g. coeffs "[K][D][N]" means
+ *    elem = (k*D + d)*N + n. With B = 1 both layouts coincide with the
+ *    reference's natural per-object order.
  */
 #ifndef MTG_CUDA_H_
 #define MTG_CUDA_H_
@@ -57,6 +57,16 @@ extern "C" {
 #define MTG_MEM_DEVICE 0
 #define MTG_MEM_HOST 1
 
+/* Every per-trajectory tensor is a batch of B fixed-size RECORDS; a record's
+ * element order is given per tensor below ("elem"). desc.layout places the batch:
+ *   MTG_LAYOUT_SOA  element-major, batch innermost:  x[elem * B + b]
+ *   MTG_LAYOUT_AOS  record-contiguous:               x[b * record_len + elem]
+ * AOS is the reference's natural per-object order (Segment -> Polynomial ->
+ * coefficients) and is what the C++ shim uses; SOA gives fully coalesced accesses
+ * for one-thread-per-trajectory kernels. */
+#define MTG_LAYOUT_SOA 0
+#define MTG_LAYOUT_AOS 1
+
 #define MTG_MAX_N 12 /* Polynomial::kMaxN, polynomial.h:45 */
 
 typedef struct mtg_ctx mtg_ctx;
@@ -71,6 +81,7 @@ typedef struct mtg_problem_desc {
   int32_t N;                      /* coefficients per polynomial, even, <= 12      */
   int32_t derivative_to_optimize; /* 0 .. N/2-1                                    */
   int32_t memory;                 /* MTG_MEM_DEVICE / MTG_MEM_HOST                 */
+  int32_t layout;                 /* MTG_LAYOUT_SOA / MTG_LAYOUT_AOS               */
 } mtg_problem_desc;
 
 /* ------------------------------------------------------------------ context */
@@ -97,15 +108,17 @@ int mtg_get_tables(int N, int derivative, double* H1, double* Ainv1);
  * for the constraint pattern createRandomVertices produces [src/vertex.cpp:27-82]:
  * first and last vertex fix derivatives 0..N/2-1, interior vertices fix position.
  *
- *  positions        [K+1][D][B]      in
- *  end_derivatives  [2][N/2-1][D][B] in, derivatives 1..N/2-1 at the first ([0]) and
+ *  (record element orders; batch placement per desc.layout)
+ *  positions        [K+1][D]         in
+ *  end_derivatives  [2][N/2-1][D]    in, derivatives 1..N/2-1 at the first ([0]) and
  *                                    last ([1]) vertex; NULL = all zero (makeStartOrEnd,
  *                                    src/vertex.cpp:147-153)
- *  seg_times        [K][B]           in
- *  coeffs           [K][D][N][B]     out, increasing powers (polynomial.h:35-36)
+ *  seg_times        [K]              in
+ *  coeffs           [K][D][N]        out, increasing powers (polynomial.h:35-36)
  *  cost             [B]              out or NULL, computeCost() = 0.5 sum c^T Q c
- *  free_constraints [K-1][N/2-1][D][B] out or NULL, d_p (getFreeConstraints order:
- *                                    vertex-major, derivative 1.. within a vertex)
+ *  free_constraints [D][K-1][N/2-1]  out or NULL, d_p exactly as getFreeConstraints
+ *                                    returns it: per dimension, vertex-major,
+ *                                    derivative 1.. within a vertex (LIN_H:289-296)
  *  status           [B] uint32       out or NULL                                   */
 int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc,
                     const double* positions, const double* end_derivatives,

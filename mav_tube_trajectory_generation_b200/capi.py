@@ -2,7 +2,8 @@
 reaches the product path. There is no CPU fallback: if the library is missing or
 no CUDA device is present this module raises.
 
-Tensors are struct-of-arrays with the batch innermost (see mtg_cuda.h). A
+Tensors are batches of records in SoA (batch innermost) or AoS (record-contiguous)
+layout (see mtg_cuda.h). A
 ``torch`` CUDA tensor selects MTG_MEM_DEVICE (nothing is copied; work is
 enqueued on torch's current stream); a numpy array or CPU torch tensor selects
 MTG_MEM_HOST (the library stages H2D/D2H itself).
@@ -18,6 +19,8 @@ from . import _build
 
 MTG_MEM_DEVICE = 0
 MTG_MEM_HOST = 1
+LAYOUT_SOA = 0
+LAYOUT_AOS = 1
 
 ST_BAD_TIME = 1
 ST_NOT_SPD = 2
@@ -32,7 +35,7 @@ class MtgError(RuntimeError):
 
 class ProblemDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("D", C.c_int32), ("N", C.c_int32),
-                ("derivative_to_optimize", C.c_int32), ("memory", C.c_int32)]
+                ("derivative_to_optimize", C.c_int32), ("memory", C.c_int32), ("layout", C.c_int32)]
 
 
 _lib = None
@@ -151,28 +154,36 @@ class Context:
 
     # ------------------------------------------------------------------ solve
     def solve_batch(self, positions, seg_times, end_derivatives=None, N: int = 10,
-                    derivative: int = 4, want_cost=True, want_free=False, want_status=True,
-                    out=None, stream=None):
-        """mtg_solve_batch. positions [K+1,D,B], seg_times [K,B], end_derivatives
-        [2,N/2-1,D,B] or None. Returns dict(coeffs [K,D,N,B], cost [B], free
-        [K-1,N/2-1,D,B], status [B])."""
-        Kp1, D, B = positions.shape
+                    derivative: int = 4, layout: str = "soa", want_cost=True, want_free=False,
+                    want_status=True, out=None, stream=None):
+        """mtg_solve_batch.
+        layout "soa": positions [K+1,D,B], seg_times [K,B], end_derivatives [2,N/2-1,D,B];
+                      returns coeffs [K,D,N,B], free [D,K-1,N/2-1,B]
+        layout "aos": positions [B,K+1,D], seg_times [B,K], end_derivatives [B,2,N/2-1,D];
+                      returns coeffs [B,K,D,N], free [B,D,K-1,N/2-1]
+        plus cost [B], status [B]."""
+        aos = layout == "aos"
+        if aos:
+            B, Kp1, D = positions.shape
+        else:
+            Kp1, D, B = positions.shape
         K = Kp1 - 1
-        assert tuple(seg_times.shape) == (K, B)
+        assert tuple(seg_times.shape) == ((B, K) if aos else (K, B))
         for nm, x in (("positions", positions), ("seg_times", seg_times)):
             self._contig(x, nm)
         mode = self._mode(positions)
-        desc = ProblemDesc(B, K, D, N, derivative, mode)
+        desc = ProblemDesc(B, K, D, N, derivative, mode, LAYOUT_AOS if aos else LAYOUT_SOA)
         out = out or {}
+        nf = N // 2 - 1
         coeffs = out.get("coeffs")
         if coeffs is None:
-            coeffs = self._empty(positions, (K, D, N, B))
+            coeffs = self._empty(positions, (B, K, D, N) if aos else (K, D, N, B))
         cost = out.get("cost") if want_cost else None
         if want_cost and cost is None:
             cost = self._empty(positions, (B,))
         free = out.get("free") if want_free else None
         if want_free and free is None:
-            free = self._empty(positions, (max(K - 1, 0), N // 2 - 1, D, B))
+            free = self._empty(positions, (B, D, max(K - 1, 0), nf) if aos else (D, max(K - 1, 0), nf, B))
         status = out.get("status") if want_status else None
         if want_status and status is None:
             status = self._empty(positions, (B,), "u4")

@@ -91,6 +91,7 @@ int ensure_tables(mtg_ctx* ctx, int N, int derivative) {
   mtg::DevTables h;
   std::memcpy(h.H1, t.H1, sizeof(h.H1));
   std::memcpy(h.Ainv1, t.Ainv1, sizeof(h.Ainv1));
+  std::memcpy(h.W, t.W, sizeof(h.W));
   std::memcpy(h.base, t.base, sizeof(h.base));
   for (int j = 0; j < MTG_TAB_LD; ++j) h.inv_factorial[j] = 1.0 / t.base[j * MTG_BASE_LD + j];
   h.N = N;
@@ -115,36 +116,42 @@ int validate_desc(mtg_ctx* ctx, const mtg_problem_desc* d) {
     return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "derivative_to_optimize must be in [0, N/2-1]");
   if (d->memory != MTG_MEM_DEVICE && d->memory != MTG_MEM_HOST)
     return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "desc.memory must be MTG_MEM_DEVICE or MTG_MEM_HOST");
+  if (d->layout != MTG_LAYOUT_SOA && d->layout != MTG_LAYOUT_AOS)
+    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "desc.layout must be MTG_LAYOUT_SOA or MTG_LAYOUT_AOS");
   return MTG_OK;
 }
 
 // -------------------------------------------------------------- solve launch
-template <int HN, int D>
+template <int HN, int D, bool AOS>
 int launch_solve_canonical_t(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, cudaStream_t stream) {
   constexpr int NF = HN - 1;
   constexpr int SLOTS = NF * NF + NF * D;
-  const size_t per_thread = (size_t)std::max(p.K - 2, 0) * SLOTS * sizeof(double);
+  // two lanes per trajectory; each parks (G_j, z_j) of all but the last vertex it eliminates
+  const int K = p.K, m = K / 2;
+  const int n_own_max = std::max(K - 1 - m, m - 1);
+  const size_t per_thread = (size_t)std::max(n_own_max - 1, 0) * SLOTS * sizeof(double);
   const size_t optin = ctx->smem_optin;
   int block = 128;
   if (const char* env = std::getenv("MTG_SOLVE_BLOCK")) {
-    block = std::max(1, std::min(128, std::atoi(env)));
+    block = std::max(2, std::min(128, std::atoi(env))) & ~1;
   } else if (per_thread > 0) {
     const size_t half_sm = (optin + 1024) / 2 - 1024;  // two CTAs per SM, 1 KB reserved each
-    if (per_thread * 64 <= half_sm)
-      block = 64;
+    if (per_thread * 128 <= half_sm)
+      block = 128;
     else if (per_thread * 32 <= optin)
       block = (int)std::min<size_t>(128, (optin / per_thread) / 32 * 32);
     else
-      block = (int)(optin / per_thread);
+      block = (int)(optin / per_thread) & ~1;
   }
-  if (block < 1 || per_thread * block > optin)
+  if (block < 2 || per_thread * block > optin)
     return fail(ctx, MTG_ERR_UNSUPPORTED,
-                "solve_canonical: K too large for the shared-memory sweep state; use the generic path");
+                "solve_canonical: K too large for the shared-memory sweep state; use mtg_solve_generic_batch");
   const size_t smem = per_thread * block;
-  auto kern = mtg::solve_canonical_kernel<HN, D>;
+  auto kern = mtg::solve_canonical_kernel<HN, D, AOS>;
   if (smem > 48 * 1024)  // per device and per instantiation; a cheap host-side call
     MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
-  const int grid = (p.nb + block - 1) / block;
+  const long long threads = 2LL * p.nb;
+  const int grid = (int)((threads + block - 1) / block);
   if (grid == 0) return MTG_OK;
   kern<<<grid, block, smem, stream>>>(p);
   ++ctx->launches;
@@ -152,38 +159,48 @@ int launch_solve_canonical_t(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, c
   return MTG_OK;
 }
 
-template <int HN>
+template <int HN, bool AOS>
 int launch_solve_canonical_d(mtg_ctx* ctx, int D, const mtg::SolveCanonicalParams& p, cudaStream_t s) {
   switch (D) {
-    case 1: return launch_solve_canonical_t<HN, 1>(ctx, p, s);
-    case 2: return launch_solve_canonical_t<HN, 2>(ctx, p, s);
-    case 3: return launch_solve_canonical_t<HN, 3>(ctx, p, s);
-    case 4: return launch_solve_canonical_t<HN, 4>(ctx, p, s);
+    case 1: return launch_solve_canonical_t<HN, 1, AOS>(ctx, p, s);
+    case 2: return launch_solve_canonical_t<HN, 2, AOS>(ctx, p, s);
+    case 3: return launch_solve_canonical_t<HN, 3, AOS>(ctx, p, s);
+    case 4: return launch_solve_canonical_t<HN, 4, AOS>(ctx, p, s);
   }
   return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "D must be 1..4");
 }
 
-int launch_solve_canonical(mtg_ctx* ctx, int N, int D, const mtg::SolveCanonicalParams& p, cudaStream_t s) {
+template <bool AOS>
+int launch_solve_canonical_n(mtg_ctx* ctx, int N, int D, const mtg::SolveCanonicalParams& p, cudaStream_t s) {
   switch (N) {
-    case 4: return launch_solve_canonical_d<2>(ctx, D, p, s);
-    case 6: return launch_solve_canonical_d<3>(ctx, D, p, s);
-    case 8: return launch_solve_canonical_d<4>(ctx, D, p, s);
-    case 10: return launch_solve_canonical_d<5>(ctx, D, p, s);
-    case 12: return launch_solve_canonical_d<6>(ctx, D, p, s);
+    case 4: return launch_solve_canonical_d<2, AOS>(ctx, D, p, s);
+    case 6: return launch_solve_canonical_d<3, AOS>(ctx, D, p, s);
+    case 8: return launch_solve_canonical_d<4, AOS>(ctx, D, p, s);
+    case 10: return launch_solve_canonical_d<5, AOS>(ctx, D, p, s);
+    case 12: return launch_solve_canonical_d<6, AOS>(ctx, D, p, s);
   }
   return fail(ctx, MTG_ERR_UNSUPPORTED, "solve_canonical supports N in {4,6,8,10,12}");
 }
 
-// 2-D strided copies between the caller's [rows][B] host tensors and a chunk
-// [rows][C] device tensor.
-cudaError_t h2d_rows(void* dst, size_t C, const void* src, size_t B, size_t b0, size_t nb, size_t rows,
-                     size_t elem, cudaStream_t s) {
-  return cudaMemcpy2DAsync(dst, C * elem, (const char*)src + b0 * elem, B * elem, nb * elem, rows,
+int launch_solve_canonical(mtg_ctx* ctx, int N, int D, bool aos, const mtg::SolveCanonicalParams& p,
+                           cudaStream_t s) {
+  return aos ? launch_solve_canonical_n<true>(ctx, N, D, p, s) : launch_solve_canonical_n<false>(ctx, N, D, p, s);
+}
+
+// Copies of a chunk [b0, b0+nb) of a batched tensor with `rec` elements per record
+// between the caller's host tensor (batch B) and a chunk-sized device tensor (batch C).
+cudaError_t h2d_chunk(void* dst, size_t C, const void* src, size_t B, size_t b0, size_t nb, size_t rec,
+                      size_t elem, bool aos, cudaStream_t s) {
+  if (aos)
+    return cudaMemcpyAsync(dst, (const char*)src + b0 * rec * elem, nb * rec * elem, cudaMemcpyHostToDevice, s);
+  return cudaMemcpy2DAsync(dst, C * elem, (const char*)src + b0 * elem, B * elem, nb * elem, rec,
                            cudaMemcpyHostToDevice, s);
 }
-cudaError_t d2h_rows(void* dst, size_t B, size_t b0, const void* src, size_t C, size_t nb, size_t rows,
-                     size_t elem, cudaStream_t s) {
-  return cudaMemcpy2DAsync((char*)dst + b0 * elem, B * elem, src, C * elem, nb * elem, rows,
+cudaError_t d2h_chunk(void* dst, size_t B, size_t b0, const void* src, size_t C, size_t nb, size_t rec,
+                      size_t elem, bool aos, cudaStream_t s) {
+  if (aos)
+    return cudaMemcpyAsync((char*)dst + b0 * rec * elem, src, nb * rec * elem, cudaMemcpyDeviceToHost, s);
+  return cudaMemcpy2DAsync((char*)dst + b0 * elem, B * elem, src, C * elem, nb * elem, rec,
                            cudaMemcpyDeviceToHost, s);
 }
 
@@ -267,6 +284,7 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* po
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = desc->B, K = desc->K, D = desc->D, N = desc->N, NF = N / 2 - 1;
+  const bool aos = desc->layout == MTG_LAYOUT_AOS;
 
   mtg::SolveCanonicalParams p;
   p.K = K;
@@ -282,14 +300,15 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* po
     p.B = B;
     p.b0 = 0;
     p.nb = B;
-    return launch_solve_canonical(ctx, N, D, p, stream);
+    p.vec_ok = ((uintptr_t)coeffs % 16 == 0) ? 1 : 0;
+    return launch_solve_canonical(ctx, N, D, aos, p, stream);
   }
 
   // ---- host-memory mode: pipelined chunks over kStageSlots streams
-  const size_t rows_pos = (size_t)(K + 1) * D, rows_end = (size_t)2 * NF * D, rows_t = K;
-  const size_t rows_c = (size_t)K * D * N, rows_free = (size_t)std::max(K - 1, 0) * NF * D;
-  const size_t in_rows = rows_pos + (end_derivatives ? rows_end : 0) + rows_t;
-  const size_t out_rows = rows_c + (cost ? 1 : 0) + (free_constraints ? rows_free : 0);
+  const size_t rec_pos = (size_t)(K + 1) * D, rec_end = (size_t)2 * NF * D, rec_t = K;
+  const size_t rec_c = (size_t)K * D * N, rec_free = (size_t)std::max(K - 1, 0) * NF * D;
+  const size_t in_rows = rec_pos + (end_derivatives ? rec_end : 0) + rec_t;
+  const size_t out_rows = rec_c + (cost ? 1 : 0) + (free_constraints ? rec_free : 0);
   size_t C = 8192;
   if (const char* env = std::getenv("MTG_HOST_CHUNK")) C = std::max(1, std::atoi(env));
   C = std::min<size_t>(C, (size_t)B);
@@ -308,16 +327,16 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* po
     const size_t b0 = (size_t)c * C, nb = std::min(C, (size_t)B - b0);
     double* din = (double*)ctx->stage_in[s].ptr;
     double* d_pos = din;
-    double* d_end = d_pos + rows_pos * C;
-    double* d_t = d_end + (end_derivatives ? rows_end * C : 0);
+    double* d_end = d_pos + rec_pos * C;
+    double* d_t = d_end + (end_derivatives ? rec_end * C : 0);
     double* dout = (double*)ctx->stage_out[s].ptr;
     double* d_c = dout;
-    double* d_cost = d_c + rows_c * C;
+    double* d_cost = d_c + rec_c * C;
     double* d_free = d_cost + (cost ? C : 0);
     uint32_t* d_status = (uint32_t*)((char*)dout + align256(out_rows * C * 8));
-    MTG_CUDA_TRY(h2d_rows(d_pos, C, positions, B, b0, nb, rows_pos, 8, st));
-    if (end_derivatives) MTG_CUDA_TRY(h2d_rows(d_end, C, end_derivatives, B, b0, nb, rows_end, 8, st));
-    MTG_CUDA_TRY(h2d_rows(d_t, C, seg_times, B, b0, nb, rows_t, 8, st));
+    MTG_CUDA_TRY(h2d_chunk(d_pos, C, positions, B, b0, nb, rec_pos, 8, aos, st));
+    if (end_derivatives) MTG_CUDA_TRY(h2d_chunk(d_end, C, end_derivatives, B, b0, nb, rec_end, 8, aos, st));
+    MTG_CUDA_TRY(h2d_chunk(d_t, C, seg_times, B, b0, nb, rec_t, 8, aos, st));
     p.positions = d_pos;
     p.end_derivatives = end_derivatives ? d_end : nullptr;
     p.seg_times = d_t;
@@ -328,13 +347,14 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* po
     p.B = (int)C;
     p.b0 = 0;
     p.nb = (int)nb;
-    rc = launch_solve_canonical(ctx, N, D, p, st);
+    p.vec_ok = 1;
+    rc = launch_solve_canonical(ctx, N, D, aos, p, st);
     if (rc) return rc;
-    MTG_CUDA_TRY(d2h_rows(coeffs, B, b0, d_c, C, nb, rows_c, 8, st));
-    if (cost) MTG_CUDA_TRY(d2h_rows(cost, B, b0, d_cost, C, nb, 1, 8, st));
-    if (free_constraints && rows_free)
-      MTG_CUDA_TRY(d2h_rows(free_constraints, B, b0, d_free, C, nb, rows_free, 8, st));
-    if (status) MTG_CUDA_TRY(d2h_rows(status, B, b0, d_status, C, nb, 1, 4, st));
+    MTG_CUDA_TRY(d2h_chunk(coeffs, B, b0, d_c, C, nb, rec_c, 8, aos, st));
+    if (cost) MTG_CUDA_TRY(d2h_chunk(cost, B, b0, d_cost, C, nb, 1, 8, true, st));
+    if (free_constraints && rec_free)
+      MTG_CUDA_TRY(d2h_chunk(free_constraints, B, b0, d_free, C, nb, rec_free, 8, aos, st));
+    if (status) MTG_CUDA_TRY(d2h_chunk(status, B, b0, d_status, C, nb, 1, 4, true, st));
   }
   for (int s = 0; s < slots; ++s) MTG_CUDA_TRY(cudaStreamSynchronize(ctx->stage_stream[s]));
   return MTG_OK;

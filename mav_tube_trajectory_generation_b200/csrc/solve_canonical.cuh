@@ -1,7 +1,6 @@
-// solve_canonical — batched closed-form min-derivative solve, one THREAD per
-// trajectory, for the constraint pattern of createRandomVertices
-// (reference src/vertex.cpp:27-82): first/last vertex fix derivatives 0..h-1,
-// interior vertices fix position only.
+// solve_canonical — batched closed-form min-derivative solve for the constraint
+// pattern of createRandomVertices (reference src/vertex.cpp:27-82): first/last
+// vertex fix derivatives 0..h-1, interior vertices fix position only.
 //
 // Replaces per trajectory (reference include/.../impl/polynomial_optimization_linear_impl.h):
 //   updateSegmentTimes :277-304 (Q :557-573, A :101-111, A^-1 :132-169)
@@ -9,18 +8,30 @@
 //   solveLinear :337-379     updateSegmentsFromCompactConstraints :254-275
 //   computeCost :113-130
 //
-// Math: with H_i = T_i^(1-2d) S_i H1 S_i the normal matrix R_pp of the
-// free derivatives (k = 1..h-1 at vertices 1..K-1) is block tridiagonal with
-// (h-1)x(h-1) blocks
-//   D_v = H_{v-1}[end,end] + H_v[start,start],   U_v = H_v[start,end]
-// and is solved by a block Thomas sweep (Cholesky of each Schur block):
-//   S_v = D_v - U_{v-1}^T G_{v-1},  G_v = S_v^-1 U_v,  z_v = S_v^-1 (b_v - U_{v-1}^T z_{v-1})
-//   x_v = z_v - G_v x_{v+1}
-// The sweep state (G_v, z_v for v = 1..K-2) lives in shared memory,
-// slot-major / thread-minor (bank-conflict free); everything else in registers.
-// Coefficients come from the scaled constant inverse:
-//   c_j = d_j / j! (j < h),   c_j = T^-j sum_m Ainv1[j][m] (T^alpha_m d_m)  (j >= h)
-// and the cost from the same scaled endpoint vector: 0.5 T^(1-2d) dhat^T H1 dhat.
+// Math. With H_i = T_i^(1-2d) S_i H1 S_i the normal matrix R_pp of
+// the free derivatives (orders 1..h-1 at vertices 1..K-1) is block tridiagonal,
+//   D_v = H_{v-1}[end,end] + H_v[start,start],   U_v = H_v[start,end],
+// and the right-hand side only needs position DIFFERENCES (H annihilates constant
+// offsets: H[r][0] = -H[r][h]), so the solve is translation invariant by construction.
+//
+// Mapping: TWO LANES PER TRAJECTORY ("twisted" block factorisation). Lane A
+// eliminates vertices 1..m-1 top-down, lane B eliminates K-1..m+1 bottom-up, both
+// with the same block-Thomas recurrences
+//   S_j = D_j - U_{j-1}^T G_{j-1},  G_j = S_j^-1 U_j,  z_j = S_j^-1 (r_j - U_{j-1}^T z_{j-1}).
+// Lane B runs the SAME code on the time-reversed trajectory: reversing time swaps
+// segment start/end and negates odd derivatives, H1[pi r][pi c] = (-1)^(a_r+a_c) H1[r][c],
+// so the mirrored chain has exactly the original form (no divergence between the
+// lanes, constant tables read uniformly). The lanes exchange their Schur
+// contributions to the meeting vertex m with one round of shuffles, both solve the
+// (h-1)x(h-1) meeting system, then each back-substitutes x_j = z_j - G_j x_{j+1} over
+// its half and writes the coefficients and cost of its half of the segments.
+// The parked (G_j, z_j) live in shared memory, slot-major / thread-minor
+// (conflict free); half the state per lane doubles the resident warps.
+//
+// Coefficients:  c_j = d_j / j! (j < h),
+//                c_j = T^-j [Ainv1[j][h] (p_e - p_s) + sum_{m>=1} Ainv1[j][m] T^m d_m + ...]
+// Cost: 0.5 T^(1-2d) |W dhat|^2 with H1 = W^T W (tables.cpp): a sum of squares; a
+// direct dhat^T H1 dhat cancels ~6 digits.
 #ifndef MTG_SOLVE_CANONICAL_CUH_
 #define MTG_SOLVE_CANONICAL_CUH_
 
@@ -31,19 +42,26 @@
 namespace mtg {
 
 struct SolveCanonicalParams {
-  const double* __restrict__ positions;        // [K+1][D][B]
-  const double* __restrict__ end_derivatives;  // [2][h-1][D][B] or nullptr
-  const double* __restrict__ seg_times;        // [K][B]
-  double* __restrict__ coeffs;                 // [K][D][N][B]
+  const double* __restrict__ positions;        // elem (v*D + dim),                 rec (K+1)*D
+  const double* __restrict__ end_derivatives;  // elem ((side*(h-1) + m-1)*D + dim), rec 2*(h-1)*D; or nullptr
+  const double* __restrict__ seg_times;        // elem i,                            rec K
+  double* __restrict__ coeffs;                 // elem ((i*D + dim)*N + j),          rec K*D*N
   double* __restrict__ cost;                   // [B] or nullptr
-  double* __restrict__ free_constraints;       // [K-1][h-1][D][B] or nullptr
+  double* __restrict__ free_constraints;       // elem ((dim*(K-1) + v-1)*(h-1) + k-1), rec D*(K-1)*(h-1); or nullptr
   uint32_t* __restrict__ status;               // [B] or nullptr
-  int B;   // leading dimension of every tensor
+  int B;   // leading dimension (SoA) / number of records
   int b0;  // first trajectory handled by this launch
   int nb;  // number of trajectories handled by this launch
   int K;
   int derivative;
+  int vec_ok;  // AoS only: coeffs is 16-byte aligned -> double2 stores
 };
+
+// element `elem` of record `b`: SoA = batch innermost, AoS = record-contiguous
+template <bool AOS>
+__device__ __forceinline__ size_t at(size_t elem, size_t rec, size_t B, size_t b) {
+  return AOS ? b * rec + elem : elem * B + b;
+}
 
 template <int HN>
 __device__ __forceinline__ void segment_powers(double T, int derivative, double (&pw)[2 * HN - 1]) {
@@ -63,13 +81,15 @@ __device__ __forceinline__ void segment_powers(double T, int derivative, double 
 
 #define MTG_H1(r, c) c_tab.H1[(r) * MTG_TAB_LD + (c)]
 #define MTG_AI(r, c) c_tab.Ainv1[(r) * MTG_TAB_LD + (c)]
+#define MTG_W(r, c) c_tab.W[(r) * MTG_TAB_LD + (c)]
 
-// Writes the N coefficients of every dimension of one segment and returns the
-// segment's cost contribution  T^(1-2d) * sum_dim dhat^T H1 dhat  (without 1/2).
-// ds / de: derivative values 0..h-1 at the segment start / end, per dimension.
-template <int HN, int D>
-__device__ __forceinline__ double emit_segment(const SolveCanonicalParams& p, int seg, int b, double T,
-                                               const double (&ds)[D][HN], const double (&de)[D][HN]) {
+// Writes the N coefficients of every dimension of one segment (original
+// orientation: ds at the segment start, de at its end) and returns the segment's
+// cost contribution  T^(1-2d) * sum_dim |W dhat|^2  (without the 1/2).
+template <int HN, int D, bool AOS>
+__device__ __forceinline__ double emit_segment(const SolveCanonicalParams& p, int seg, int b, bool active,
+                                               double T, const double (&ds)[D][HN],
+                                               const double (&de)[D][HN]) {
   constexpr int N = 2 * HN;
   double tp[HN];  // T^m
   tp[0] = 1.0;
@@ -79,38 +99,63 @@ __device__ __forceinline__ double emit_segment(const SolveCanonicalParams& p, in
   double uh = u;  // u^HN
 #pragma unroll
   for (int m = 1; m < HN; ++m) uh *= u;
+  const int nq = N - p.derivative;
   double quad = 0.0;
+  const size_t rec = (size_t)p.K * D * N;
 #pragma unroll
   for (int dim = 0; dim < D; ++dim) {
-    double dh[N];
+    double dh[N];  // scaled endpoint derivatives; slots 0 and HN unused (position enters as a difference)
+    const double dlt = de[dim][0] - ds[dim][0];
 #pragma unroll
-    for (int m = 0; m < HN; ++m) {
+    for (int m = 1; m < HN; ++m) {
       dh[m] = tp[m] * ds[dim][m];
       dh[HN + m] = tp[m] * de[dim][m];
     }
-    double* out = p.coeffs + ((size_t)(seg * D + dim) * N) * p.B + b;
+    double c[N];
 #pragma unroll
-    for (int j = 0; j < HN; ++j) out[(size_t)j * p.B] = ds[dim][j] * c_tab.inv_factorial[j];
+    for (int j = 0; j < HN; ++j) c[j] = ds[dim][j] * c_tab.inv_factorial[j];
     double us = uh;
 #pragma unroll
     for (int j = HN; j < N; ++j) {
-      double acc = 0.0;
+      double acc = MTG_AI(j, HN) * dlt;
 #pragma unroll
-      for (int m = 0; m < N; ++m) acc = fma(MTG_AI(j, m), dh[m], acc);
-      out[(size_t)j * p.B] = acc * us;
+      for (int m = 1; m < HN; ++m) {
+        acc = fma(MTG_AI(j, m), dh[m], acc);
+        acc = fma(MTG_AI(j, HN + m), dh[HN + m], acc);
+      }
+      c[j] = acc * us;
       us *= u;
     }
-    // dhat^T H1 dhat using symmetry
+    if (active) {
+      if (AOS) {
+        double* out = p.coeffs + (size_t)b * rec + (size_t)(seg * D + dim) * N;
+        if (p.vec_ok) {
 #pragma unroll
-    for (int r = 0; r < N; ++r) {
-      double row = 0.5 * MTG_H1(r, r) * dh[r];
+          for (int j = 0; j < N; j += 2) *reinterpret_cast<double2*>(out + j) = make_double2(c[j], c[j + 1]);
+        } else {
 #pragma unroll
-      for (int c = r + 1; c < N; ++c) row = fma(MTG_H1(r, c), dh[c], row);
-      quad = fma(2.0 * dh[r], row, quad);
+          for (int j = 0; j < N; ++j) out[j] = c[j];
+        }
+      } else {
+        double* out = p.coeffs + ((size_t)(seg * D + dim) * N) * p.B + b;
+#pragma unroll
+        for (int j = 0; j < N; ++j) out[(size_t)j * p.B] = c[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (i < nq) {
+        double w = MTG_W(i, HN) * dlt;
+#pragma unroll
+        for (int m = 1; m < HN; ++m) {
+          w = fma(MTG_W(i, m), dh[m], w);
+          w = fma(MTG_W(i, HN + m), dh[HN + m], w);
+        }
+        quad = fma(w, w, quad);
+      }
     }
   }
-  // T^(1-2d)
-  double s = 1.0;
+  double s = 1.0;  // T^(1-2d)
   const int e0 = 1 - 2 * p.derivative;
   if (e0 >= 0) {
     for (int i = 0; i < e0; ++i) s *= T;
@@ -120,267 +165,335 @@ __device__ __forceinline__ double emit_segment(const SolveCanonicalParams& p, in
   return quad * s;
 }
 
-template <int HN, int D>
-__global__ void __launch_bounds__(128) solve_canonical_kernel(const SolveCanonicalParams p) {
-  constexpr int NF = HN - 1;             // free derivatives per interior vertex
-  constexpr int SLOTS = NF * NF + NF * D;  // G_v and z_v
+// In-place Cholesky of the lower triangle of S (reciprocal diagonal in linv).
+template <int NF>
+__device__ __forceinline__ void chol_lower(double (&S)[NF][NF], double (&linv)[NF], uint32_t& st) {
+#pragma unroll
+  for (int j = 0; j < NF; ++j) {
+    double piv = S[j][j];
+#pragma unroll
+    for (int q = 0; q < j; ++q) piv = fma(-S[j][q], S[j][q], piv);
+    if (!(piv > 0.0)) {
+      st |= 2u;
+      piv = 1.0;
+    }
+    const double rs = rsqrt(piv);
+    linv[j] = rs;
+#pragma unroll
+    for (int i = j + 1; i < NF; ++i) {
+      double s = S[i][j];
+#pragma unroll
+      for (int q = 0; q < j; ++q) s = fma(-S[i][q], S[j][q], s);
+      S[i][j] = s * rs;
+    }
+  }
+}
+
+// x <- (L L^T)^-1 x
+template <int NF>
+__device__ __forceinline__ void chol_solve(const double (&L)[NF][NF], const double (&linv)[NF], double (&x)[NF]) {
+#pragma unroll
+  for (int i = 0; i < NF; ++i) {
+    double s = x[i];
+#pragma unroll
+    for (int q = 0; q < i; ++q) s = fma(-L[i][q], x[q], s);
+    x[i] = s * linv[i];
+  }
+#pragma unroll
+  for (int i = NF - 1; i >= 0; --i) {
+    double s = x[i];
+#pragma unroll
+    for (int q = i + 1; q < NF; ++q) s = fma(-L[q][i], x[q], s);
+    x[i] = s * linv[i];
+  }
+}
+
+template <int HN, int D, bool AOS>
+__global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCanonicalParams p) {
+  constexpr int N = 2 * HN;
+  constexpr int NF = HN - 1;               // free derivatives per interior vertex
+  constexpr int SLOTS = NF * NF + NF * D;  // parked G_j and z_j
+  constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
   const int nt = blockDim.x;
-  const int local = blockIdx.x * nt + tid;
-  if (local >= p.nb) return;
-  const int b = p.b0 + local;
+  const int pair = (blockIdx.x * nt + tid) >> 1;
+  const int side = tid & 1;  // 0: lane A (original orientation), 1: lane B (time-reversed chain)
+  const bool active = pair < p.nb;
+  const int b = p.b0 + (active ? pair : p.nb - 1);
   const int K = p.K;
   const size_t B = (size_t)p.B;
   const int d = p.derivative;
   uint32_t st = 0;
 
-  auto pos = [&](int v, int dim) { return p.positions[((size_t)v * D + dim) * B + b]; };
+  const size_t rec_pos = (size_t)(K + 1) * D, rec_t = (size_t)K, rec_end = (size_t)2 * NF * D;
+  auto pos = [&](int v, int dim) { return p.positions[at<AOS>((size_t)v * D + dim, rec_pos, B, b)]; };
   auto seg_time = [&](int i) {
-    double T = p.seg_times[(size_t)i * B + b];
+    double T = p.seg_times[at<AOS>((size_t)i, rec_t, B, b)];
     if (!(T > 0.0) || !(T < 1.7e308)) {  // LIN_I:296 CHECK_GT(segment_time, 0)
       st |= 1u;
       T = 1.0;
     }
     return T;
   };
+  // chain -> original indices
+  auto V = [&](int j) { return side ? K - j : j; };
+  auto SG = [&](int c) { return side ? K - 1 - c : c; };
 
-  // endpoint derivative constraints (zero = makeStartOrEnd)
-  double sd[D][HN], ed[D][HN];
+  // sign of derivative order m under time reversal (lane B only)
+  double sg[HN];
+#pragma unroll
+  for (int m = 0; m < HN; ++m) sg[m] = (side && (m & 1)) ? -1.0 : 1.0;
+
+  // constraints at the chain start (vertex 0 for A, vertex K for B), chain sign convention
+  double sdt[D][HN];
+  const bool have_end = (p.end_derivatives != nullptr);
 #pragma unroll
   for (int dim = 0; dim < D; ++dim) {
-    sd[dim][0] = pos(0, dim);
-    ed[dim][0] = pos(K, dim);
+    sdt[dim][0] = pos(V(0), dim);
 #pragma unroll
-    for (int m = 1; m < HN; ++m) {
-      sd[dim][m] = 0.0;
-      ed[dim][m] = 0.0;
-    }
-  }
-  const bool have_end = (p.end_derivatives != nullptr);
-  if (have_end) {
-#pragma unroll
-    for (int dim = 0; dim < D; ++dim)
-#pragma unroll
-      for (int m = 1; m < HN; ++m) {
-        sd[dim][m] = p.end_derivatives[((size_t)(0 * NF + (m - 1)) * D + dim) * B + b];
-        ed[dim][m] = p.end_derivatives[((size_t)(1 * NF + (m - 1)) * D + dim) * B + b];
-      }
+    for (int m = 1; m < HN; ++m)
+      sdt[dim][m] = have_end ? sg[m] * p.end_derivatives[at<AOS>((size_t)(side * NF + (m - 1)) * D + dim,
+                                                                  rec_end, B, b)]
+                             : 0.0;
   }
 
   double cost_acc = 0.0;
 
   if (K == 1) {
+    // fully constrained single segment: lane A writes it from both vertices' constraints
+    double other[D][HN];
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim)
+#pragma unroll
+      for (int m = 0; m < HN; ++m)  // lane B's constraints arrive in its reversed-time sign convention
+        other[dim][m] = ((m & 1) ? -1.0 : 1.0) * __shfl_xor_sync(FULL, sdt[dim][m], 1);
     const double T = seg_time(0);
-    cost_acc = emit_segment<HN, D>(p, 0, b, T, sd, ed);
-  } else {
-    // ------------------------------------------------------------ forward
-    double pl[2 * HN - 1], pr[2 * HN - 1];
-    double U[NF][NF];   // U_{v-1} on entry of step v (rows: vertex v-1, cols: vertex v)
-    double G[NF][NF];   // G_{v-1}
-    double z[D][NF];    // z_{v-1}
-    double p_prev[D], p_cur[D], p_next[D];
-    {
-      const double T0 = seg_time(0);
-      segment_powers<HN>(T0, d, pr);
+    cost_acc = emit_segment<HN, D, AOS>(p, 0, b, active && side == 0, T, sdt, other);
+    if (active && side == 0) {
+      if (p.cost) p.cost[b] = 0.5 * cost_acc;
+      if (p.status) p.status[b] = st;
     }
+    return;
+  }
+
+  const int m_meet = K / 2;                                 // meeting vertex, 1 <= m <= K-1
+  const int n_own = side ? (K - 1 - m_meet) : (m_meet - 1);  // vertices this lane eliminates
+
+  // ---------------------------------------------------------------- forward
+  double pl[2 * HN - 1], pr[2 * HN - 1];
+  double U[NF][NF];  // U_{j-1} on entry of step j (rows: chain vertex j-1, cols: chain vertex j)
+  double G[NF][NF];  // G_{j-1}
+  double z[D][NF];   // z_{j-1}
+  double S[NF][NF];
+  double r[D][NF];
+  double p_prev[D], p_cur[D], p_next[D];
+  segment_powers<HN>(seg_time(SG(0)), d, pr);
+#pragma unroll
+  for (int dim = 0; dim < D; ++dim) {
+    p_cur[dim] = sdt[dim][0];
+    p_next[dim] = pos(V(1), dim);
+  }
+#pragma unroll 1
+  for (int j = 1;; ++j) {
+    const bool own = (j <= n_own);
+#pragma unroll
+    for (int q = 0; q < 2 * HN - 1; ++q) pl[q] = pr[q];
 #pragma unroll
     for (int dim = 0; dim < D; ++dim) {
-      p_cur[dim] = sd[dim][0];
-      p_next[dim] = pos(1, dim);
+      p_prev[dim] = p_cur[dim];
+      p_cur[dim] = p_next[dim];
     }
-#pragma unroll 1
-    for (int v = 1; v <= K - 1; ++v) {
+    if (own) {
+      segment_powers<HN>(seg_time(SG(j)), d, pr);
 #pragma unroll
-      for (int q = 0; q < 2 * HN - 1; ++q) pl[q] = pr[q];
-      segment_powers<HN>(seg_time(v), d, pr);
+      for (int dim = 0; dim < D; ++dim) p_next[dim] = pos(V(j + 1), dim);
+    }
+    // contribution of the chain segment on the left of vertex j
 #pragma unroll
-      for (int dim = 0; dim < D; ++dim) {
-        p_prev[dim] = p_cur[dim];
-        p_cur[dim] = p_next[dim];
-        p_next[dim] = pos(v + 1, dim);
-      }
-      // Schur block (lower triangle) and right-hand sides
-      double S[NF][NF];
-      double r[D][NF];
+    for (int k = 0; k < NF; ++k) {
+#pragma unroll
+      for (int kk = 0; kk <= k; ++kk) S[k][kk] = MTG_H1(HN + 1 + k, HN + 1 + kk) * pl[k + kk + 2];
+      const double a_l = MTG_H1(HN + 1 + k, HN) * pl[k + 1];
+#pragma unroll
+      for (int dim = 0; dim < D; ++dim) r[dim][k] = -a_l * (p_cur[dim] - p_prev[dim]);
+    }
+    if (j == 1 && have_end) {
+#pragma unroll
+      for (int k = 0; k < NF; ++k)
+#pragma unroll
+        for (int mm = 1; mm < HN; ++mm) {
+          const double a = MTG_H1(HN + 1 + k, mm) * pl[k + 1 + mm];
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) r[dim][k] = fma(-a, sdt[dim][mm], r[dim][k]);
+        }
+    }
+    if (j > 1) {
 #pragma unroll
       for (int k = 0; k < NF; ++k) {
 #pragma unroll
         for (int kk = 0; kk <= k; ++kk) {
-          double s = MTG_H1(HN + 1 + k, HN + 1 + kk) * pl[k + kk + 2];
-          s = fma(MTG_H1(1 + k, 1 + kk), pr[k + kk + 2], s);
+          double s = S[k][kk];
+#pragma unroll
+          for (int q = 0; q < NF; ++q) s = fma(-U[q][k], G[q][kk], s);
           S[k][kk] = s;
         }
-        const double a_self = fma(MTG_H1(HN + 1 + k, HN), pl[k + 1], MTG_H1(1 + k, 0) * pr[k + 1]);
-        const double a_prev = MTG_H1(HN + 1 + k, 0) * pl[k + 1];
-        const double a_next = MTG_H1(1 + k, HN) * pr[k + 1];
 #pragma unroll
-        for (int dim = 0; dim < D; ++dim)
-          r[dim][k] = -fma(a_self, p_cur[dim], fma(a_prev, p_prev[dim], a_next * p_next[dim]));
-      }
-      if (have_end) {
-        if (v == 1) {
+        for (int dim = 0; dim < D; ++dim) {
+          double s = r[dim][k];
 #pragma unroll
-          for (int k = 0; k < NF; ++k)
-#pragma unroll
-            for (int m = 1; m < HN; ++m) {
-              const double a = MTG_H1(HN + 1 + k, m) * pl[k + 1 + m];
-#pragma unroll
-              for (int dim = 0; dim < D; ++dim) r[dim][k] = fma(-a, sd[dim][m], r[dim][k]);
-            }
+          for (int q = 0; q < NF; ++q) s = fma(-U[q][k], z[dim][q], s);
+          r[dim][k] = s;
         }
-        if (v == K - 1) {
-#pragma unroll
-          for (int k = 0; k < NF; ++k)
-#pragma unroll
-            for (int m = 1; m < HN; ++m) {
-              const double a = MTG_H1(1 + k, HN + m) * pr[k + 1 + m];
-#pragma unroll
-              for (int dim = 0; dim < D; ++dim) r[dim][k] = fma(-a, ed[dim][m], r[dim][k]);
-            }
-        }
-      }
-      if (v > 1) {
-#pragma unroll
-        for (int k = 0; k < NF; ++k) {
-#pragma unroll
-          for (int kk = 0; kk <= k; ++kk) {
-            double s = S[k][kk];
-#pragma unroll
-            for (int j = 0; j < NF; ++j) s = fma(-U[j][k], G[j][kk], s);
-            S[k][kk] = s;
-          }
-#pragma unroll
-          for (int dim = 0; dim < D; ++dim) {
-            double s = r[dim][k];
-#pragma unroll
-            for (int j = 0; j < NF; ++j) s = fma(-U[j][k], z[dim][j], s);
-            r[dim][k] = s;
-          }
-        }
-      }
-      // Cholesky S = L L^T, diagonal kept as its reciprocal
-      double linv[NF];
-#pragma unroll
-      for (int j = 0; j < NF; ++j) {
-        double piv = S[j][j];
-#pragma unroll
-        for (int q = 0; q < j; ++q) piv = fma(-S[j][q], S[j][q], piv);
-        if (!(piv > 0.0)) {
-          st |= 2u;
-          piv = 1.0;
-        }
-        const double rs2 = rsqrt(piv);
-        linv[j] = rs2;
-#pragma unroll
-        for (int i = j + 1; i < NF; ++i) {
-          double s = S[i][j];
-#pragma unroll
-          for (int q = 0; q < j; ++q) s = fma(-S[i][q], S[j][q], s);
-          S[i][j] = s * rs2;
-        }
-      }
-      // z_v = S^-1 r   (L y = r ; L^T z = y)
-#pragma unroll
-      for (int dim = 0; dim < D; ++dim) {
-#pragma unroll
-        for (int i = 0; i < NF; ++i) {
-          double s = r[dim][i];
-#pragma unroll
-          for (int q = 0; q < i; ++q) s = fma(-S[i][q], z[dim][q], s);
-          z[dim][i] = s * linv[i];
-        }
-#pragma unroll
-        for (int i = NF - 1; i >= 0; --i) {
-          double s = z[dim][i];
-#pragma unroll
-          for (int q = i + 1; q < NF; ++q) s = fma(-S[q][i], z[dim][q], s);
-          z[dim][i] = s * linv[i];
-        }
-      }
-      if (v < K - 1) {
-        // U_v and G_v = S^-1 U_v
-#pragma unroll
-        for (int k = 0; k < NF; ++k)
-#pragma unroll
-          for (int kk = 0; kk < NF; ++kk) U[k][kk] = MTG_H1(1 + k, HN + 1 + kk) * pr[k + kk + 2];
-#pragma unroll
-        for (int c = 0; c < NF; ++c) {
-#pragma unroll
-          for (int i = 0; i < NF; ++i) {
-            double s = U[i][c];
-#pragma unroll
-            for (int q = 0; q < i; ++q) s = fma(-S[i][q], G[q][c], s);
-            G[i][c] = s * linv[i];
-          }
-#pragma unroll
-          for (int i = NF - 1; i >= 0; --i) {
-            double s = G[i][c];
-#pragma unroll
-            for (int q = i + 1; q < NF; ++q) s = fma(-S[q][i], G[q][c], s);
-            G[i][c] = s * linv[i];
-          }
-        }
-        // park G_v, z_v
-        double* slot = smem + (size_t)(v - 1) * SLOTS * nt + tid;
-#pragma unroll
-        for (int i = 0; i < NF; ++i)
-#pragma unroll
-          for (int c = 0; c < NF; ++c) slot[(size_t)(i * NF + c) * nt] = G[i][c];
-#pragma unroll
-        for (int dim = 0; dim < D; ++dim)
-#pragma unroll
-          for (int i = 0; i < NF; ++i) slot[(size_t)(NF * NF + dim * NF + i) * nt] = z[dim][i];
       }
     }
-    // ----------------------------------------------------------- backward
-    // on exit: z = x_{K-1}; p_cur = pos(K-1), p_next = pos(K)
-    double xs[D][HN], xe[D][HN];
+    if (!own) break;  // j = n_own + 1: S, r hold this lane's half of the meeting vertex
+    // contribution of the chain segment on the right of vertex j
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {
+#pragma unroll
+      for (int kk = 0; kk <= k; ++kk) S[k][kk] = fma(MTG_H1(1 + k, 1 + kk), pr[k + kk + 2], S[k][kk]);
+      const double a_r = MTG_H1(1 + k, HN) * pr[k + 1];
+#pragma unroll
+      for (int dim = 0; dim < D; ++dim) r[dim][k] = fma(-a_r, p_next[dim] - p_cur[dim], r[dim][k]);
+    }
+    double linv[NF];
+    chol_lower<NF>(S, linv, st);
 #pragma unroll
     for (int dim = 0; dim < D; ++dim) {
-      xs[dim][0] = p_cur[dim];
 #pragma unroll
-      for (int i = 0; i < NF; ++i) xs[dim][1 + i] = z[dim][i];
+      for (int i = 0; i < NF; ++i) z[dim][i] = r[dim][i];
+      chol_solve<NF>(S, linv, z[dim]);
     }
-    if (p.free_constraints) {
+#pragma unroll
+    for (int k = 0; k < NF; ++k)
+#pragma unroll
+      for (int kk = 0; kk < NF; ++kk) U[k][kk] = MTG_H1(1 + k, HN + 1 + kk) * pr[k + kk + 2];
+#pragma unroll
+    for (int c = 0; c < NF; ++c) {
+      double col[NF];
+#pragma unroll
+      for (int i = 0; i < NF; ++i) col[i] = U[i][c];
+      chol_solve<NF>(S, linv, col);
+#pragma unroll
+      for (int i = 0; i < NF; ++i) G[i][c] = col[i];
+    }
+    if (j < n_own) {  // park; the last own vertex stays in registers
+      double* slot = smem + (size_t)(j - 1) * SLOTS * nt + tid;
+#pragma unroll
+      for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int c = 0; c < NF; ++c) slot[(size_t)(i * NF + c) * nt] = G[i][c];
 #pragma unroll
       for (int dim = 0; dim < D; ++dim)
+#pragma unroll
+        for (int i = 0; i < NF; ++i) slot[(size_t)(NF * NF + dim * NF + i) * nt] = z[dim][i];
+    }
+  }
+
+  // --------------------------------------------------- meeting vertex m_meet
+  // to the original sign convention, add the partner's half, solve (both lanes)
+#pragma unroll
+  for (int k = 0; k < NF; ++k) {
+#pragma unroll
+    for (int kk = 0; kk <= k; ++kk) {
+      const double mine = S[k][kk] * (sg[k + 1] * sg[kk + 1]);
+      S[k][kk] = mine + __shfl_xor_sync(FULL, mine, 1);
+    }
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim) {
+      const double mine = r[dim][k] * sg[k + 1];
+      r[dim][k] = mine + __shfl_xor_sync(FULL, mine, 1);
+    }
+  }
+  double xe[D][HN];  // values at the chain vertex after the current one, chain sign convention
+  {
+    double linv[NF];
+    chol_lower<NF>(S, linv, st);
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim) {
+      chol_solve<NF>(S, linv, r[dim]);
+      xe[dim][0] = p_cur[dim];
+#pragma unroll
+      for (int i = 0; i < NF; ++i) xe[dim][1 + i] = r[dim][i] * sg[1 + i];
+    }
+  }
+  const size_t rec_free = (size_t)D * (K - 1) * NF;
+  if (p.free_constraints && active && side == 0) {
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim)
+#pragma unroll
+      for (int i = 0; i < NF; ++i)
+        p.free_constraints[at<AOS>((size_t)(dim * (K - 1) + (m_meet - 1)) * NF + i, rec_free, B, b)] =
+            r[dim][i];
+  }
+
+  // ---------------------------------------------------------------- backward
+  double xs[D][HN];
+#pragma unroll 1
+  for (int c = n_own; c >= 0; --c) {
+    const double T = seg_time(SG(c));
+    if (c == 0) {
+#pragma unroll
+      for (int dim = 0; dim < D; ++dim)
+#pragma unroll
+        for (int mm = 0; mm < HN; ++mm) xs[dim][mm] = sdt[dim][mm];
+    } else {
+      if (c < n_own) {
+        const double* slot = smem + (size_t)(c - 1) * SLOTS * nt + tid;
 #pragma unroll
         for (int i = 0; i < NF; ++i)
-          p.free_constraints[((size_t)((K - 2) * NF + i) * D + dim) * B + b] = z[dim][i];
-    }
-    cost_acc += emit_segment<HN, D>(p, K - 1, b, seg_time(K - 1), xs, ed);
-#pragma unroll 1
-    for (int v = K - 2; v >= 1; --v) {
 #pragma unroll
-      for (int dim = 0; dim < D; ++dim)
+          for (int q = 0; q < NF; ++q) G[i][q] = slot[(size_t)(i * NF + q) * nt];
 #pragma unroll
-        for (int m = 0; m < HN; ++m) xe[dim][m] = xs[dim][m];
-      const double* slot = smem + (size_t)(v - 1) * SLOTS * nt + tid;
+        for (int dim = 0; dim < D; ++dim)
+#pragma unroll
+          for (int i = 0; i < NF; ++i) z[dim][i] = slot[(size_t)(NF * NF + dim * NF + i) * nt];
+      }
 #pragma unroll
       for (int dim = 0; dim < D; ++dim) {
-        xs[dim][0] = pos(v, dim);
+        xs[dim][0] = pos(V(c), dim);
 #pragma unroll
         for (int i = 0; i < NF; ++i) {
-          double s = slot[(size_t)(NF * NF + dim * NF + i) * nt];
+          double s = z[dim][i];
 #pragma unroll
-          for (int c = 0; c < NF; ++c) s = fma(-slot[(size_t)(i * NF + c) * nt], xe[dim][1 + c], s);
+          for (int q = 0; q < NF; ++q) s = fma(-G[i][q], xe[dim][1 + q], s);
           xs[dim][1 + i] = s;
         }
       }
-      if (p.free_constraints) {
+      if (p.free_constraints && active) {
+        const int v = V(c);
 #pragma unroll
         for (int dim = 0; dim < D; ++dim)
 #pragma unroll
           for (int i = 0; i < NF; ++i)
-            p.free_constraints[((size_t)((v - 1) * NF + i) * D + dim) * B + b] = xs[dim][1 + i];
+            p.free_constraints[at<AOS>((size_t)(dim * (K - 1) + (v - 1)) * NF + i, rec_free, B, b)] =
+                xs[dim][1 + i] * sg[1 + i];
       }
-      cost_acc += emit_segment<HN, D>(p, v, b, seg_time(v), xs, xe);
     }
-    cost_acc += emit_segment<HN, D>(p, 0, b, seg_time(0), sd, xs);
+    // original orientation / sign: lane B's chain start is the segment's END
+    double ds[D][HN], de[D][HN];
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim)
+#pragma unroll
+      for (int mm = 0; mm < HN; ++mm) {
+        const double a = xs[dim][mm] * sg[mm];
+        const double e = xe[dim][mm] * sg[mm];
+        ds[dim][mm] = side ? e : a;
+        de[dim][mm] = side ? a : e;
+      }
+    cost_acc += emit_segment<HN, D, AOS>(p, SG(c), b, active, T, ds, de);
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim)
+#pragma unroll
+      for (int mm = 0; mm < HN; ++mm) xe[dim][mm] = xs[dim][mm];
   }
-  if (p.cost) p.cost[b] = 0.5 * cost_acc;
-  if (p.status) p.status[b] = st;
+  cost_acc += __shfl_xor_sync(FULL, cost_acc, 1);
+  st |= __shfl_xor_sync(FULL, st, 1);
+  if (active && side == 0) {
+    if (p.cost) p.cost[b] = 0.5 * cost_acc;
+    if (p.status) p.status[b] = st;
+  }
 }
 
 }  // namespace mtg

@@ -87,9 +87,35 @@ bool compute_tables(int N, int derivative, Tables* out) {
       for (int k = 0; k < N; ++k) s += Ai[k * N + i] * tmp[k * N + j];
       H[i * N + j] = H[j * N + i] = s;
     }
+  // W = L^T Ainv1[d.., :],  Q[d.., d..] = L L^T (Cholesky in binary128)
+  const int nq = N - d;
+  q128 L[MTG_TAB_LD * MTG_TAB_LD], Wm[MTG_TAB_LD * MTG_TAB_LD];
+  for (int i = 0; i < nq * nq; ++i) L[i] = 0;
+  for (int j = 0; j < nq; ++j) {
+    q128 s = Q[(d + j) * N + (d + j)];
+    for (int k = 0; k < j; ++k) s -= L[j * nq + k] * L[j * nq + k];
+    if (!(s > 0)) return false;
+    // Newton square root in binary128 from a double seed
+    q128 r = static_cast<q128>(__builtin_sqrt(static_cast<double>(s)));
+    for (int it = 0; it < 4; ++it) r = (r + s / r) / 2;
+    L[j * nq + j] = r;
+    for (int i = j + 1; i < nq; ++i) {
+      q128 t = Q[(d + i) * N + (d + j)];
+      for (int k = 0; k < j; ++k) t -= L[i * nq + k] * L[j * nq + k];
+      L[i * nq + j] = t / r;
+    }
+  }
+  for (int i = 0; i < nq; ++i)
+    for (int m = 0; m < N; ++m) {
+      q128 s = 0;
+      for (int a = i; a < nq; ++a) s += L[a * nq + i] * Ai[(d + a) * N + m];
+      Wm[i * N + m] = s;
+    }
   out->N = N;
   out->derivative = d;
-  for (int i = 0; i < MTG_TAB_LD * MTG_TAB_LD; ++i) out->H1[i] = out->Ainv1[i] = 0.0;
+  for (int i = 0; i < MTG_TAB_LD * MTG_TAB_LD; ++i) out->H1[i] = out->Ainv1[i] = out->W[i] = 0.0;
+  for (int i = 0; i < nq; ++i)
+    for (int m = 0; m < N; ++m) out->W[i * MTG_TAB_LD + m] = static_cast<double>(Wm[i * N + m]);
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) {
       out->H1[i * MTG_TAB_LD + j] = static_cast<double>(H[i * N + j]);

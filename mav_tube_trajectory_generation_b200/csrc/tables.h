@@ -11,6 +11,10 @@ struct Tables {
   int derivative;
   double H1[MTG_TAB_LD * MTG_TAB_LD];     // row-major, leading dimension MTG_TAB_LD
   double Ainv1[MTG_TAB_LD * MTG_TAB_LD];
+  // rank factor of H1: H1 = W^T W, W is (N-d) x N. W = L^T Ainv1[d..N-1, :] with
+  // Q(1)[d.., d..] = L L^T. The cost is evaluated as a sum of squares |W dhat|^2,
+  // which has no cancellation across terms (a direct dhat^T H1 dhat loses ~6 digits).
+  double W[MTG_TAB_LD * MTG_TAB_LD];
   double base[MTG_BASE_LD * MTG_BASE_LD]; // base_coefficients_: B(n,i) = i!/(i-n)!
 };
 

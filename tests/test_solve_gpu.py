@@ -22,20 +22,26 @@ N = 10
 TOL = 1e-9
 
 
-def gpu_solve(pos, times, derivative=4, end=None, device=True, want_free=True):
-    """pos [B,K+1,D], times [B,K] (AoS) -> coeffs [B,K,D,N], cost [B], free [B,K-1,4,D], status [B]."""
+def gpu_solve(pos, times, derivative=4, end=None, device=True, want_free=True, layout="soa"):
+    """pos [B,K+1,D], times [B,K], end [B,2,4,D] (AoS) -> coeffs [B,K,D,N], cost [B],
+    free [B,D,K-1,4] (getFreeConstraints order), status [B]."""
     c = ctx()
-    p, t = soa(pos), soa(times)
-    e = soa(end) if end is not None else None
+    if layout == "soa":
+        p, t = soa(pos), soa(times)
+        e = soa(end) if end is not None else None
+    else:
+        p, t = np.ascontiguousarray(pos), np.ascontiguousarray(times)
+        e = np.ascontiguousarray(end) if end is not None else None
     if device:
         p, t = dev(p), dev(t)
         e = dev(e) if e is not None else None
-    r = c.solve_batch(p, t, e, N=N, derivative=derivative, want_free=want_free)
+    r = c.solve_batch(p, t, e, N=N, derivative=derivative, want_free=want_free, layout=layout)
     if device:
         import torch
 
         torch.cuda.synchronize()
-    return (aos(host(r["coeffs"])), host(r["cost"]), aos(host(r["free"])) if want_free else None,
+    conv = aos if layout == "soa" else (lambda x: x)
+    return (conv(host(r["coeffs"])), host(r["cost"]), conv(host(r["free"])) if want_free else None,
             host(r["status"]))
 
 
@@ -54,7 +60,7 @@ def test_reference_parameter_sets(po, name):
     if s.n_free:
         # getFreeConstraints order: vertex-major, derivative-minor (LIN_H:289-296)
         K, D = prob["K"], prob["D"]
-        want = s.d_p.reshape(D, K - 1, 4).transpose(1, 2, 0)
+        want = s.d_p.reshape(D, K - 1, 4)
         assert np.abs(free[0] - want).max() <= tol * np.abs(want).max()
 
 
@@ -85,11 +91,13 @@ def test_two_vertices_setup_golden():
     assert np.abs(coeffs[0, 0, 0] - exact).max() < 1e-15
 
 
-@pytest.mark.parametrize("K,D,der", [(10, 3, 4), (10, 1, 4), (5, 3, 3), (5, 3, 2), (2, 3, 4), (3, 2, 4)])
-def test_random_batch_vs_oracle(po, K, D, der):
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+@pytest.mark.parametrize("K,D,der", [(10, 3, 4), (10, 1, 4), (5, 3, 3), (5, 3, 2), (2, 3, 4), (3, 2, 4),
+                                     (4, 3, 4), (7, 4, 4), (9, 3, 1), (6, 1, 0)])
+def test_random_batch_vs_oracle(po, K, D, der, layout):
     B = 2048 if (K, D, der) == (10, 3, 4) else 256
     pos, times = random_problems(po, B, K, D, seed0=1000)
-    coeffs, cost, free, status = gpu_solve(pos, times, der)
+    coeffs, cost, free, status = gpu_solve(pos, times, der, layout=layout)
     ref_c, ref_cost = po.solve_canonical_batch(pos, times, N=N, derivative=der, n_threads=8)
     assert np.all(status == 0)
     tol = TOL if der == 4 else 1e-8
@@ -132,16 +140,30 @@ def test_nonzero_end_derivatives(po):
         assert abs(cost[b] - s.cost) <= TOL * abs(s.cost)
 
 
-def test_host_memory_mode_matches_device_mode(po):
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_host_memory_mode_matches_device_mode(po, layout):
     pos, times = random_problems(po, 777, 10, 3, seed0=3)
-    a = gpu_solve(pos, times, 4, device=True)
+    a = gpu_solve(pos, times, 4, device=True, layout=layout)
     os.environ["MTG_HOST_CHUNK"] = "200"   # force several ragged chunks through all staging slots
     try:
-        b = gpu_solve(pos, times, 4, device=False)
+        b = gpu_solve(pos, times, 4, device=False, layout=layout)
     finally:
         del os.environ["MTG_HOST_CHUNK"]
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+    c = gpu_solve(pos, times, 4, device=True, layout="soa")
+    for x, y in zip(a, c):   # the layout never changes a result bit
+        assert np.array_equal(x, y)
+
+
+def test_translation_invariance(po):
+    """H annihilates constant offsets: a 1e6 m shift of all vertices changes only c_0."""
+    pos, times = random_problems(po, 64, 10, 3, seed0=11)
+    c0, cost0, free0, _ = gpu_solve(pos, times, 4)
+    c1, cost1, free1, _ = gpu_solve(pos + 1.0e6, times, 4)
+    assert np.allclose(c0[..., 1:], c1[..., 1:], rtol=1e-9, atol=0)
+    assert np.allclose(cost0, cost1, rtol=1e-9) and np.allclose(free0, free1, rtol=1e-9, atol=1e-12)
+    assert np.allclose(c1[..., 0] - 1.0e6, c0[..., 0], rtol=0, atol=1e-9)
 
 
 def test_status_flags_and_argument_errors(po):
@@ -159,6 +181,11 @@ def test_status_flags_and_argument_errors(po):
     c = ctx()
     r = c.solve_batch(np.zeros((5, 3, 0)), np.zeros((4, 0)))
     assert r["coeffs"].shape == (4, 3, 10, 0)
+    # inf / nan times
+    times[3, 2] = np.inf
+    times[5, 0] = np.nan
+    _, _, _, status = gpu_solve(pos, times, 4)
+    assert status[3] & 1 and status[5] & 1
 
 
 def _powers(t, n):
@@ -196,7 +223,8 @@ def test_full_size_properties(po):
             assert np.abs(at0[:, 0]).max() < 1e-6 and np.abs(atT[:, -1]).max() < 1e-6
         assert np.abs(atT[:, :-1] - at0[:, 1:]).max() < 1e-6 * max(1.0, scale)
         if k >= 1:  # and the solved free derivatives are those values
-            assert np.abs(at0[:, 1:] - free[:, :, k - 1, :]).max() < 1e-9 * max(1.0, np.abs(free).max())
+            want = np.moveaxis(free[:, :, :, k - 1], 1, 2)   # [B,D,K-1] -> [B,K-1,D]
+            assert np.abs(at0[:, 1:] - want).max() < 1e-9 * max(1.0, np.abs(free).max())
     # cost == 0.5 sum c^T Q c with Q of LIN_I:557-573
     d = 4
     a = np.arange(d, N)
