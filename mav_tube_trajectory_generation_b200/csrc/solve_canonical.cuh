@@ -146,6 +146,7 @@ __device__ __forceinline__ double emit_segment(const SolveCanonicalParams& p, in
     for (int i = 0; i < N; ++i) {
       if (i < nq) {
         double w = MTG_W(i, HN) * dlt;
+        if (p.derivative == 0) w = fma(MTG_W(i, 0) + MTG_W(i, HN), ds[dim][0], w);
 #pragma unroll
         for (int m = 1; m < HN; ++m) {
           w = fma(MTG_W(i, m), dh[m], w);
@@ -318,6 +319,14 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
 #pragma unroll
       for (int dim = 0; dim < D; ++dim) r[dim][k] = -a_l * (p_cur[dim] - p_prev[dim]);
     }
+    if (d == 0) {  // only a position cost is not translation invariant: H[r][0] + H[r][h] != 0
+#pragma unroll
+      for (int k = 0; k < NF; ++k) {
+        const double a = (MTG_H1(HN + 1 + k, 0) + MTG_H1(HN + 1 + k, HN)) * pl[k + 1];
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) r[dim][k] = fma(-a, p_prev[dim], r[dim][k]);
+      }
+    }
     if (j == 1 && have_end) {
 #pragma unroll
       for (int k = 0; k < NF; ++k)
@@ -356,6 +365,14 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
       const double a_r = MTG_H1(1 + k, HN) * pr[k + 1];
 #pragma unroll
       for (int dim = 0; dim < D; ++dim) r[dim][k] = fma(-a_r, p_next[dim] - p_cur[dim], r[dim][k]);
+    }
+    if (d == 0) {
+#pragma unroll
+      for (int k = 0; k < NF; ++k) {
+        const double a = (MTG_H1(1 + k, 0) + MTG_H1(1 + k, HN)) * pr[k + 1];
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) r[dim][k] = fma(-a, p_cur[dim], r[dim][k]);
+      }
     }
     double linv[NF];
     chol_lower<NF>(S, linv, st);
