@@ -125,6 +125,62 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc,
                     const double* seg_times, double* coeffs, double* cost,
                     double* free_constraints, uint32_t* status, void* stream);
 
+
+/* --------------------------------------------- E1..E4: sampled evaluation
+ * All take the solve's output layout: coeffs [K][D][N], seg_times [K] records.
+ *
+ * mtg_max_time_batch: Trajectory::getMaxTime() [trajectory.h:63-72,84]: the
+ * segment times summed in segment order. max_time [B]. */
+int mtg_max_time_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* seg_times,
+                       double* max_time, void* stream);
+
+/* mtg_eval_range_batch: Trajectory::evaluateRange(t_start, t_end, dt, derivative,
+ * &result, &sampling_times) [src/trajectory.cpp:74-134] for every trajectory, with
+ * Segment::evaluate / Polynomial::evaluate [src/segment.cpp:51-58, polynomial.h:136-149].
+ * The reference's serial recurrence (acc += dt, tau += dt, tau -= T_i on a strict
+ * '>' crossing, loop counter restarting at the START of the segment holding
+ * t_start) is replayed bit-exactly, so n_samples, sampling_times and segment_idx
+ * equal the reference's; sample values use fused multiply-adds (value parity).
+ *  t_start, t_end, dt [B]   per-trajectory range (the reference takes scalars per call)
+ *  samples        [max_samples][D]  out or NULL   (rows >= n_samples[b] are not written)
+ *  sampling_times [max_samples]     out or NULL   (the reference's accumulated_time)
+ *  segment_idx    [max_samples]     out or NULL
+ *  n_samples      [B] int32         out or NULL
+ * status: MTG_ST_OUT_OF_RANGE if t_start is beyond the trajectory or dt <= 0
+ * (reference: LOG(ERROR) + empty result; t_start == max time is UB there, an error
+ * here); MTG_ST_TRUNCATED if more than max_samples samples exist. */
+int mtg_eval_range_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                         const double* seg_times, const double* t_start, const double* t_end,
+                         const double* dt, int derivative, int max_samples, double* samples,
+                         double* sampling_times, int32_t* segment_idx, int32_t* n_samples,
+                         uint32_t* status, void* stream);
+
+/* mtg_eval_at_batch: Trajectory::evaluate(t, derivative) [src/trajectory.cpp:41-72]
+ * at M query times per trajectory. t [M], out [M][D], segment_idx [M] (or NULL;
+ * -1 where t is out of range, in which case out is zero like the reference). */
+int mtg_eval_at_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                      const double* seg_times, const double* t, int M, int derivative, double* out,
+                      int32_t* segment_idx, uint32_t* status, void* stream);
+
+/* mtg_feasibility_batch: fused sweep over the evaluateRange sample set: position,
+ * velocity and acceleration of every sample, per-sample flags and per-trajectory
+ * maxima. Sampled forms of: the v/a limit check [test_utils.h:43-54,
+ * impl/polynomial_optimization_nonlinear_impl.h:2686-2733] and the tube / end-cap
+ * geometry that the reference only hands to MOSEK
+ * [impl/polynomial_optimization_qcqp_impl.h:369-474] (PARITY UNPINNED by any
+ * reference test; D = 3 only).
+ *  positions [K+1][3], radii [K][2] (pair<first,second> per segment, QC_H:55): tube
+ *            check inputs, both NULL to skip it (bit2 is then always set)
+ *  samples [max_samples][D] out or NULL (positions)
+ *  flags   [max_samples] uint8 out or NULL: bit0 |v| <= v_max, bit1 |a| <= a_max, bit2 in tube
+ *  max_v, max_a [B] out or NULL; feasible [B] uint8 out or NULL (all samples carry all bits) */
+int mtg_feasibility_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                          const double* seg_times, const double* positions, const double* radii,
+                          double v_max, double a_max, const double* t_start, const double* t_end,
+                          const double* dt, int max_samples, double* samples, uint8_t* flags,
+                          double* max_v, double* max_a, uint8_t* feasible, int32_t* n_samples,
+                          uint32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,13 @@ def load() -> C.CDLL:
     lib.mtg_sync.argtypes = [vp, vp]
     lib.mtg_get_tables.argtypes = [C.c_int, C.c_int, dp, dp]
     lib.mtg_solve_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, u32p, vp]
+    lib.mtg_max_time_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, vp]
+    lib.mtg_eval_range_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, C.c_int, C.c_int,
+                                         dp, dp, vp, vp, u32p, vp]
+    lib.mtg_eval_at_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, C.c_int, C.c_int, dp, vp,
+                                      u32p, vp]
+    lib.mtg_feasibility_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, C.c_double,
+                                          C.c_double, dp, dp, dp, C.c_int, dp, vp, dp, dp, vp, vp, u32p, vp]
     _lib = lib
     return lib
 
@@ -192,3 +199,103 @@ class Context:
                                        _ptr(status), self._stream(mode, stream))
         self._check(rc, "mtg_solve_batch")
         return dict(coeffs=coeffs, cost=cost, free=free, status=status)
+
+    # ------------------------------------------------------------- evaluation
+    def _shape_kdn(self, coeffs, aos):
+        if aos:
+            B, K, D, N = coeffs.shape
+        else:
+            K, D, N, B = coeffs.shape
+        return B, K, D, N
+
+    def _desc_for(self, coeffs, layout):
+        aos = layout == "aos"
+        B, K, D, N = self._shape_kdn(coeffs, aos)
+        mode = self._mode(coeffs)
+        # derivative_to_optimize only selects the constant tables; evaluation uses the base table
+        return aos, B, K, D, N, mode, ProblemDesc(B, K, D, N, N // 2 - 1, mode,
+                                                  LAYOUT_AOS if aos else LAYOUT_SOA)
+
+    def _bvec(self, like, x, B):
+        """[B] float64 vector in the memory space of `like` from a scalar or array."""
+        if _is_torch(like):
+            import torch
+
+            if _is_torch(x):
+                return x.to(device=like.device, dtype=torch.float64).contiguous()
+            return torch.as_tensor(np.broadcast_to(np.asarray(x, dtype=np.float64), (B,)).copy(),
+                                   device=like.device)
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (B,)))
+
+    def max_time_batch(self, seg_times, layout="soa", stream=None):
+        aos = layout == "aos"
+        B, K = seg_times.shape if aos else seg_times.shape[::-1]
+        mode = self._mode(seg_times)
+        desc = ProblemDesc(B, K, 1, 10, 4, mode, LAYOUT_AOS if aos else LAYOUT_SOA)
+        out = self._empty(seg_times, (B,))
+        self._check(self._lib.mtg_max_time_batch(self._h, C.byref(desc), _ptr(seg_times), _ptr(out),
+                                                 self._stream(mode, stream)), "mtg_max_time_batch")
+        return out
+
+    def eval_range_batch(self, coeffs, seg_times, t_start, t_end, dt, derivative=0, max_samples=1024,
+                         layout="soa", want_samples=True, want_times=False, want_segments=False,
+                         out=None, stream=None):
+        """mtg_eval_range_batch. soa: samples [S,D,B], times/segments [S,B]; aos: [B,S,D], [B,S]."""
+        aos, B, K, D, N, mode, desc = self._desc_for(coeffs, layout)
+        S = max_samples
+        out = out or {}
+        t0, t1, dtv = (self._bvec(coeffs, x, B) for x in (t_start, t_end, dt))
+        samples = out.get("samples")
+        if want_samples and samples is None:
+            samples = self._empty(coeffs, (B, S, D) if aos else (S, D, B))
+        times = self._empty(coeffs, (B, S) if aos else (S, B)) if want_times else None
+        segs = self._empty(coeffs, (B, S) if aos else (S, B), "i4") if want_segments else None
+        n = out.get("n_samples")
+        if n is None:
+            n = self._empty(coeffs, (B,), "i4")
+        status = self._empty(coeffs, (B,), "u4")
+        rc = self._lib.mtg_eval_range_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(seg_times), _ptr(t0),
+                                            _ptr(t1), _ptr(dtv), derivative, S, _ptr(samples), _ptr(times),
+                                            _ptr(segs), _ptr(n), _ptr(status), self._stream(mode, stream))
+        self._check(rc, "mtg_eval_range_batch")
+        return dict(samples=samples, sampling_times=times, segment_idx=segs, n_samples=n, status=status)
+
+    def eval_at_batch(self, coeffs, seg_times, t, derivative=0, layout="soa", stream=None):
+        """mtg_eval_at_batch. t: soa [M,B] / aos [B,M]. Returns out soa [M,D,B] / aos [B,M,D]."""
+        aos, B, K, D, N, mode, desc = self._desc_for(coeffs, layout)
+        M = t.shape[1] if aos else t.shape[0]
+        out = self._empty(coeffs, (B, M, D) if aos else (M, D, B))
+        segs = self._empty(coeffs, (B, M) if aos else (M, B), "i4")
+        status = self._empty(coeffs, (B,), "u4")
+        rc = self._lib.mtg_eval_at_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(seg_times), _ptr(t), M,
+                                         derivative, _ptr(out), _ptr(segs), _ptr(status),
+                                         self._stream(mode, stream))
+        self._check(rc, "mtg_eval_at_batch")
+        return dict(out=out, segment_idx=segs, status=status)
+
+    def feasibility_batch(self, coeffs, seg_times, t_start, t_end, dt, v_max, a_max, positions=None,
+                          radii=None, max_samples=1024, layout="soa", want_samples=False, want_flags=True,
+                          out=None, stream=None):
+        """mtg_feasibility_batch. positions soa [K+1,3,B] / aos [B,K+1,3]; radii soa [K,2,B] / aos [B,K,2]."""
+        aos, B, K, D, N, mode, desc = self._desc_for(coeffs, layout)
+        S = max_samples
+        out = out or {}
+        t0, t1, dtv = (self._bvec(coeffs, x, B) for x in (t_start, t_end, dt))
+        samples = out.get("samples")
+        if want_samples and samples is None:
+            samples = self._empty(coeffs, (B, S, D) if aos else (S, D, B))
+        flags = out.get("flags")
+        if want_flags and flags is None:
+            flags = self._empty(coeffs, (B, S) if aos else (S, B), "u1")
+        max_v, max_a = self._empty(coeffs, (B,)), self._empty(coeffs, (B,))
+        feasible = self._empty(coeffs, (B,), "u1")
+        n = self._empty(coeffs, (B,), "i4")
+        status = self._empty(coeffs, (B,), "u4")
+        rc = self._lib.mtg_feasibility_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(seg_times),
+                                             _ptr(positions), _ptr(radii), float(v_max), float(a_max),
+                                             _ptr(t0), _ptr(t1), _ptr(dtv), S, _ptr(samples), _ptr(flags),
+                                             _ptr(max_v), _ptr(max_a), _ptr(feasible), _ptr(n), _ptr(status),
+                                             self._stream(mode, stream))
+        self._check(rc, "mtg_feasibility_batch")
+        return dict(samples=samples, flags=flags, max_v=max_v, max_a=max_a, feasible=feasible, n_samples=n,
+                    status=status)

@@ -16,6 +16,7 @@
 #include "device_tables.cuh"
 
 #include "solve_canonical.cuh"
+#include "eval.cuh"
 
 namespace {
 
@@ -50,8 +51,7 @@ struct mtg_ctx {
   uint64_t launches = 0;
   cudaStream_t stage_stream[kStageSlots] = {nullptr, nullptr, nullptr};
   // per staging slot: inputs / outputs of one chunk (HOST-memory mode)
-  DeviceBuffer stage_in[kStageSlots];
-  DeviceBuffer stage_out[kStageSlots];
+  DeviceBuffer stage[kStageSlots];
 };
 
 namespace {
@@ -206,6 +206,111 @@ cudaError_t d2h_chunk(void* dst, size_t B, size_t b0, const void* src, size_t C,
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// One batched tensor of a host-memory call.
+struct HostTensor {
+  const void* host;  // caller pointer (may be null = absent)
+  size_t rec;        // elements per trajectory record
+  size_t elem;       // bytes per element
+  bool input;        // copied H2D before the launch, else D2H after it
+  bool vector;       // a plain [B] vector: contiguous in both layouts
+  void* dev;         // chunk-local device pointer handed to the launcher
+};
+
+// Host-memory mode shared by all entry points: splits the batch into chunks,
+// round-robins them over kStageSlots streams (H2D -> kernels -> D2H per chunk, so
+// that copies of one chunk overlap the kernels and copies of its neighbours) and
+// returns when every output is in place. launch(nb, C, stream) reads ts[i].dev.
+template <class Launch>
+int run_chunked(mtg_ctx* ctx, cudaStream_t user_stream, size_t B, bool aos, std::vector<HostTensor>& ts,
+                Launch&& launch) {
+  size_t bytes_per_traj = 0;
+  for (auto& t : ts)
+    if (t.host) bytes_per_traj += t.rec * t.elem;
+  if (bytes_per_traj == 0 || B == 0) return MTG_OK;
+  size_t C = 8192;
+  if (const char* env = std::getenv("MTG_HOST_CHUNK")) C = std::max(1, std::atoi(env));
+  const size_t budget = (size_t)384 << 20;  // per staging slot
+  C = std::max<size_t>(1, std::min(C, budget / bytes_per_traj));
+  C = std::min(C, B);
+  size_t slot_bytes = 0;
+  for (auto& t : ts)
+    if (t.host) slot_bytes += align256(t.rec * t.elem * C);
+  const int n_chunks = (int)((B + C - 1) / C);
+  const int slots = std::min(kStageSlots, n_chunks);
+  for (int s = 0; s < slots; ++s)
+    if (ctx->stage[s].ensure(slot_bytes)) return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of staging buffers failed");
+  MTG_CUDA_TRY(cudaStreamSynchronize(user_stream));  // order after work queued on the caller's stream
+  for (int c = 0; c < n_chunks; ++c) {
+    const int s = c % kStageSlots;
+    cudaStream_t st = ctx->stage_stream[s];
+    const size_t b0 = (size_t)c * C, nb = std::min(C, B - b0);
+    char* base = (char*)ctx->stage[s].ptr;
+    size_t off = 0;
+    for (auto& t : ts) {
+      t.dev = nullptr;
+      if (!t.host) continue;
+      t.dev = base + off;
+      off += align256(t.rec * t.elem * C);
+      if (t.input) MTG_CUDA_TRY(h2d_chunk(t.dev, C, t.host, B, b0, nb, t.rec, t.elem, aos || t.vector, st));
+    }
+    const int rc = launch((int)nb, (int)C, st);
+    if (rc) return rc;
+    for (auto& t : ts)
+      if (t.host && !t.input)
+        MTG_CUDA_TRY(d2h_chunk(const_cast<void*>(t.host), B, b0, t.dev, C, nb, t.rec, t.elem, aos || t.vector, st));
+  }
+  for (int s = 0; s < slots; ++s) MTG_CUDA_TRY(cudaStreamSynchronize(ctx->stage_stream[s]));
+  return MTG_OK;
+}
+
+template <int NT, bool AOS>
+int launch_eval_range_d(mtg_ctx* ctx, int D, const mtg::EvalParams& p, cudaStream_t s) {
+  const int block = 128, grid = (p.nb + block - 1) / block;
+  if (grid == 0) return MTG_OK;
+  switch (D) {
+    case 1: mtg::eval_range_kernel<NT, 1, AOS><<<grid, block, 0, s>>>(p); break;
+    case 2: mtg::eval_range_kernel<NT, 2, AOS><<<grid, block, 0, s>>>(p); break;
+    case 3: mtg::eval_range_kernel<NT, 3, AOS><<<grid, block, 0, s>>>(p); break;
+    case 4: mtg::eval_range_kernel<NT, 4, AOS><<<grid, block, 0, s>>>(p); break;
+    default: return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "D must be 1..4");
+  }
+  ++ctx->launches;
+  MTG_CUDA_TRY(cudaGetLastError());
+  return MTG_OK;
+}
+int launch_eval_range(mtg_ctx* ctx, int D, bool aos, const mtg::EvalParams& p, cudaStream_t s) {
+  if (p.N == 10) return aos ? launch_eval_range_d<10, true>(ctx, D, p, s) : launch_eval_range_d<10, false>(ctx, D, p, s);
+  return aos ? launch_eval_range_d<12, true>(ctx, D, p, s) : launch_eval_range_d<12, false>(ctx, D, p, s);
+}
+
+template <int NT, bool AOS>
+int launch_feasibility_d(mtg_ctx* ctx, int D, const mtg::EvalParams& p, cudaStream_t s) {
+  const int block = 128, grid = (p.nb + block - 1) / block;
+  if (grid == 0) return MTG_OK;
+  switch (D) {
+    case 1: mtg::feasibility_kernel<NT, 1, AOS><<<grid, block, 0, s>>>(p); break;
+    case 2: mtg::feasibility_kernel<NT, 2, AOS><<<grid, block, 0, s>>>(p); break;
+    case 3: mtg::feasibility_kernel<NT, 3, AOS><<<grid, block, 0, s>>>(p); break;
+    case 4: mtg::feasibility_kernel<NT, 4, AOS><<<grid, block, 0, s>>>(p); break;
+    default: return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "D must be 1..4");
+  }
+  ++ctx->launches;
+  MTG_CUDA_TRY(cudaGetLastError());
+  return MTG_OK;
+}
+int launch_feasibility(mtg_ctx* ctx, int D, bool aos, const mtg::EvalParams& p, cudaStream_t s) {
+  if (p.N == 10) return aos ? launch_feasibility_d<10, true>(ctx, D, p, s) : launch_feasibility_d<10, false>(ctx, D, p, s);
+  return aos ? launch_feasibility_d<12, true>(ctx, D, p, s) : launch_feasibility_d<12, false>(ctx, D, p, s);
+}
+
+int validate_eval(mtg_ctx* ctx, const mtg_problem_desc* desc, int derivative, int max_samples) {
+  int rc = validate_desc(ctx, desc);
+  if (rc) return rc;
+  if (derivative < 0) return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "derivative must be >= 0");
+  if (max_samples < 0) return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "max_samples must be >= 0");
+  return MTG_OK;
+}
+
 }  // namespace
 
 // ================================================================== C ABI
@@ -243,8 +348,7 @@ void mtg_destroy(mtg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (int i = 0; i < kStageSlots; ++i) {
-    ctx->stage_in[i].release();
-    ctx->stage_out[i].release();
+    ctx->stage[i].release();
     if (ctx->stage_stream[i]) cudaStreamDestroy(ctx->stage_stream[i]);
   }
   delete ctx;
@@ -304,60 +408,203 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* po
     return launch_solve_canonical(ctx, N, D, aos, p, stream);
   }
 
-  // ---- host-memory mode: pipelined chunks over kStageSlots streams
+  // ---- host-memory mode
   const size_t rec_pos = (size_t)(K + 1) * D, rec_end = (size_t)2 * NF * D, rec_t = K;
   const size_t rec_c = (size_t)K * D * N, rec_free = (size_t)std::max(K - 1, 0) * NF * D;
-  const size_t in_rows = rec_pos + (end_derivatives ? rec_end : 0) + rec_t;
-  const size_t out_rows = rec_c + (cost ? 1 : 0) + (free_constraints ? rec_free : 0);
-  size_t C = 8192;
-  if (const char* env = std::getenv("MTG_HOST_CHUNK")) C = std::max(1, std::atoi(env));
-  C = std::min<size_t>(C, (size_t)B);
-  const size_t in_bytes = align256(in_rows * C * 8);
-  const size_t out_bytes = align256(out_rows * C * 8) + align256(C * 4);
-  const int n_chunks = (int)((B + C - 1) / C);
-  const int slots = std::min(kStageSlots, n_chunks);
-  for (int s = 0; s < slots; ++s)
-    if (ctx->stage_in[s].ensure(in_bytes) || ctx->stage_out[s].ensure(out_bytes))
-      return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of staging buffers failed");
-  // order after work already queued on the caller's stream
-  MTG_CUDA_TRY(cudaStreamSynchronize(stream));
-  for (int c = 0; c < n_chunks; ++c) {
-    const int s = c % kStageSlots;
-    cudaStream_t st = ctx->stage_stream[s];
-    const size_t b0 = (size_t)c * C, nb = std::min(C, (size_t)B - b0);
-    double* din = (double*)ctx->stage_in[s].ptr;
-    double* d_pos = din;
-    double* d_end = d_pos + rec_pos * C;
-    double* d_t = d_end + (end_derivatives ? rec_end * C : 0);
-    double* dout = (double*)ctx->stage_out[s].ptr;
-    double* d_c = dout;
-    double* d_cost = d_c + rec_c * C;
-    double* d_free = d_cost + (cost ? C : 0);
-    uint32_t* d_status = (uint32_t*)((char*)dout + align256(out_rows * C * 8));
-    MTG_CUDA_TRY(h2d_chunk(d_pos, C, positions, B, b0, nb, rec_pos, 8, aos, st));
-    if (end_derivatives) MTG_CUDA_TRY(h2d_chunk(d_end, C, end_derivatives, B, b0, nb, rec_end, 8, aos, st));
-    MTG_CUDA_TRY(h2d_chunk(d_t, C, seg_times, B, b0, nb, rec_t, 8, aos, st));
-    p.positions = d_pos;
-    p.end_derivatives = end_derivatives ? d_end : nullptr;
-    p.seg_times = d_t;
-    p.coeffs = d_c;
-    p.cost = cost ? d_cost : nullptr;
-    p.free_constraints = free_constraints ? d_free : nullptr;
-    p.status = status ? d_status : nullptr;
-    p.B = (int)C;
+  std::vector<HostTensor> ts = {
+      {positions, rec_pos, 8, true, false, nullptr},  {end_derivatives, rec_end, 8, true, false, nullptr},
+      {seg_times, rec_t, 8, true, false, nullptr},    {coeffs, rec_c, 8, false, false, nullptr},
+      {cost, 1, 8, false, true, nullptr},             {rec_free ? free_constraints : nullptr, rec_free, 8, false, false, nullptr},
+      {status, 1, 4, false, true, nullptr}};
+  return run_chunked(ctx, stream, (size_t)B, aos, ts, [&](int nb, int C, cudaStream_t st) {
+    p.positions = (const double*)ts[0].dev;
+    p.end_derivatives = (const double*)ts[1].dev;
+    p.seg_times = (const double*)ts[2].dev;
+    p.coeffs = (double*)ts[3].dev;
+    p.cost = (double*)ts[4].dev;
+    p.free_constraints = (double*)ts[5].dev;
+    p.status = (uint32_t*)ts[6].dev;
+    p.B = C;
     p.b0 = 0;
-    p.nb = (int)nb;
+    p.nb = nb;
     p.vec_ok = 1;
-    rc = launch_solve_canonical(ctx, N, D, aos, p, st);
-    if (rc) return rc;
-    MTG_CUDA_TRY(d2h_chunk(coeffs, B, b0, d_c, C, nb, rec_c, 8, aos, st));
-    if (cost) MTG_CUDA_TRY(d2h_chunk(cost, B, b0, d_cost, C, nb, 1, 8, true, st));
-    if (free_constraints && rec_free)
-      MTG_CUDA_TRY(d2h_chunk(free_constraints, B, b0, d_free, C, nb, rec_free, 8, aos, st));
-    if (status) MTG_CUDA_TRY(d2h_chunk(status, B, b0, d_status, C, nb, 1, 4, true, st));
+    return launch_solve_canonical(ctx, N, D, aos, p, st);
+  });
+}
+
+/* ------------------------------------------------------------ evaluation */
+int mtg_max_time_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* seg_times, double* max_time,
+                       void* stream_) {
+  int rc = validate_desc(ctx, desc);
+  if (rc) return rc;
+  if (!seg_times || !max_time) return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "seg_times and max_time are required");
+  if (desc->B == 0) return MTG_OK;
+  MTG_CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool aos = desc->layout == MTG_LAYOUT_AOS;
+  const int K = desc->K;
+  auto launch = [&](const double* t, double* out, int Bld, int nb, cudaStream_t st) {
+    const int block = 256, grid = (nb + block - 1) / block;
+    if (aos)
+      mtg::max_time_kernel<true><<<grid, block, 0, st>>>(t, out, Bld, 0, nb, K);
+    else
+      mtg::max_time_kernel<false><<<grid, block, 0, st>>>(t, out, Bld, 0, nb, K);
+    ++ctx->launches;
+    return cudaGetLastError() == cudaSuccess ? MTG_OK : fail(ctx, MTG_ERR_CUDA, "max_time_kernel launch failed");
+  };
+  if (desc->memory == MTG_MEM_DEVICE) return launch(seg_times, max_time, desc->B, desc->B, stream);
+  std::vector<HostTensor> ts = {{seg_times, (size_t)K, 8, true, false, nullptr}, {max_time, 1, 8, false, true, nullptr}};
+  return run_chunked(ctx, stream, (size_t)desc->B, aos, ts, [&](int nb, int C, cudaStream_t st) {
+    return launch((const double*)ts[0].dev, (double*)ts[1].dev, C, nb, st);
+  });
+}
+
+int mtg_eval_range_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                         const double* seg_times, const double* t_start, const double* t_end,
+                         const double* dt, int derivative, int max_samples, double* samples,
+                         double* sampling_times, int32_t* segment_idx, int32_t* n_samples,
+                         uint32_t* status, void* stream_) {
+  int rc = validate_eval(ctx, desc, derivative, max_samples);
+  if (rc) return rc;
+  if (!coeffs || !seg_times || !t_start || !t_end || !dt)
+    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "coeffs, seg_times, t_start, t_end and dt are required");
+  if (desc->B == 0) return MTG_OK;
+  MTG_CUDA_TRY(cudaSetDevice(ctx->device));
+  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool aos = desc->layout == MTG_LAYOUT_AOS;
+  const int B = desc->B, K = desc->K, D = desc->D, N = desc->N;
+  mtg::EvalParams p = {};
+  p.K = K;
+  p.N = N;
+  p.derivative = derivative;
+  p.max_samples = max_samples;
+  if (desc->memory == MTG_MEM_DEVICE) {
+    p.coeffs = coeffs; p.seg_times = seg_times; p.t_start = t_start; p.t_end = t_end; p.dt = dt;
+    p.samples = samples; p.sampling_times = sampling_times; p.segment_idx = segment_idx;
+    p.n_samples = n_samples; p.status = status;
+    p.B = B; p.b0 = 0; p.nb = B;
+    p.vec_ok = ((uintptr_t)coeffs % 16 == 0) ? 1 : 0;
+    return launch_eval_range(ctx, D, aos, p, stream);
   }
-  for (int s = 0; s < slots; ++s) MTG_CUDA_TRY(cudaStreamSynchronize(ctx->stage_stream[s]));
-  return MTG_OK;
+  const size_t S = (size_t)max_samples;
+  std::vector<HostTensor> ts = {
+      {coeffs, (size_t)K * D * N, 8, true, false, nullptr}, {seg_times, (size_t)K, 8, true, false, nullptr},
+      {t_start, 1, 8, true, true, nullptr},  {t_end, 1, 8, true, true, nullptr},
+      {dt, 1, 8, true, true, nullptr},       {S ? samples : nullptr, S * D, 8, false, false, nullptr},
+      {S ? sampling_times : nullptr, S, 8, false, false, nullptr},
+      {S ? segment_idx : nullptr, S, 4, false, false, nullptr},
+      {n_samples, 1, 4, false, true, nullptr}, {status, 1, 4, false, true, nullptr}};
+  return run_chunked(ctx, stream, (size_t)B, aos, ts, [&](int nb, int C, cudaStream_t st) {
+    p.coeffs = (const double*)ts[0].dev; p.seg_times = (const double*)ts[1].dev;
+    p.t_start = (const double*)ts[2].dev; p.t_end = (const double*)ts[3].dev; p.dt = (const double*)ts[4].dev;
+    p.samples = (double*)ts[5].dev; p.sampling_times = (double*)ts[6].dev; p.segment_idx = (int32_t*)ts[7].dev;
+    p.n_samples = (int32_t*)ts[8].dev; p.status = (uint32_t*)ts[9].dev;
+    p.B = C; p.b0 = 0; p.nb = nb; p.vec_ok = 1;
+    return launch_eval_range(ctx, D, aos, p, st);
+  });
+}
+
+int mtg_eval_at_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                      const double* seg_times, const double* t, int M, int derivative, double* out,
+                      int32_t* segment_idx, uint32_t* status, void* stream_) {
+  int rc = validate_eval(ctx, desc, derivative, M);
+  if (rc) return rc;
+  if (!coeffs || !seg_times || !t || !out)
+    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "coeffs, seg_times, t and out are required");
+  if (desc->B == 0 || M == 0) return MTG_OK;
+  MTG_CUDA_TRY(cudaSetDevice(ctx->device));
+  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool aos = desc->layout == MTG_LAYOUT_AOS;
+  const int B = desc->B, K = desc->K, D = desc->D, N = desc->N;
+  mtg::EvalAtParams p = {};
+  p.K = K; p.N = N; p.D = D; p.M = M; p.derivative = derivative;
+  auto launch = [&](cudaStream_t st) {
+    if (p.status) {
+      cudaError_t e = cudaMemsetAsync(p.status, 0, sizeof(uint32_t) * p.nb, st);
+      if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMemsetAsync(status)");
+    }
+    const long long total = (long long)p.nb * M;
+    const int block = 256;
+    const long long grid = (total + block - 1) / block;
+    if (aos)
+      mtg::eval_at_kernel<true><<<(unsigned)grid, block, 0, st>>>(p);
+    else
+      mtg::eval_at_kernel<false><<<(unsigned)grid, block, 0, st>>>(p);
+    ++ctx->launches;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MTG_OK : cuda_fail(ctx, e, "eval_at_kernel");
+  };
+  if (desc->memory == MTG_MEM_DEVICE) {
+    p.coeffs = coeffs; p.seg_times = seg_times; p.t = t; p.out = out; p.segment_idx = segment_idx;
+    p.status = status; p.B = B; p.b0 = 0; p.nb = B;
+    return launch(stream);
+  }
+  std::vector<HostTensor> ts = {
+      {coeffs, (size_t)K * D * N, 8, true, false, nullptr}, {seg_times, (size_t)K, 8, true, false, nullptr},
+      {t, (size_t)M, 8, true, false, nullptr},              {out, (size_t)M * D, 8, false, false, nullptr},
+      {segment_idx, (size_t)M, 4, false, false, nullptr},   {status, 1, 4, false, true, nullptr}};
+  return run_chunked(ctx, stream, (size_t)B, aos, ts, [&](int nb, int C, cudaStream_t st) {
+    p.coeffs = (const double*)ts[0].dev; p.seg_times = (const double*)ts[1].dev; p.t = (const double*)ts[2].dev;
+    p.out = (double*)ts[3].dev; p.segment_idx = (int32_t*)ts[4].dev; p.status = (uint32_t*)ts[5].dev;
+    p.B = C; p.b0 = 0; p.nb = nb;
+    return launch(st);
+  });
+}
+
+int mtg_feasibility_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                          const double* seg_times, const double* positions, const double* radii,
+                          double v_max, double a_max, const double* t_start, const double* t_end,
+                          const double* dt, int max_samples, double* samples, uint8_t* flags,
+                          double* max_v, double* max_a, uint8_t* feasible, int32_t* n_samples,
+                          uint32_t* status, void* stream_) {
+  int rc = validate_eval(ctx, desc, 0, max_samples);
+  if (rc) return rc;
+  if (!coeffs || !seg_times || !t_start || !t_end || !dt)
+    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "coeffs, seg_times, t_start, t_end and dt are required");
+  if (radii && (desc->D != 3 || !positions))
+    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "the tube check needs D == 3 and the vertex positions");
+  if (desc->B == 0) return MTG_OK;
+  MTG_CUDA_TRY(cudaSetDevice(ctx->device));
+  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool aos = desc->layout == MTG_LAYOUT_AOS;
+  const int B = desc->B, K = desc->K, D = desc->D, N = desc->N;
+  mtg::EvalParams p = {};
+  p.K = K; p.N = N; p.derivative = 0; p.max_samples = max_samples; p.v_max = v_max; p.a_max = a_max;
+  if (desc->memory == MTG_MEM_DEVICE) {
+    p.coeffs = coeffs; p.seg_times = seg_times; p.t_start = t_start; p.t_end = t_end; p.dt = dt;
+    p.samples = samples; p.flags = flags; p.max_v = max_v; p.max_a = max_a; p.feasible = feasible;
+    p.positions = radii ? positions : nullptr; p.radii = radii;
+    p.n_samples = n_samples; p.status = status;
+    p.B = B; p.b0 = 0; p.nb = B;
+    p.vec_ok = ((uintptr_t)coeffs % 16 == 0) ? 1 : 0;
+    return launch_feasibility(ctx, D, aos, p, stream);
+  }
+  const size_t S = (size_t)max_samples;
+  std::vector<HostTensor> ts = {
+      {coeffs, (size_t)K * D * N, 8, true, false, nullptr}, {seg_times, (size_t)K, 8, true, false, nullptr},
+      {t_start, 1, 8, true, true, nullptr}, {t_end, 1, 8, true, true, nullptr}, {dt, 1, 8, true, true, nullptr},
+      {radii ? positions : nullptr, (size_t)(K + 1) * 3, 8, true, false, nullptr},
+      {radii, (size_t)K * 2, 8, true, false, nullptr},
+      {S ? samples : nullptr, S * D, 8, false, false, nullptr}, {S ? flags : nullptr, S, 1, false, false, nullptr},
+      {max_v, 1, 8, false, true, nullptr}, {max_a, 1, 8, false, true, nullptr},
+      {feasible, 1, 1, false, true, nullptr}, {n_samples, 1, 4, false, true, nullptr},
+      {status, 1, 4, false, true, nullptr}};
+  return run_chunked(ctx, stream, (size_t)B, aos, ts, [&](int nb, int C, cudaStream_t st) {
+    p.coeffs = (const double*)ts[0].dev; p.seg_times = (const double*)ts[1].dev;
+    p.t_start = (const double*)ts[2].dev; p.t_end = (const double*)ts[3].dev; p.dt = (const double*)ts[4].dev;
+    p.positions = (const double*)ts[5].dev; p.radii = (const double*)ts[6].dev;
+    p.samples = (double*)ts[7].dev; p.flags = (uint8_t*)ts[8].dev;
+    p.max_v = (double*)ts[9].dev; p.max_a = (double*)ts[10].dev; p.feasible = (uint8_t*)ts[11].dev;
+    p.n_samples = (int32_t*)ts[12].dev; p.status = (uint32_t*)ts[13].dev;
+    p.B = C; p.b0 = 0; p.nb = nb; p.vec_ok = 1;
+    return launch_feasibility(ctx, D, aos, p, st);
+  });
 }
 
 }  // extern "C"
