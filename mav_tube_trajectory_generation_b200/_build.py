@@ -46,23 +46,44 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
+def _run(cmd, verbose):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: " + " ".join(cmd))
+
+
+def _stale(obj, deps):
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles every csrc/*.cu to an object (in parallel; only the stale ones) and links
+    libmtg_cuda.so. Each .cu is a self-contained translation unit (no -rdc)."""
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
+
     os.makedirs(BUILD, exist_ok=True)
+    headers = [s for s in _sources() if s.endswith((".cuh", ".h"))]
+    jobs, objs = [], []
     tables_o = os.path.join(BUILD, "tables.o")
-    # g++ from PATH: the image exports CXX=/opt/gcc/bin/g++, which is not what nvcc pairs with
-    cmds = [
-        ["g++", "-O2", "-fPIC", "-std=c++14", "-c", os.path.join(CSRC, "tables.cpp"), "-o", tables_o],
-        [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
-        ["-shared", os.path.join(CSRC, "mtg_cuda.cu"), tables_o, "-o", LIB, "-ldl"],
-    ]
-    for cmd in cmds:
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-        if r.returncode != 0:
-            raise RuntimeError("build failed: " + " ".join(cmd))
+    objs.append(tables_o)
+    if force or _stale(tables_o, [os.path.join(CSRC, "tables.cpp"), os.path.join(CSRC, "tables.h")]):
+        # g++ from PATH: the image exports CXX=/opt/gcc/bin/g++, which is not what nvcc pairs with
+        jobs.append(["g++", "-O2", "-fPIC", "-std=c++14", "-c", os.path.join(CSRC, "tables.cpp"), "-o", tables_o])
+    for cu in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):
+        obj = os.path.join(BUILD, os.path.basename(cu)[:-3] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [cu] + headers):
+            jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", cu, "-o", obj])
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        list(ex.map(lambda c: _run(c, verbose), jobs))
+    _run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-ldl"], verbose)
     return LIB
 
 

@@ -17,9 +17,10 @@ struct DevTables {
 };
 
 #ifdef __CUDACC__
-// libmtg_cuda.so is ONE CUDA translation unit (mtg_cuda.cu #includes every kernel
-// header), so the table is defined here, once, without relocatable device code.
-__constant__ DevTables c_tab;
+// Every kernel translation unit of libmtg_cuda.so has its own private copy (no
+// relocatable device code); host_common.h registers an uploader per unit and
+// ensure_tables() refreshes all copies together.
+static __constant__ DevTables c_tab;
 #endif
 
 }  // namespace mtg
