@@ -106,6 +106,7 @@ void mtg_destroy(mtg_ctx* ctx) {
     if (ctx->stage_stream[i]) cudaStreamDestroy(ctx->stage_stream[i]);
   }
   ctx->scratch.release();
+  for (auto& e : ctx->stream_scratch) e.second.release();
   delete ctx;
 }
 

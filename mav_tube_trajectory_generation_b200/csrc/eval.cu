@@ -24,6 +24,9 @@ int launch_eval_range_d(mtg_ctx* ctx, int D, const mtg::EvalParams& p, cudaStrea
   return MTG_OK;
 }
 int launch_eval_range(mtg_ctx* ctx, int D, bool aos, const mtg::EvalParams& p, cudaStream_t s) {
+  // trajectory-contiguous outputs: the time-major sweep (eval_tm.cuh); MTG_EVAL_LEGACY=1 keeps
+  // the one-thread-per-trajectory kernel for A/B measurements
+  if (aos && mtg::eval_tm_supported(p) && !std::getenv("MTG_EVAL_LEGACY")) return mtg::launch_eval_tm(ctx, D, false, p, s);
   if (p.N == 10) return aos ? launch_eval_range_d<10, true>(ctx, D, p, s) : launch_eval_range_d<10, false>(ctx, D, p, s);
   return aos ? launch_eval_range_d<12, true>(ctx, D, p, s) : launch_eval_range_d<12, false>(ctx, D, p, s);
 }
@@ -44,6 +47,7 @@ int launch_feasibility_d(mtg_ctx* ctx, int D, const mtg::EvalParams& p, cudaStre
   return MTG_OK;
 }
 int launch_feasibility(mtg_ctx* ctx, int D, bool aos, const mtg::EvalParams& p, cudaStream_t s) {
+  if (aos && mtg::eval_tm_supported(p) && !std::getenv("MTG_EVAL_LEGACY")) return mtg::launch_eval_tm(ctx, D, true, p, s);
   if (p.N == 10) return aos ? launch_feasibility_d<10, true>(ctx, D, p, s) : launch_feasibility_d<10, false>(ctx, D, p, s);
   return aos ? launch_feasibility_d<12, true>(ctx, D, p, s) : launch_feasibility_d<12, false>(ctx, D, p, s);
 }

@@ -39,6 +39,7 @@ struct EvalParams {
   double* __restrict__ max_a;             // [B] or nullptr
   uint8_t* __restrict__ feasible;         // [B] or nullptr
   double v_max, a_max;
+  double v2_lim, a2_lim;  // largest doubles whose sqrt is <= v_max / a_max (time-major sweep)
   int B, b0, nb, K, N;  // N = coefficients actually stored (<= NT of the kernel)
   int derivative;
   int max_samples;

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mtg_cuda.h"
@@ -48,6 +49,14 @@ struct mtg_ctx {
   cudaStream_t stage_stream[kStageSlots] = {nullptr, nullptr, nullptr};
   DeviceBuffer stage[kStageSlots];  // one staging arena per slot (host-memory mode)
   DeviceBuffer scratch;             // small per-context device scratch
+  // per-stream scratch (tube constants of the sweep): launches on different streams never share one
+  std::vector<std::pair<cudaStream_t, DeviceBuffer>> stream_scratch;
+  DeviceBuffer* scratch_for(cudaStream_t s) {
+    for (auto& e : stream_scratch)
+      if (e.first == s) return &e.second;
+    stream_scratch.emplace_back(s, DeviceBuffer());
+    return &stream_scratch.back().second;
+  }
   void* nccl = nullptr;             // lazily created NCCL state (argmin gather)
 };
 
@@ -82,6 +91,11 @@ void register_table_uploader(TableUploader f);
     TableRegistrar_() { mtg::register_table_uploader(&upload_tables_); }                    \
   } table_registrar_;                                                                       \
   }
+
+// eval_tm.cu: time-major sweep (trajectory-contiguous sample outputs, AoS layout)
+struct EvalParams;
+bool eval_tm_supported(const EvalParams& p);
+int launch_eval_tm(mtg_ctx* ctx, int D, bool feasibility, const EvalParams& p, cudaStream_t s);
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 

@@ -44,6 +44,9 @@ def main():
     p, t = torch.from_numpy(pos).cuda(), torch.from_numpy(times).cuda()
     sol = ctx.solve_batch(p, t, layout=args.layout)
     coeffs = sol["coeffs"]
+    secs = timeit(lambda: ctx.solve_batch(p, t, layout=args.layout, out=sol), args.reps)
+    print(json.dumps({"kernel": "solve_canonical", "layout": args.layout, "batch": B, "ms": secs * 1e3,
+                      "trajectories_per_s": B / secs, "achieved_gbs": bench.BYTES_PER_TRAJ * B / secs / 1e9}), flush=True)
     tmax = ctx.max_time_batch(t, layout=args.layout)
     dt = tmax / S
     Smax = S + 8
