@@ -22,13 +22,13 @@ double sq_limit(double lim) {
   return y;
 }
 
-constexpr int kTmBlock = 64;            // 2 warps = 64 trajectories per CTA (fine-grained shared-memory packing)
+constexpr int kTmBlock = 32;            // one warp = 32 trajectories per CTA (finest shared-memory packing)
 constexpr int kTubeChunk = 65536;       // trajectories per launch pair when a tube scratch is needed
 
 template <int NT, int D, int MODE>
 int launch_tm_t(mtg_ctx* ctx, const EvalParams& p, const double* geom, cudaStream_t s) {
   const bool want_acc = MODE < TM_FEAS && p.sampling_times != nullptr;
-  const size_t smem = (size_t)tm_layout(D, NT, want_acc, MODE == TM_FEAS_TUBE, true).per_warp * (kTmBlock / 32);
+  const size_t smem = (size_t)tm_layout(D, NT, want_acc, MODE == TM_FEAS_TUBE).per_warp * (kTmBlock / 32);
   auto kern = eval_tm_kernel<NT, D, MODE>;
   if (smem > 48 * 1024) MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (p.nb + kTmBlock - 1) / kTmBlock;

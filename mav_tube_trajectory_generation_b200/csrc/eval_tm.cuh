@@ -104,35 +104,39 @@ __global__ void __launch_bounds__(256) tube_setup_kernel(const EvalParams p, dou
 // ------------------------------------------------------------------ the sweep
 // FEAS = false: samples of derivative p.derivative (+ sampling_times, segment_idx).
 // FEAS = true : position samples (optional) + v/a/tube flags + per-trajectory maxima.
-// Inputs (coeffs, seg_times, positions, radii) in AOS_IN layout; every per-sample
-// output is trajectory-contiguous: x[b * max_samples * width + n * width + ...].
+// Every per-sample output is trajectory-contiguous: x[b * max_samples * width + n * width + ...].
 //
-// Shared memory per warp (TmLayout): tau[32][33] | output staging rows | info[32] |
+// Shared memory per warp (TmLayout): tau[32][33] | staging tile | info[32] | flag rows |
 // acc[32][33] (only when sampling_times is requested) | per-trajectory SEGMENT SLOTS.
-// A slot pair holds the records {coefficients, tube constants, duration} of the two
+// A slot pair holds the records {coefficients, tube constants} + durations of the two
 // segments a chunk may touch: segment s lives in slot s & 1, is fetched ONCE with
 // cp.async (LDGSTS) by the trajectory's lane, and the next segment is prefetched right
 // after a chunk has been evaluated, a few chunks before it is needed, so neither phase
 // waits on DRAM in steady state (one commit group per chunk; wait_group 1 retires all
 // but the newest). A chunk stops early if a third segment would start (tiny segments
 // or large dt).
+constexpr int kTmR = 8;                  // consecutive samples per lane in phase 2
+constexpr int kTmG = 32 / (kTmChunk / kTmR);  // trajectories per phase-2 pass (8): 4 lanes each
 struct TmLayout {
-  int slot_bytes;   // one segment: D*NT coefficients (+ tube record) + {T, pad}; multiple of 16
-  int traj_bytes;   // 2 slots + 16 B pad (odd multiple of 16 B: conflict-free lane-major cp.async)
-  int t_off;        // byte offset of the segment duration inside a slot
-  int off_stage, off_info, off_acc, off_slots, per_warp;
+  int slot_bytes;   // one segment record: D*NT coefficients (+ tube record); multiple of 16
+  int traj_bytes;   // 2 slots + {T of slot 0, T of slot 1}
+  int blk_ld;       // doubles per lane block in the staging tile: 8*D + 1 (bank skew)
+  int row_ld;       // doubles per trajectory row of the staging tile: 4 * blk_ld
+  int off_stage, off_info, off_off, off_flag, off_acc, off_slots, per_warp;
 };
-constexpr int kTmU = 2;  // trajectories evaluated together in phase 2 (independent FMA chains)
-__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, bool slots) {
+__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube) {
   TmLayout L;
-  L.t_off = D * NT * 8 + (tube ? kTubeGeomLd * 8 : 0);
-  L.slot_bytes = L.t_off + 16;
+  L.slot_bytes = D * NT * 8 + (tube ? kTubeGeomLd * 8 : 0);
   L.traj_bytes = 2 * L.slot_bytes + 16;
+  L.blk_ld = kTmR * D + 1;
+  L.row_ld = (kTmChunk / kTmR) * L.blk_ld;
   L.off_stage = 32 * kTmTauLd * 8;
-  L.off_info = L.off_stage + kTmU * 32 * D * 8;
-  L.off_acc = L.off_info + 32 * 16;
+  L.off_info = L.off_stage + kTmG * L.row_ld * 8;
+  L.off_off = L.off_info + 32 * 16;
+  L.off_flag = L.off_off + 32 * 8;
+  L.off_acc = L.off_flag + kTmG * 40;
   L.off_slots = L.off_acc + (want_acc ? 32 * kTmTauLd * 8 : 0);
-  L.per_warp = L.off_slots + (slots ? 32 * L.traj_bytes : 0);
+  L.per_warp = L.off_slots + 32 * L.traj_bytes;
   L.per_warp = (L.per_warp + 15) & ~15;
   return L;
 }
@@ -140,25 +144,25 @@ __host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool
 enum TmMode { TM_POSITION = 0, TM_DERIVATIVE = 1, TM_FEAS = 2, TM_FEAS_TUBE = 3 };
 
 // Requirements (checked by the launcher, which otherwise falls back to the one-thread-per-
-// trajectory kernels of eval.cuh): AoS layout, N == NT, coeffs/seg_times/geom 16-/8-byte aligned.
+// trajectory kernels of eval.cuh): AoS layout, N == NT, coeffs 16-byte aligned.
 template <int NT, int D, int MODE>
-__global__ void __launch_bounds__(64, 4) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
-  constexpr bool FEAS = MODE >= TM_FEAS;
-  constexpr bool AOS_IN = true;
-  constexpr bool fast_c = true;  // segment records staged in shared memory
-  constexpr bool tube = MODE == TM_FEAS_TUBE;
-  static_assert(!tube || D == 3, "the tube predicate is 3-D");
+__global__ void __launch_bounds__(32, 7) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr bool FEAS = MODE >= TM_FEAS;
+  constexpr bool tube = MODE == TM_FEAS_TUBE;
   constexpr int Q = D * NT / 2;  // 16-byte pieces of one segment's coefficients
-  constexpr int U = kTmU;
+  constexpr int R = kTmR, G = kTmG;
+  static_assert(!tube || D == 3, "the tube predicate is 3-D");
   extern __shared__ __align__(16) unsigned char tm_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool want_acc = (!FEAS) && p.sampling_times != nullptr;
-  const TmLayout L = tm_layout(D, NT, want_acc, tube, fast_c);
+  const TmLayout L = tm_layout(D, NT, want_acc, tube);
   unsigned char* wbase = tm_smem + (size_t)warp * L.per_warp;
   double* tau_s = reinterpret_cast<double*>(wbase);
   double* stage = reinterpret_cast<double*>(wbase + L.off_stage);
   int4* info_s = reinterpret_cast<int4*>(wbase + L.off_info);
+  unsigned char* flag_s = wbase + L.off_flag;
+  size_t* off_s = reinterpret_cast<size_t*>(wbase + L.off_off);
   double* acc_s = reinterpret_cast<double*>(wbase + L.off_acc);
   unsigned char* slots = wbase + L.off_slots;
 
@@ -167,17 +171,21 @@ __global__ void __launch_bounds__(64, 4) eval_tm_kernel(const EvalParams p, cons
   const int local = first + lane;
   const bool valid = local < p.nb;
   const int b = p.b0 + (valid ? local : p.nb - 1);
-  const size_t B = (size_t)p.B;
   const int K = p.K;
   const size_t S = (size_t)p.max_samples;
-  const size_t rec_c = (size_t)K * D * p.N;
+
+  const size_t traj_off = (size_t)(p.b0 + local) * S;  // first output row of this lane's trajectory
+  const int q8 = lane >> 2, sb = lane & 3, k0 = sb * R;  // phase-2 role: trajectory in pass, block, first sample
+  int skew[D];  // staging-tile position of element lane + 32 q of a trajectory row
+#pragma unroll
+  for (int q = 0; q < D; ++q) skew[q] = (lane + 32 * q) + (lane + 32 * q) / (R * D);
 
   // ---- phase-1 state (lane = trajectory)
   uint32_t st = 0;
   int n = 0, i = 0;
   const double t0 = p.t_start[b], t1 = p.t_end[b], dt = p.dt[b];
   double acc = 0.0, tau = 0.0, Ti = 0.0;
-  bool done = !locate_start<AOS_IN>(p, b, t0, dt, i, acc);
+  bool done = !locate_start<true>(p, b, t0, dt, i, acc);
   if (done)
     st |= 4u;
   else
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(64, 4) eval_tm_kernel(const EvalParams p, cons
   int age0 = -1, age1 = -1;    // chunk index whose commit group carries that fetch
   int chunk = 0;
   unsigned char* my_slots = slots + (size_t)lane * L.traj_bytes;
-  const double* my_coeffs = p.coeffs + (size_t)b * rec_c;
+  const double* my_coeffs = p.coeffs + (size_t)b * ((size_t)K * D * NT);
   const double* my_times = p.seg_times + (size_t)b * K;
   const double* my_geom = tube ? geom + (size_t)(valid ? local : p.nb - 1) * K * kTubeGeomLd : nullptr;
   auto ensure = [&](int seg) {  // make segment `seg` resident in slot seg & 1 (asynchronously)
@@ -207,11 +215,10 @@ __global__ void __launch_bounds__(64, 4) eval_tm_kernel(const EvalParams p, cons
 #pragma unroll
       for (int q = 0; q < kTubeGeomLd / 2; ++q) cp_async16(dst + D * NT + 2 * q, g + 2 * q);
     }
-    cp_async8(reinterpret_cast<double*>(my_slots + sl * L.slot_bytes + L.t_off), my_times + seg);
+    cp_async8(reinterpret_cast<double*>(my_slots + 2 * L.slot_bytes) + sl, my_times + seg);
   };
-  // duration of segment `seg`; with slots: from its landed record (fetching it on demand)
+  // duration of segment `seg` from its landed record (fetching it on demand)
   auto duration = [&](int seg) -> double {
-    if (!fast_c) return p.seg_times[at<AOS_IN>((size_t)seg, (size_t)K, B, (size_t)b)];
     const int sl = seg & 1;
     if ((sl ? held1 : held0) != seg) {
       ensure(seg);
@@ -220,20 +227,18 @@ __global__ void __launch_bounds__(64, 4) eval_tm_kernel(const EvalParams p, cons
     } else if ((sl ? age1 : age0) >= chunk - 1) {
       cp_async_wait_all();  // carried by the newest group: not retired by wait_group 1
     }
-    return *reinterpret_cast<const double*>(my_slots + sl * L.slot_bytes + L.t_off);
+    return reinterpret_cast<const double*>(my_slots + 2 * L.slot_bytes)[sl];
   };
-  if (fast_c) {
-    if (!done) {
-      ensure(i);
-      if (i + 1 < K) ensure(i + 1);
-    }
-    cp_async_commit();
-    ++chunk;
+  if (!done) {
+    ensure(i);
+    if (i + 1 < K) ensure(i + 1);
   }
+  cp_async_commit();
+  ++chunk;
 
   for (;; ++chunk) {
     // ------------------------------------------------ phase 1: trajectory.cpp:114-133
-    if (fast_c) cp_async_wait_group1();
+    cp_async_wait_group1();
     int cnt = 0, seg0 = i, cross = kTmChunk;  // samples [cross, cnt) lie in segment seg0 + 1
     if (!done) {
       Ti = duration(i);
@@ -279,64 +284,69 @@ __global__ void __launch_bounds__(64, 4) eval_tm_kernel(const EvalParams p, cons
       }
     }
     info_s[lane] = make_int4(cnt, n, seg0, cross);
+    off_s[lane] = traj_off + (size_t)n;
     __syncwarp();
     if (!__any_sync(FULL, cnt > 0)) break;
 
-    // ------------------------------------------------ phase 2: lane = sample, U trajectories at a time
+    // ------------------------------------------------ phase 2: 4 lanes x 8 consecutive samples per
+    // trajectory, 8 trajectories per pass. The lane's coefficients stay in registers for its 8
+    // samples; the one lane whose block contains the crossing reloads in the middle.
 #pragma unroll 1
-    for (int r = 0; r < 32; r += U) {
-      int4 info[U];
+    for (int g = 0; g < 32 / G; ++g) {
+      const int r = g * G + q8;
+      const int4 info = info_s[r];
+      if (!__any_sync(FULL, info.x > 0)) continue;
+      const int cnt_r = info.x, last = max(cnt_r - 1, 0);
+      const int jr = info.w - k0;  // first sample of this lane's block in segment seg0 + 1
+      const unsigned char* tslots = slots + (size_t)r * L.traj_bytes;
+      double c[D][NT];
+      TubeSeg tsg;
+      auto load_segment = [&](int seg) {
+        const double2* slot = reinterpret_cast<const double2*>(tslots + (seg & 1) * L.slot_bytes);
 #pragma unroll
-      for (int u = 0; u < U; ++u) info[u] = info_s[r + u];
-      bool any = false;
-#pragma unroll
-      for (int u = 0; u < U; ++u) any = any || info[u].x > 0;
-      if (!any) continue;
-      double x[U][D];
-      int seg[U];
-      bool act[U];
-      unsigned fl[U];
-      double wv[U], wa[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int cnt_r = info[u].x;
-        act[u] = lane < cnt_r;
-        const int l = act[u] ? lane : max(cnt_r - 1, 0);
-        const double ta = tau_s[(r + u) * kTmTauLd + l];
-        seg[u] = info[u].z + (l >= info[u].w ? 1 : 0);
-        double c[D][NT];
-        const double2* slot =
-            reinterpret_cast<const double2*>(slots + (size_t)(r + u) * L.traj_bytes + (seg[u] & 1) * L.slot_bytes);
-        if (fast_c) {
-#pragma unroll
-          for (int q = 0; q < Q; ++q) {
-            const double2 v = slot[q];
-            c[(2 * q) / NT][(2 * q) % NT] = v.x;
-            c[(2 * q + 1) / NT][(2 * q + 1) % NT] = v.y;
-          }
-        } else {
-          const int br = min(p.b0 + first + r + u, p.b0 + p.nb - 1);
-          const double* src = p.coeffs + at<AOS_IN>((size_t)seg[u] * D * p.N, rec_c, B, (size_t)br);
-          const size_t stride = AOS_IN ? 1 : B;
-#pragma unroll
-          for (int dim = 0; dim < D; ++dim)
-#pragma unroll
-            for (int j = 0; j < NT; ++j) c[dim][j] = (j < p.N) ? __ldg(src + ((size_t)dim * p.N + j) * stride) : 0.0;
+        for (int q = 0; q < Q; ++q) {
+          const double2 v = slot[q];
+          c[(2 * q) / NT][(2 * q) % NT] = v.x;
+          c[(2 * q + 1) / NT][(2 * q + 1) % NT] = v.y;
         }
+        if (tube) {
+          const double2* gq = slot + Q;
+          const double2 g0 = gq[0], g1 = gq[1], g2 = gq[2], g3 = gq[3], g4 = gq[4], g5 = gq[5], g6 = gq[6], g7 = gq[7];
+          tsg.A[0] = g0.x; tsg.A[1] = g0.y; tsg.A[2] = g1.x; tsg.A[3] = g1.y; tsg.A[4] = g2.x; tsg.A[5] = g2.y;
+          tsg.bvec[0] = g3.x; tsg.bvec[1] = g3.y; tsg.bvec[2] = g4.x;
+          tsg.n[0] = g4.y; tsg.n[1] = g5.x; tsg.n[2] = g5.y;
+          tsg.cs = g6.x; tsg.ce = g6.y; tsg.r2 = g7.x;
+        }
+      };
+      load_segment(info.z + (jr <= 0 ? 1 : 0));
+      double v2m = 0.0, a2m = 0.0;
+      unsigned fand = 7u;
+      unsigned long long fpack = 0ull;
+      double* srow = stage + q8 * L.row_ld + sb * L.blk_ld;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        if (j > 0) {
+          if (__any_sync(FULL, j == jr)) {
+            if (j == jr) load_segment(info.z + 1);
+          }
+        }
+        const int k = k0 + j;
+        const double ta = tau_s[r * kTmTauLd + min(k, last)];
+        double x[D];
         if (!FEAS) {
           if (MODE == TM_POSITION) {
 #pragma unroll
-            for (int dim = 0; dim < D; ++dim) x[u][dim] = horner<NT>(c[dim], ta);
+            for (int dim = 0; dim < D; ++dim) x[dim] = horner<NT>(c[dim], ta);
           } else {
             // polynomial.h:136-149 with the table row B(derivative, .)
             const int der = p.derivative;
 #pragma unroll
             for (int dim = 0; dim < D; ++dim) {
-              double acc_h = 0.0;
+              double h = 0.0;
 #pragma unroll
-              for (int j = NT - 1; j >= 0; --j)
-                if (j >= der) acc_h = fma(acc_h, ta, c_tab.base[der * MTG_BASE_LD + j] * c[dim][j]);
-              x[u][dim] = acc_h;
+              for (int jj = NT - 1; jj >= 0; --jj)
+                if (jj >= der) h = fma(h, ta, c_tab.base[der * MTG_BASE_LD + jj] * c[dim][jj]);
+              x[dim] = h;
             }
           }
         } else {
@@ -345,93 +355,84 @@ __global__ void __launch_bounds__(64, 4) eval_tm_kernel(const EvalParams p, cons
           for (int dim = 0; dim < D; ++dim) {
             double p0 = c[dim][NT - 1], p1 = 0.0, p2 = 0.0;
 #pragma unroll
-            for (int j = NT - 2; j >= 0; --j) {
+            for (int jj = NT - 2; jj >= 0; --jj) {
               p2 = fma(p2, ta, p1);
               p1 = fma(p1, ta, p0);
-              p0 = fma(p0, ta, c[dim][j]);
+              p0 = fma(p0, ta, c[dim][jj]);
             }
-            x[u][dim] = p0;
+            x[dim] = p0;
             v2 = fma(p1, p1, v2);
             a2 = fma(2.0 * p2, 2.0 * p2, a2);
           }
           // sqrt is monotone and correctly rounded: |v| <= v_max <=> |v|^2 <= v2_lim (host-computed
           // largest double whose root is <= v_max), and max|v| = sqrt(max |v|^2).
           unsigned f = (v2 <= p.v2_lim ? 1u : 0u) | (a2 <= p.a2_lim ? 2u : 0u) | 4u;
-          if (D == 3 && tube) {
-            const int lr = min(first + r + u, p.nb - 1);
-            const double2* g = fast_c ? slot + Q
-                                      : reinterpret_cast<const double2*>(geom + ((size_t)lr * K + seg[u]) * kTubeGeomLd);
-            const double2 g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3], g4 = g[4], g5 = g[5], g6 = g[6], g7 = g[7];
-            TubeSeg t;
-            t.A[0] = g0.x; t.A[1] = g0.y; t.A[2] = g1.x; t.A[3] = g1.y; t.A[4] = g2.x; t.A[5] = g2.y;
-            t.bvec[0] = g3.x; t.bvec[1] = g3.y; t.bvec[2] = g4.x;
-            t.n[0] = g4.y; t.n[1] = g5.x; t.n[2] = g5.y;
-            t.cs = g6.x; t.ce = g6.y; t.r2 = g7.x;
-            const double x3[3] = {x[u][0], x[u][D > 1 ? 1 : 0], x[u][D > 2 ? 2 : 0]};
-            if (!in_tube(t, x3)) f &= 3u;
+          if (tube) {
+            const double x3[3] = {x[0], x[D > 1 ? 1 : 0], x[D > 2 ? 2 : 0]};
+            if (!in_tube(tsg, x3)) f &= 3u;
           }
-          if (!act[u]) {
-            f = 7u;
-            v2 = 0.0;
-            a2 = 0.0;
+          if (k < cnt_r) {
+            v2m = fmax(v2m, v2);
+            a2m = fmax(a2m, a2);
+            fand &= f;
           }
-          fl[u] = f;
-          wv[u] = v2;
-          wa[u] = a2;
+          fpack |= (unsigned long long)f << (8 * j);
         }
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) srow[j * D + dim] = x[dim];
       }
       if (FEAS) {
+        // block maxima -> trajectory maxima (4 lanes) -> the trajectory's phase-1 lane
+        *reinterpret_cast<unsigned long long*>(flag_s + q8 * 40 + k0) = fpack;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const double mv = warp_max_nonneg(wv[u]), ma = warp_max_nonneg(wa[u]);
-          const unsigned wf = __reduce_and_sync(FULL, fl[u]);
-          if (lane == r + u) {
-            mv2 = fmax(mv2, mv);
-            ma2 = fmax(ma2, ma);
-            all_bits &= wf;
-          }
-          if (p.flags && act[u]) p.flags[(size_t)(p.b0 + first + r + u) * S + info[u].y + lane] = (uint8_t)fl[u];
+        for (int m = 1; m <= 2; m <<= 1) {
+          v2m = fmax(v2m, __shfl_xor_sync(FULL, v2m, m));
+          a2m = fmax(a2m, __shfl_xor_sync(FULL, a2m, m));
+          fand &= __shfl_xor_sync(FULL, fand, m);
+        }
+        const int src = 4 * (lane & (G - 1));
+        const double ov = __shfl_sync(FULL, v2m, src), oa = __shfl_sync(FULL, a2m, src);
+        const unsigned of = __shfl_sync(FULL, fand, src);
+        if ((lane / G) == g) {
+          mv2 = fmax(mv2, ov);
+          ma2 = fmax(ma2, oa);
+          all_bits &= of;
         }
       }
-      if (p.samples) {
+      __syncwarp();
+      // staged rows -> global memory: whole consecutive 256-byte stores per trajectory
+      // (cnt == 0 rows fall out through the predicates; everything else is branch-free)
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+      for (int t = 0; t < G; ++t) {
+        const int4 it = info_s[g * G + t];
+        const size_t o = off_s[g * G + t];
+        if (p.samples) {
+          double* out = p.samples + o * D + lane;
+          const double* row = stage + t * L.row_ld;
+          const int total = it.x * D;
 #pragma unroll
-          for (int dim = 0; dim < D; ++dim) stage[u * (32 * D) + lane * D + dim] = x[u][dim];
-        __syncwarp();
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          double* out = p.samples + ((size_t)(p.b0 + first + r + u) * S + info[u].y) * D;
-          const int total = info[u].x * D;
-#pragma unroll
-          for (int q = 0; q < D; ++q) {
-            const int e = lane + 32 * q;
-            if (e < total) out[e] = stage[u * (32 * D) + e];
+          for (int q = 0; q < D; ++q)
+            if (lane + 32 * q < total) out[32 * q] = row[skew[q]];
+        }
+        if (lane < it.x) {
+          if (FEAS) {
+            if (p.flags) p.flags[o + lane] = flag_s[t * 40 + lane];
+          } else {
+            if (want_acc) p.sampling_times[o + lane] = acc_s[(g * G + t) * kTmTauLd + lane];
+            if (p.segment_idx) p.segment_idx[o + lane] = it.z + (lane >= it.w ? 1 : 0);
           }
         }
-        __syncwarp();
       }
-      if (!FEAS) {
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (act[u]) {
-            const size_t o = (size_t)(p.b0 + first + r + u) * S + info[u].y + lane;
-            if (want_acc) p.sampling_times[o] = acc_s[(r + u) * kTmTauLd + lane];
-            if (p.segment_idx) p.segment_idx[o] = seg[u];
-          }
-      }
+      __syncwarp();
     }
     n += cnt;
-    __syncwarp();
     // every sample emitted so far has been evaluated: both slots may be re-targeted.
     // Prefetch the current and the next segment (no-ops while they are resident).
-    if (fast_c) {
-      if (!done) {
-        ensure(i);
-        if (i + 1 < K) ensure(i + 1);
-      }
-      cp_async_commit();
+    if (!done) {
+      ensure(i);
+      if (i + 1 < K) ensure(i + 1);
     }
+    cp_async_commit();
   }
   cp_async_wait_all();
   if (valid) {
