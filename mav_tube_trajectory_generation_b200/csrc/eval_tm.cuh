@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(32, 7) eval_tm_kernel(const EvalParams p, cons
   const size_t S = (size_t)p.max_samples;
 
   const size_t traj_off = (size_t)(p.b0 + local) * S;  // first output row of this lane's trajectory
-  const int q8 = lane >> 2, sb = lane & 3, k0 = sb * R;  // phase-2 role: trajectory in pass, block, first sample
+  const int q8 = lane >> 2, sb = lane & 3;  // phase-2 role: trajectory within the pass, block within the trajectory
   int skew[D];  // staging-tile position of element lane + 32 q of a trajectory row
 #pragma unroll
   for (int q = 0; q < D; ++q) skew[q] = (lane + 32 * q) + (lane + 32 * q) / (R * D);
@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(32, 7) eval_tm_kernel(const EvalParams p, cons
     int cnt = 0, seg0 = i, cross = kTmChunk;  // samples [cross, cnt) lie in segment seg0 + 1
     if (!done) {
       Ti = duration(i);
-      const int limit = min(kTmChunk, p.max_samples - n);
+      const int rows_left = p.max_samples - n;
+      int limit = min(kTmChunk, rows_left);
       double* trow = tau_s + lane * kTmTauLd;
       double* arow = acc_s + lane * kTmTauLd;
       for (;;) {
@@ -271,12 +272,15 @@ __global__ void __launch_bounds__(32, 7) eval_tm_kernel(const EvalParams p, cons
             break;  // a third segment: leave it to the next chunk
           } else {
             cross = cnt;
+            // phase 2 gives segment A the blocks [0, ceil(cross/8)) and segment B the rest:
+            // no 8-sample block straddles the crossing (costs < 8 samples of this chunk)
+            limit = min(limit, cross + R * (kTmChunk / R - (cross + R - 1) / R));
           }
           Ti = duration(i);
           continue;
         }
         // cnt == limit
-        if (limit < kTmChunk) {  // out of output rows
+        if (cnt >= rows_left) {  // out of output rows
           st |= 8u;
           done = true;
         }
@@ -297,7 +301,13 @@ __global__ void __launch_bounds__(32, 7) eval_tm_kernel(const EvalParams p, cons
       const int4 info = info_s[r];
       if (!__any_sync(FULL, info.x > 0)) continue;
       const int cnt_r = info.x, last = max(cnt_r - 1, 0);
-      const int jr = info.w - k0;  // first sample of this lane's block in segment seg0 + 1
+      // blocks of <= 8 consecutive samples: segment A (seg0) owns the first nA blocks from sample 0,
+      // segment B (seg0 + 1) the others from sample `cross`
+      const int cross_r = min(info.w, cnt_r);
+      const int nA = (cross_r + R - 1) / R;
+      const bool isB = sb >= nA;
+      const int start = isB ? cross_r + (sb - nA) * R : sb * R;
+      const int count = min(R, (isB ? cnt_r : cross_r) - start);  // may be <= 0
       const unsigned char* tslots = slots + (size_t)r * L.traj_bytes;
       double c[D][NT];
       TubeSeg tsg;
@@ -318,72 +328,105 @@ __global__ void __launch_bounds__(32, 7) eval_tm_kernel(const EvalParams p, cons
           tsg.cs = g6.x; tsg.ce = g6.y; tsg.r2 = g7.x;
         }
       };
-      load_segment(info.z + (jr <= 0 ? 1 : 0));
+      load_segment(info.z + (isB ? 1 : 0));
       double v2m = 0.0, a2m = 0.0;
       unsigned fand = 7u;
-      unsigned long long fpack = 0ull;
-      double* srow = stage + q8 * L.row_ld + sb * L.blk_ld;
+      double* srow = stage + q8 * L.row_ld;
+      // JB samples advance together, one Horner step at a time: JB*D (position) or 3*JB*D
+      // (feasibility) independent FMA chains cover the fp64 pipe latency from a single warp.
+      constexpr int JB = FEAS ? 4 : R;
 #pragma unroll
-      for (int j = 0; j < R; ++j) {
-        if (j > 0) {
-          if (__any_sync(FULL, j == jr)) {
-            if (j == jr) load_segment(info.z + 1);
-          }
-        }
-        const int k = k0 + j;
-        const double ta = tau_s[r * kTmTauLd + min(k, last)];
-        double x[D];
+      for (int j0 = 0; j0 < R; j0 += JB) {
+        double ta[JB];
+#pragma unroll
+        for (int j = 0; j < JB; ++j) ta[j] = tau_s[r * kTmTauLd + min(start + j0 + j, last)];
+        double x[JB][D];
         if (!FEAS) {
           if (MODE == TM_POSITION) {
 #pragma unroll
-            for (int dim = 0; dim < D; ++dim) x[dim] = horner<NT>(c[dim], ta);
+            for (int j = 0; j < JB; ++j)
+#pragma unroll
+              for (int dim = 0; dim < D; ++dim) x[j][dim] = c[dim][NT - 1];
+#pragma unroll
+            for (int jj = NT - 2; jj >= 0; --jj)
+#pragma unroll
+              for (int j = 0; j < JB; ++j)
+#pragma unroll
+                for (int dim = 0; dim < D; ++dim) x[j][dim] = fma(x[j][dim], ta[j], c[dim][jj]);
           } else {
             // polynomial.h:136-149 with the table row B(derivative, .)
             const int der = p.derivative;
 #pragma unroll
-            for (int dim = 0; dim < D; ++dim) {
-              double h = 0.0;
+            for (int j = 0; j < JB; ++j)
 #pragma unroll
-              for (int jj = NT - 1; jj >= 0; --jj)
-                if (jj >= der) h = fma(h, ta, c_tab.base[der * MTG_BASE_LD + jj] * c[dim][jj]);
-              x[dim] = h;
+              for (int dim = 0; dim < D; ++dim) x[j][dim] = 0.0;
+#pragma unroll
+            for (int jj = NT - 1; jj >= 0; --jj) {
+              if (jj >= der) {
+                double bc[D];
+#pragma unroll
+                for (int dim = 0; dim < D; ++dim) bc[dim] = c_tab.base[der * MTG_BASE_LD + jj] * c[dim][jj];
+#pragma unroll
+                for (int j = 0; j < JB; ++j)
+#pragma unroll
+                  for (int dim = 0; dim < D; ++dim) x[j][dim] = fma(x[j][dim], ta[j], bc[dim]);
+              }
             }
           }
         } else {
-          double v2 = 0.0, a2 = 0.0;
+          double p1[JB][D], p2[JB][D];
 #pragma unroll
-          for (int dim = 0; dim < D; ++dim) {
-            double p0 = c[dim][NT - 1], p1 = 0.0, p2 = 0.0;
+          for (int j = 0; j < JB; ++j)
 #pragma unroll
-            for (int jj = NT - 2; jj >= 0; --jj) {
-              p2 = fma(p2, ta, p1);
-              p1 = fma(p1, ta, p0);
-              p0 = fma(p0, ta, c[dim][jj]);
+            for (int dim = 0; dim < D; ++dim) {
+              x[j][dim] = c[dim][NT - 1];
+              p1[j][dim] = 0.0;
+              p2[j][dim] = 0.0;
             }
-            x[dim] = p0;
-            v2 = fma(p1, p1, v2);
-            a2 = fma(2.0 * p2, 2.0 * p2, a2);
+#pragma unroll
+          for (int jj = NT - 2; jj >= 0; --jj)
+#pragma unroll
+            for (int j = 0; j < JB; ++j)
+#pragma unroll
+              for (int dim = 0; dim < D; ++dim) {
+                p2[j][dim] = fma(p2[j][dim], ta[j], p1[j][dim]);
+                p1[j][dim] = fma(p1[j][dim], ta[j], x[j][dim]);
+                x[j][dim] = fma(x[j][dim], ta[j], c[dim][jj]);
+              }
+#pragma unroll
+          for (int j = 0; j < JB; ++j) {
+            double v2 = 0.0, a2 = 0.0;
+#pragma unroll
+            for (int dim = 0; dim < D; ++dim) {
+              v2 = fma(p1[j][dim], p1[j][dim], v2);
+              a2 = fma(2.0 * p2[j][dim], 2.0 * p2[j][dim], a2);
+            }
+            // sqrt is monotone and correctly rounded: |v| <= v_max <=> |v|^2 <= v2_lim (host-computed
+            // largest double whose root is <= v_max), and max|v| = sqrt(max |v|^2).
+            unsigned f = (v2 <= p.v2_lim ? 1u : 0u) | (a2 <= p.a2_lim ? 2u : 0u) | 4u;
+            if (tube) {
+              const double x3[3] = {x[j][0], x[j][D > 1 ? 1 : 0], x[j][D > 2 ? 2 : 0]};
+              if (!in_tube(tsg, x3)) f &= 3u;
+            }
+            if (j0 + j < count) {
+              v2m = fmax(v2m, v2);
+              a2m = fmax(a2m, a2);
+              fand &= f;
+              flag_s[q8 * 40 + start + j0 + j] = (unsigned char)f;
+            }
           }
-          // sqrt is monotone and correctly rounded: |v| <= v_max <=> |v|^2 <= v2_lim (host-computed
-          // largest double whose root is <= v_max), and max|v| = sqrt(max |v|^2).
-          unsigned f = (v2 <= p.v2_lim ? 1u : 0u) | (a2 <= p.a2_lim ? 2u : 0u) | 4u;
-          if (tube) {
-            const double x3[3] = {x[0], x[D > 1 ? 1 : 0], x[D > 2 ? 2 : 0]};
-            if (!in_tube(tsg, x3)) f &= 3u;
-          }
-          if (k < cnt_r) {
-            v2m = fmax(v2m, v2);
-            a2m = fmax(a2m, a2);
-            fand &= f;
-          }
-          fpack |= (unsigned long long)f << (8 * j);
         }
 #pragma unroll
-        for (int dim = 0; dim < D; ++dim) srow[j * D + dim] = x[dim];
+        for (int j = 0; j < JB; ++j) {
+          const int k = start + j0 + j;
+          if (j0 + j < count) {
+#pragma unroll
+            for (int dim = 0; dim < D; ++dim) srow[k * D + (k >> 3) + dim] = x[j][dim];
+          }
+        }
       }
       if (FEAS) {
         // block maxima -> trajectory maxima (4 lanes) -> the trajectory's phase-1 lane
-        *reinterpret_cast<unsigned long long*>(flag_s + q8 * 40 + k0) = fpack;
 #pragma unroll
         for (int m = 1; m <= 2; m <<= 1) {
           v2m = fmax(v2m, __shfl_xor_sync(FULL, v2m, m));
