@@ -125,6 +125,28 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc,
                     const double* seg_times, double* coeffs, double* cost,
                     double* free_constraints, uint32_t* status, void* stream);
 
+/* ------------------------------------- P9: finite-difference time perturbations
+ * Replaces the per-segment perturbation loop of the reference's non-linear layer,
+ * getCostAndGradientTime [impl/polynomial_optimization_nonlinear_impl.h:2495-2584,
+ * central differences] / getCostAndGradientTimeSimple [:2586-2657, forward] with
+ * getCostAndGradientDerivative [:1537-1606] as the cost: for every segment n
+ *   T(+-)[n] = T[n] <= 0.1 ? 0.1 : T[n] +- increment_time      (:2527-2530, :2547-2550)
+ *   J_d(T(+-)) = sum_dim [d_f; d_p]^T R(T(+-)) [d_f; d_p]       (no 1/2; d_p HELD FIXED)
+ * i.e. 1 + K (forward) or 1 + 2K (central) rebuilds of every segment's Q, A^-1 and R
+ * per optimiser evaluation in the reference, one kernel here.
+ *  positions, end_derivatives, seg_times   as mtg_solve_batch
+ *  free_constraints [D][K-1][N/2-1]        in, d_p as mtg_solve_batch returns it
+ *  J_nominal [B]   out or NULL, J_d(T)
+ *  J_plus    [K]   out or NULL, J_d with segment n lengthened
+ *  J_minus   [K]   out or NULL, J_d with segment n shortened (central only)
+ *  grad      [K]   out or NULL, dJ_d/dT_n: (J_plus - J_minus)/(2 inc) or (J_plus - J_nominal)/inc,
+ *                  formed from the perturbed segment's own term (the other K-1 cancel exactly)
+ * The caller applies the weights (w_d, w_t ...) of NL_I:2573. */
+int mtg_cost_time_fd_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* positions,
+                           const double* end_derivatives, const double* seg_times,
+                           const double* free_constraints, double increment_time, int central,
+                           double* J_nominal, double* J_plus, double* J_minus, double* grad,
+                           uint32_t* status, void* stream);
 
 /* --------------------------------------------- E1..E4: sampled evaluation
  * All take the solve's output layout: coeffs [K][D][N], seg_times [K] records.

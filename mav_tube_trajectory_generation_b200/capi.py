@@ -63,6 +63,8 @@ def load() -> C.CDLL:
     lib.mtg_sync.argtypes = [vp, vp]
     lib.mtg_get_tables.argtypes = [C.c_int, C.c_int, dp, dp]
     lib.mtg_solve_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, u32p, vp]
+    lib.mtg_cost_time_fd_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, C.c_double, C.c_int,
+                                           dp, dp, dp, dp, u32p, vp]
     lib.mtg_max_time_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, vp]
     lib.mtg_eval_range_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, C.c_int, C.c_int,
                                          dp, dp, vp, vp, u32p, vp]
@@ -199,6 +201,30 @@ class Context:
                                        _ptr(status), self._stream(mode, stream))
         self._check(rc, "mtg_solve_batch")
         return dict(coeffs=coeffs, cost=cost, free=free, status=status)
+
+    def cost_time_fd_batch(self, positions, seg_times, free, increment_time, central=True,
+                           end_derivatives=None, N: int = 10, derivative: int = 4, layout: str = "soa",
+                           stream=None):
+        """mtg_cost_time_fd_batch. Returns J [B], J_plus/J_minus/grad ([K,B] soa, [B,K] aos), status."""
+        aos = layout == "aos"
+        if aos:
+            B, Kp1, D = positions.shape
+        else:
+            Kp1, D, B = positions.shape
+        K = Kp1 - 1
+        mode = self._mode(positions)
+        desc = ProblemDesc(B, K, D, N, derivative, mode, LAYOUT_AOS if aos else LAYOUT_SOA)
+        shape = (B, K) if aos else (K, B)
+        J = self._empty(positions, (B,))
+        Jp, grad = self._empty(positions, shape), self._empty(positions, shape)
+        Jm = self._empty(positions, shape) if central else None
+        status = self._empty(positions, (B,), "u4")
+        rc = self._lib.mtg_cost_time_fd_batch(self._h, C.byref(desc), _ptr(positions), _ptr(end_derivatives),
+                                              _ptr(seg_times), _ptr(free), float(increment_time),
+                                              1 if central else 0, _ptr(J), _ptr(Jp), _ptr(Jm), _ptr(grad),
+                                              _ptr(status), self._stream(mode, stream))
+        self._check(rc, "mtg_cost_time_fd_batch")
+        return dict(J=J, J_plus=Jp, J_minus=Jm, grad=grad, status=status)
 
     # ------------------------------------------------------------- evaluation
     def _shape_kdn(self, coeffs, aos):

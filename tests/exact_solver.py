@@ -83,3 +83,36 @@ def exact_solve(N, derivative, times, mask, values):
             c = Ainvs[i] * nd
             coeffs[i, dim, :] = [float(x) for x in c]
     return coeffs, float(cost), d_p
+
+
+def exact_cost_derivative(N, derivative, times, mask, values, d_p):
+    """J_d = sum_dim [d_f; d_p]^T R(times) [d_f; d_p] (NL_I:1537-1606, no 1/2) in 60 digits,
+    for the float64 inputs as given (d_p [D, n_free] held fixed)."""
+    d = derivative
+    h = N // 2
+    K = len(times)
+    D = values.shape[2]
+    all_c, fixed, free, cols = constraint_columns(mask)
+    nf = len(fixed)
+    J = mp.mpf(0)
+    for i in range(K):
+        t = mp.mpf(float(times[i]))
+        A = mp.zeros(N, N)
+        for r in range(h):
+            A[r, r] = _base(r, r)
+            for j in range(r, N):
+                A[r + h, j] = _base(r, j) * t ** (j - r)
+        Q = mp.zeros(N, N)
+        for a in range(d, N):
+            for b in range(d, N):
+                e = a + b - 2 * d + 1
+                Q[a, b] = _base(d, a) * _base(d, b) * t ** e * 2 / e
+        for dim in range(D):
+            dv = []
+            for r in range(N):
+                v, k = all_c[i * N + r]
+                col = cols[(v, k)]
+                dv.append(mp.mpf(float(values[v, k, dim])) if col < nf else mp.mpf(float(d_p[dim][col - nf])))
+            c = mp.lu_solve(A, mp.matrix(dv))
+            J += (c.T * Q * c)[0]
+    return J
