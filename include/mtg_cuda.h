@@ -203,6 +203,30 @@ int mtg_feasibility_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const doub
                           double* max_v, double* max_a, uint8_t* feasible, int32_t* n_samples,
                           uint32_t* status, void* stream);
 
+/* --------------------------------- E6 / R1: analytic extrema of |p^(derivative)(t)|
+ * Trajectory::computeMinMaxMagnitude(derivative, all dimensions, &minimum, &maximum)
+ * [src/trajectory.cpp:184-220] for every trajectory, with
+ * Segment::computeMinMaxMagnitudeCandidates / selectMinMaxMagnitudeFromCandidates
+ * [src/segment.cpp:82-184], Polynomial::convolve / computeMinMaxCandidates
+ * [src/polynomial.cpp:32-83, 163-181] and the Jenkins-Traub root finder
+ * [src/rpoly/rpoly_ak1.cpp:57-937] behind it; also what
+ * PolynomialOptimization::computeMaximumOfMagnitude [LIN_I:455-487] and the v/a limit
+ * check evaluateMaximumMagnitudeConstraint [NL_I:2686-2733] consume (seg_max_*).
+ * The candidate times of a segment are t = 0, t = T and the real roots in [0, T] of
+ * g = sum_dim p_dim^(d) * p_dim^(d+1) (one dimension: of p^(d+1)); candidate order and tie
+ * rules are the reference's (first candidate / earliest segment wins). Times are relative to
+ * the segment start (extremum.h:41-42). The real roots are isolated by a bounded derivative-
+ * chain + bracketed-Newton scheme instead of a port of rpoly: extremum VALUES agree with the
+ * reference to rounding; extremum TIMES to the root accuracy of either method, except where
+ * a root is (numerically) multiple, e.g. at the rest-to-rest ends.
+ *  min_value, min_time, max_value, max_time [B] double; min_seg, max_seg [B] int32  out or NULL
+ *  seg_max_value, seg_max_time [K]   out or NULL, maximum of every segment
+ * status: MTG_ST_NO_CONVERGENCE if a bracketed refinement hit its iteration cap. */
+int mtg_extrema_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                      const double* seg_times, int derivative, double* min_value, double* min_time,
+                      int32_t* min_seg, double* max_value, double* max_time, int32_t* max_seg,
+                      double* seg_max_value, double* seg_max_time, uint32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,8 @@ def load() -> C.CDLL:
     lib.mtg_solve_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, u32p, vp]
     lib.mtg_cost_time_fd_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, C.c_double, C.c_int,
                                            dp, dp, dp, dp, u32p, vp]
+    lib.mtg_extrema_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, C.c_int, dp, dp, vp, dp, dp, vp, dp, dp,
+                                      u32p, vp]
     lib.mtg_max_time_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, vp]
     lib.mtg_eval_range_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, C.c_int, C.c_int,
                                          dp, dp, vp, vp, u32p, vp]
@@ -298,6 +300,26 @@ class Context:
                                          self._stream(mode, stream))
         self._check(rc, "mtg_eval_at_batch")
         return dict(out=out, segment_idx=segs, status=status)
+
+    def extrema_batch(self, coeffs, seg_times, derivative, layout="soa", want_segments=False, stream=None):
+        """mtg_extrema_batch: min/max of |p^(derivative)| per trajectory (value, segment-relative time,
+        segment) and optionally per segment (seg_max_value/seg_max_time: soa [K,B], aos [B,K])."""
+        aos, B, K, D, N, mode, desc = self._desc_for(coeffs, layout)
+        out = {k: self._empty(coeffs, (B,)) for k in ("min_value", "min_time", "max_value", "max_time")}
+        out["min_seg"] = self._empty(coeffs, (B,), "i4")
+        out["max_seg"] = self._empty(coeffs, (B,), "i4")
+        out["status"] = self._empty(coeffs, (B,), "u4")
+        sv = st = None
+        if want_segments:
+            sv = self._empty(coeffs, (B, K) if aos else (K, B))
+            st = self._empty(coeffs, (B, K) if aos else (K, B))
+        rc = self._lib.mtg_extrema_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(seg_times), derivative,
+                                         _ptr(out["min_value"]), _ptr(out["min_time"]), _ptr(out["min_seg"]),
+                                         _ptr(out["max_value"]), _ptr(out["max_time"]), _ptr(out["max_seg"]),
+                                         _ptr(sv), _ptr(st), _ptr(out["status"]), self._stream(mode, stream))
+        self._check(rc, "mtg_extrema_batch")
+        out["seg_max_value"], out["seg_max_time"] = sv, st
+        return out
 
     def feasibility_batch(self, coeffs, seg_times, t_start, t_end, dt, v_max, a_max, positions=None,
                           radii=None, max_samples=1024, layout="soa", want_samples=False, want_flags=True,
