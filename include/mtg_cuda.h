@@ -227,6 +227,32 @@ int mtg_extrema_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* 
                       int32_t* min_seg, double* max_value, double* max_time, int32_t* max_seg,
                       double* seg_max_value, double* seg_max_time, uint32_t* status, void* stream);
 
+/* ------------------------------------------- candidate sweep: argmin of computeCost()
+ * The reference picks the best of many candidate trajectories on the host, one
+ * computeCost() [LIN_I:113-130] at a time (e.g. the random restarts of
+ * PolynomialOptimizationNonLinear, NL_I:274-330). Sharded over GPUs, the sweep needs
+ * exactly one exchange: every rank's {cost, global index} pair (16 bytes).
+ *
+ * mtg_argmin_batch: device-side argmin over cost[0..n) (DEVICE pointers). Entries whose
+ * status is non-zero (status may be NULL) or whose cost is NaN never win; ties go to the
+ * lower global index = global_offset + i. best -> device struct {double cost; int64 idx}
+ * (idx = -1 when nothing qualified); accumulate != 0 folds the pair already stored in
+ * *best into the result (running argmin over several batches).
+ *
+ * mtg_nccl_unique_id / mtg_nccl_init: one NCCL communicator per context (ncclGetUniqueId
+ * on rank 0, the 128 id bytes handed to every rank by the host's own channel, then
+ * ncclCommInitRank). NCCL is dlopen()ed on first use (MTG_NCCL_LIB, else libnccl.so.2).
+ *
+ * mtg_argmin_allgather: local argmin + ncclAllGather of the pairs over NVLink/NVSwitch +
+ * final selection; returns the same (cost, index) on every rank through HOST pointers
+ * (the stream is synchronised). Without an initialised communicator it is the local argmin. */
+int mtg_argmin_batch(mtg_ctx* ctx, const double* cost, const uint32_t* status, int64_t n,
+                     int64_t global_offset, int accumulate, void* best, void* stream);
+int mtg_nccl_unique_id(mtg_ctx* ctx, uint8_t id[128]);
+int mtg_nccl_init(mtg_ctx* ctx, const uint8_t id[128], int rank, int world);
+int mtg_argmin_allgather(mtg_ctx* ctx, const double* cost, const uint32_t* status, int64_t n_local,
+                         int64_t global_offset, double* best_cost, int64_t* best_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

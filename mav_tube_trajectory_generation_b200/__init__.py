@@ -6,7 +6,7 @@ of ``include/mtg_cuda.h``) plus the C++ class shim under
 ``include/mav_tube_trajectory_generation``. This Python package only builds and
 binds the library for tests and ``bench.py``.
 """
-from . import _build  # noqa: F401
+from . import _build, sweep  # noqa: F401
 from .capi import Context, MtgError, get_tables, load  # noqa: F401
 
 __all__ = ["Context", "MtgError", "get_tables", "load"]

@@ -67,6 +67,11 @@ def load() -> C.CDLL:
                                            dp, dp, dp, dp, u32p, vp]
     lib.mtg_extrema_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, C.c_int, dp, dp, vp, dp, dp, vp, dp, dp,
                                       u32p, vp]
+    lib.mtg_argmin_batch.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.c_int, vp, vp]
+    lib.mtg_nccl_unique_id.argtypes = [vp, C.c_char_p]
+    lib.mtg_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+    lib.mtg_argmin_allgather.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int64), vp]
     lib.mtg_max_time_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, vp]
     lib.mtg_eval_range_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, C.c_int, C.c_int,
                                          dp, dp, vp, vp, u32p, vp]
@@ -227,6 +232,47 @@ class Context:
                                               _ptr(status), self._stream(mode, stream))
         self._check(rc, "mtg_cost_time_fd_batch")
         return dict(J=J, J_plus=Jp, J_minus=Jm, grad=grad, status=status)
+
+    # ------------------------------------------------------------ sweep argmin
+    def argmin_batch(self, cost, status=None, global_offset: int = 0, best=None, accumulate=False, stream=None):
+        """mtg_argmin_batch on CUDA tensors. `best` is a 2-element int64 CUDA tensor holding the device
+        struct {double cost; int64 idx}; returns it (decode with `decode_best`)."""
+        import torch
+
+        if not (_is_torch(cost) and cost.is_cuda):
+            raise MtgError("argmin_batch takes CUDA tensors")
+        if best is None:
+            best = torch.zeros(2, dtype=torch.int64, device=cost.device)
+            accumulate = False
+        rc = self._lib.mtg_argmin_batch(self._h, _ptr(cost), _ptr(status), cost.numel(), int(global_offset),
+                                        1 if accumulate else 0, _ptr(best), self._stream(MTG_MEM_DEVICE, stream))
+        self._check(rc, "mtg_argmin_batch")
+        return best
+
+    @staticmethod
+    def decode_best(best):
+        """(cost, idx) from the device pair (synchronises)."""
+        import torch
+
+        h = best.cpu()
+        return float(h[:1].view(torch.float64)[0]), int(h[1])
+
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self._lib.mtg_nccl_unique_id(self._h, buf), "mtg_nccl_unique_id")
+        return buf.raw
+
+    def nccl_init(self, unique_id: bytes, rank: int, world: int):
+        self._check(self._lib.mtg_nccl_init(self._h, C.create_string_buffer(unique_id, 128), rank, world),
+                    "mtg_nccl_init")
+
+    def argmin_allgather(self, cost, status=None, global_offset: int = 0, stream=None):
+        """mtg_argmin_allgather: (best_cost, best_global_idx), identical on every rank."""
+        bc, bi = C.c_double(0.0), C.c_int64(-1)
+        rc = self._lib.mtg_argmin_allgather(self._h, _ptr(cost), _ptr(status), cost.numel(), int(global_offset),
+                                            C.byref(bc), C.byref(bi), self._stream(MTG_MEM_DEVICE, stream))
+        self._check(rc, "mtg_argmin_allgather")
+        return bc.value, bi.value
 
     # ------------------------------------------------------------- evaluation
     def _shape_kdn(self, coeffs, aos):

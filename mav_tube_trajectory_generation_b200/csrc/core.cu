@@ -47,6 +47,8 @@ int ensure_tables(mtg_ctx* ctx, int N, int derivative) {
   return MTG_OK;
 }
 
+void destroy_nccl_state(mtg_ctx* ctx);  // argmin.cu
+
 int validate_desc(mtg_ctx* ctx, const mtg_problem_desc* d) {
   if (!ctx) return MTG_ERR_INVALID_ARGUMENT;
   if (!d) return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "desc is NULL");
@@ -101,6 +103,7 @@ void mtg_destroy(mtg_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  mtg::destroy_nccl_state(ctx);
   for (int i = 0; i < kStageSlots; ++i) {
     ctx->stage[i].release();
     if (ctx->stage_stream[i]) cudaStreamDestroy(ctx->stage_stream[i]);

@@ -1,0 +1,76 @@
+"""-m gpu tests of the candidate-sweep reduction: mtg_argmin_batch / mtg_argmin_allgather
+(single rank here; the 2-rank NCCL path is exercised by tools/nccl_argmin_check.py under
+torchrun, and its host plumbing by tests/test_sweep_dist_cpu.py on gloo)."""
+import numpy as np
+import pytest
+
+from gpu_util import ctx, dev, host, random_problems, soa
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_argmin(cost, status=None, offset=0):
+    ok = ~np.isnan(cost)
+    if status is not None:
+        ok &= status == 0
+    if not ok.any():
+        return float("inf"), -1
+    m = cost[ok].min()
+    return float(m), offset + int(np.flatnonzero(ok & (cost == m))[0])
+
+
+@pytest.mark.parametrize("n", [1, 31, 257, 65536, 1_000_003])
+def test_argmin_matches_serial_scan(n):
+    import torch
+
+    rng = np.random.RandomState(n)
+    cost = rng.uniform(1.0, 100.0, size=n)
+    if n > 100:
+        cost[rng.randint(0, n, size=20)] = np.nan
+        lo = cost[~np.isnan(cost)].min() * 0.5
+        cost[[n - 3, 17, n // 2]] = lo                    # ties: the lowest index wins
+    c = ctx()
+    best = c.argmin_batch(dev(cost), global_offset=1000)
+    assert c.decode_best(best) == ref_argmin(cost, None, 1000)
+    # failed solves (status != 0) never win
+    status = np.zeros(n, dtype=np.int32)
+    if n > 100:
+        status[17] = 2
+    best = c.argmin_batch(dev(cost), status=dev(status), global_offset=0)
+    assert c.decode_best(best) == ref_argmin(cost, status, 0)
+    # the gather entry point without a communicator is the local argmin
+    assert c.argmin_allgather(dev(cost), status=dev(status), global_offset=5) == ref_argmin(cost, status, 5)
+    torch.cuda.synchronize()
+
+
+def test_running_argmin_and_empty():
+    c = ctx()
+    rng = np.random.RandomState(3)
+    chunks = [rng.uniform(0, 10, size=5000) for _ in range(6)]
+    best = None
+    for k, ch in enumerate(chunks):
+        best = c.argmin_batch(dev(ch), global_offset=5000 * k, best=best, accumulate=True)
+    assert c.decode_best(best) == ref_argmin(np.concatenate(chunks))
+    nothing = np.full(100, np.nan)
+    assert c.decode_best(c.argmin_batch(dev(nothing))) == (float("inf"), -1)
+    assert c.argmin_allgather(dev(nothing)) == (float("inf"), -1)
+
+
+def test_sweep_argmin_equals_oracle(po):
+    """BASELINE config 5 at a size the oracle finishes in seconds: the index and cost of the best
+    candidate equal the oracle's (cost parity 1e-9; the winner is well separated)."""
+    B = 20000
+    pos, times = random_problems(po, 200, 10, 3, seed0=123)
+    rng = np.random.RandomState(5)
+    pos = np.repeat(pos, B // 200, axis=0) + rng.normal(0, 1.0, size=(B, 11, 3))
+    times = np.repeat(times, B // 200, axis=0) * rng.uniform(0.9, 1.3, size=(B, 10))
+    c = ctx()
+    sol = c.solve_batch(dev(soa(pos)), dev(soa(times)))
+    cost_gpu = host(sol["cost"])
+    got_c, got_i = c.argmin_allgather(sol["cost"], status=sol["status"])
+    assert (got_c, got_i) == ref_argmin(cost_gpu, host(sol["status"]))
+    _, ref_cost = po.solve_canonical_batch(pos, times, n_threads=8)
+    order = np.argsort(ref_cost)
+    assert got_i == order[0]
+    assert abs(got_c - ref_cost[order[0]]) <= 1e-9 * ref_cost[order[0]]
+    assert ref_cost[order[1]] - ref_cost[order[0]] > 1e-6 * ref_cost[order[0]]   # a real winner
