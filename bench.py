@@ -7,8 +7,11 @@ Workload (BASELINE.json configs[1]): a batch of 65,536 random 3-D, 10-segment,
 N = 10 min-snap problems per GPU (random vertices in a +-10 m box, Nfabian
 segment times v_max = 3, a_max = 5 — the reference's createRandomVertices +
 estimateSegmentTimes recipe, vectorised with numpy's RNG). One "step" = one
-mtg_solve_batch over that batch: Q/A/R construction, the R_pp solve, all 300
-coefficients and the cost of every trajectory.
+mtg_solve_batch over that batch (Q/A/R construction, the R_pp solve, all 300
+coefficients and the cost of every trajectory) followed by mtg_argmin_batch, which
+folds the batch into the running best candidate (the sweep of BASELINE configs[4]);
+the timed region ends with the one collective of the sharded sweep: an all-gather of
+one 16-byte {cost, index} pair per rank (torch.distributed / NCCL), also at N = 1.
 
   value : trajectories solved / s, whole job, inputs resident in HBM (CUDA events)
   e2e   : the same through the C ABI with PINNED HOST buffers (H2D + kernel + D2H
@@ -16,6 +19,9 @@ coefficients and the cost of every trajectory.
   roofline    : algorithmic bytes (2,752 B / trajectory) / kernel time vs measured HBM peak
   cpu_baseline: the oracle (a port of the reference algorithm; Eigen is not on the image)
                 on all host cores over a bounded sample
+  sweep       : BASELINE configs[3] beside it (not part of `value`): evaluateRange and the fused
+                v/a/tube feasibility sweep, 1000 samples per trajectory, samples/s and fraction of
+                the measured HBM peak (rank 0, N = 1 only; --no-sweep skips it)
 `--impl reference` times that CPU port alone (rank 0 only).
 """
 import argparse
@@ -37,6 +43,9 @@ BYTES_PER_TRAJ = BYTES_IN + BYTES_OUT               # 2,752  
 FLOP_PER_TRAJ_REF = 8.8e4                           # reference formulation
 N_ROTATE = 4                                        # rotating buffer sets: 4 x 180 MB > L2 (126 MB)
 METRIC = "min-snap trajectories solved/sec (N=10, 10 seg, 3D)"
+TRAFFIC_PER_LAUNCH = 122.66e6                      # bytes: dram read 22.63 MB + write 100.03 MB (profiles/r01_solve_full.txt)
+SWEEP_BATCH = 1_000_000                             # BASELINE configs[3]: 1M trajectories x 1000 samples
+SWEEP_SAMPLES = 1000
 
 
 def make_workload(batch, seed):
@@ -168,11 +177,67 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def sweep_section(ctx, peak, batch=None):
+    """BASELINE configs[3]: evaluateRange + fused v/a/tube feasibility sweep, S ~ 1000 samples per
+    trajectory, trajectory-contiguous outputs (the reference's order), device-resident."""
+    import torch
+
+    B = batch or SWEEP_BATCH
+    S = SWEEP_SAMPLES
+    pos, times = make_workload(B, seed=4)
+    pos = np.ascontiguousarray(np.moveaxis(pos, -1, 0))
+    times = np.ascontiguousarray(np.moveaxis(times, -1, 0))
+    p, t = torch.from_numpy(pos).cuda(), torch.from_numpy(times).cuda()
+    sol = ctx.solve_batch(p, t, layout="aos")
+    tmax = ctx.max_time_batch(t, layout="aos")
+    dt = tmax / S
+    Smax = S + 8
+    samples = torch.empty((B, Smax, DIM), dtype=torch.float64, device="cuda")
+    flags = torch.empty((B, Smax), dtype=torch.uint8, device="cuda")
+    radii = torch.full((B, K_SEG, 2), 0.15, dtype=torch.float64, device="cuda")
+    n0 = ctx.launch_count
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    r = ctx.eval_range_batch(sol["coeffs"], t, 0.0, tmax, dt, 0, Smax, layout="aos", out={"samples": samples})
+    nsamp = int(r["n_samples"].sum().item())
+    out = {"workload": f"configs[3]: {B} trajectories x ~{S} samples (dt = max_time/{S}), AoS outputs; "
+                       f"outputs ({samples.numel() * 8 / 1e9:.1f} GB) exceed L2",
+           "samples": nsamp, "unit": "samples/s", "hbm_peak_gbs": peak}
+    secs = timed(lambda: ctx.eval_range_batch(sol["coeffs"], t, 0.0, tmax, dt, 0, Smax, layout="aos",
+                                              out={"samples": samples, "n_samples": r["n_samples"]}))
+    bps = 24 + 2.48
+    out["eval_range"] = {"value": nsamp / secs, "ms": secs * 1e3, "bytes_per_sample": bps,
+                         "achieved_gbs": bps * nsamp / secs / 1e9, "frac": bps * nsamp / secs / 1e9 / peak}
+    secs = timed(lambda: ctx.feasibility_batch(sol["coeffs"], t, 0.0, tmax, dt, 3.0, 5.0, positions=p, radii=radii,
+                                               max_samples=Smax, layout="aos", want_samples=True,
+                                               out={"samples": samples, "flags": flags}))
+    bps = 25 + 2.48
+    out["feasibility"] = {"value": nsamp / secs, "ms": secs * 1e3, "bytes_per_sample": bps,
+                          "achieved_gbs": bps * nsamp / secs / 1e9, "frac": bps * nsamp / secs / 1e9 / peak}
+    secs = timed(lambda: (ctx.extrema_batch(sol["coeffs"], t, 1, layout="aos"),
+                          ctx.extrema_batch(sol["coeffs"], t, 2, layout="aos")), reps=2)
+    out["extrema_v_and_a"] = {"value": 2 * K_SEG * B / secs, "unit": "root problems/s (degree 15 and 13)",
+                              "ms": secs * 1e3}
+    out["gpu_launches"] = int(ctx.launch_count - n0)
+    return out
+
+
 def workload_config(n_gpus):
     return {"workload": "configs[1]: batch of 65,536 random 3-D 10-segment min-snap (N=10) solves per GPU",
             "batch_per_gpu": BATCH_PER_GPU, "segments": K_SEG, "dims": DIM, "N": NCOEF,
             "derivative_to_optimize": DERIV, "global_batch": BATCH_PER_GPU * n_gpus,
-            "parallelism": f"batch sharded over {n_gpus} GPU(s), no data-path collective",
+            "parallelism": f"batch sharded over {n_gpus} GPU(s); one 16-byte argmin all-gather per rank at the "
+                           "end of the timed region",
             "l2": f"inputs+outputs rotate over {N_ROTATE} buffer sets of 180 MB (> 126 MB L2)"}
 
 
@@ -184,6 +249,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-sweep", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--sweep-batch", type=int, default=SWEEP_BATCH, help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -199,6 +266,7 @@ def main():
     import torch.distributed as dist
 
     import mav_tube_trajectory_generation_b200 as m
+    from mav_tube_trajectory_generation_b200 import sweep
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
@@ -223,9 +291,16 @@ def main():
                 "cost": torch.empty((B,), dtype=torch.float64).pin_memory(),
                 "status": torch.empty((B,), dtype=torch.int32).pin_memory()}
 
-    def step(i):
+    best = torch.zeros(2, dtype=torch.int64, device="cuda")   # device pair {cost, global index}
+    start, _ = sweep.shard_range(B * world, rank, world)
+
+    def step(i, fresh=False):
         p, t = dev_in[i % N_ROTATE]
-        ctx.solve_batch(p, t, N=NCOEF, derivative=DERIV, out=dev_out[i % N_ROTATE])
+        o = dev_out[i % N_ROTATE]
+        ctx.solve_batch(p, t, N=NCOEF, derivative=DERIV, out=o)
+        # candidate index = step * global_batch + position in the global batch
+        ctx.argmin_batch(o["cost"], status=o["status"], global_offset=i * B * world + start, best=best,
+                         accumulate=not fresh)
 
     def barrier():
         torch.cuda.synchronize()
@@ -242,7 +317,8 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
-        step(i)
+        step(i, fresh=(i == 0))
+    best_cost, best_idx = sweep.gather_argmin(best=best)     # the sweep's only exchange (16 B / rank)
     ev1.record()
     barrier()
     launches = ctx.launch_count - n0
@@ -274,25 +350,39 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        kernel_s = ms_per_step * 1e-3                 # one kernel launch per step
+        # the solve kernel's own duration: CUDA events around it alone, same buffers, on the launch stream
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 50
+        k0.record()
+        for i in range(reps):
+            p, t = dev_in[i % N_ROTATE]
+            ctx.solve_batch(p, t, N=NCOEF, derivative=DERIV, out=dev_out[i % N_ROTATE])
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_s = k0.elapsed_time(k1) / reps * 1e-3
         achieved = BYTES_PER_TRAJ * B / kernel_s / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world), "gpu_launches": int(launches),
-            "status_nonzero": bad,
+            "status_nonzero": bad, "sweep_argmin": {"cost": best_cost, "candidate": best_idx},
             "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": BYTES_IN * B,
                     "d2h_bytes_per_step": (BYTES_OUT + 4) * B, "steps": e2e_steps,
                     "note": "mtg_solve_batch(MTG_MEM_HOST) on pinned buffers: chunked H2D/kernel/D2H "
                             "pipeline inside the call; wall clock between device synchronisations"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "solve_canonical_kernel<5,3>",
+                         "frac": achieved / peak, "peak_source": peak_src,
+                         "kernel": "solve_canonical_kernel<5,3,false>", "kernel_ms": kernel_s * 1e3,
+                         "kernel_share_of_step": kernel_s * 1e3 / ms_per_step,
+                         "traffic": TRAFFIC_PER_LAUNCH if B == BATCH_PER_GPU else None,
+                         "traffic_source": "profiles/r01_solve_full.txt (ncu --set full, dram__bytes_read+write)",
                          "algorithmic_bytes_per_trajectory": BYTES_PER_TRAJ,
                          "fp64_gflops_reference_formulation": FLOP_PER_TRAJ_REF * B / kernel_s / 1e9},
             "clocks": clocks,
         }
+        if world == 1 and not args.no_sweep:
+            line["sweep"] = sweep_section(ctx, peak, args.sweep_batch)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = 32768

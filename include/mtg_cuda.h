@@ -4,7 +4,7 @@
  *
  * The reference has NO plugin/FFI boundary: its boundary is the C++ class API
  * (Vertex / Polynomial / Segment / Trajectory / PolynomialOptimization<N>).
- * include/mav_tube_trajectory_generation/*.h in this repo re-creates that class
+ * the headers under include/mav_tube_trajectory_generation/ in this repo re-creates that class
  * API on top of these entry points (B = 1 per object); batched callers (bench,
  * sweeps) call them directly. Every entry point cites the reference interface
  * it replaces (paths relative to the reference root;
@@ -124,6 +124,15 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc,
                     const double* positions, const double* end_derivatives,
                     const double* seg_times, double* coeffs, double* cost,
                     double* free_constraints, uint32_t* status, void* stream);
+
+/* mtg_set_free_constraints_batch: setFreeConstraints(d_p) + updateSegmentsFromCompactConstraints
+ * + computeCost [LIN_I:489-498, 254-275, 113-130]: coefficients and cost of trajectories whose free
+ * derivatives are GIVEN (the optimiser-driven call of the non-linear layer, NL_I:1309-1310).
+ * Tensors as mtg_solve_batch, with free_constraints [D][K-1][N/2-1] an input. */
+int mtg_set_free_constraints_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* positions,
+                                   const double* end_derivatives, const double* seg_times,
+                                   const double* free_constraints, double* coeffs, double* cost,
+                                   uint32_t* status, void* stream);
 
 /* ------------------------------------- P9: finite-difference time perturbations
  * Replaces the per-segment perturbation loop of the reference's non-linear layer,

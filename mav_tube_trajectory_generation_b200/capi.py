@@ -72,6 +72,7 @@ def load() -> C.CDLL:
     lib.mtg_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
     lib.mtg_argmin_allgather.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.POINTER(C.c_double),
                                          C.POINTER(C.c_int64), vp]
+    lib.mtg_set_free_constraints_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, u32p, vp]
     lib.mtg_max_time_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, vp]
     lib.mtg_eval_range_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, C.c_int, C.c_int,
                                          dp, dp, vp, vp, u32p, vp]
@@ -208,6 +209,27 @@ class Context:
                                        _ptr(status), self._stream(mode, stream))
         self._check(rc, "mtg_solve_batch")
         return dict(coeffs=coeffs, cost=cost, free=free, status=status)
+
+    def set_free_constraints_batch(self, positions, seg_times, free, end_derivatives=None, N: int = 10,
+                                   derivative: int = 4, layout: str = "soa", stream=None):
+        """mtg_set_free_constraints_batch: coefficients + cost from given free derivatives d_p."""
+        aos = layout == "aos"
+        if aos:
+            B, Kp1, D = positions.shape
+        else:
+            Kp1, D, B = positions.shape
+        K = Kp1 - 1
+        mode = self._mode(positions)
+        desc = ProblemDesc(B, K, D, N, derivative, mode, LAYOUT_AOS if aos else LAYOUT_SOA)
+        coeffs = self._empty(positions, (B, K, D, N) if aos else (K, D, N, B))
+        cost = self._empty(positions, (B,))
+        status = self._empty(positions, (B,), "u4")
+        rc = self._lib.mtg_set_free_constraints_batch(self._h, C.byref(desc), _ptr(positions),
+                                                      _ptr(end_derivatives), _ptr(seg_times), _ptr(free),
+                                                      _ptr(coeffs), _ptr(cost), _ptr(status),
+                                                      self._stream(mode, stream))
+        self._check(rc, "mtg_set_free_constraints_batch")
+        return dict(coeffs=coeffs, cost=cost, status=status)
 
     def cost_time_fd_batch(self, positions, seg_times, free, increment_time, central=True,
                            end_derivatives=None, N: int = 10, derivative: int = 4, layout: str = "soa",

@@ -39,7 +39,89 @@ int launch_fd_n(mtg_ctx* ctx, int N, int D, const CostFdParams& p, cudaStream_t 
   return fail(ctx, MTG_ERR_UNSUPPORTED, "cost_time_fd supports N in {4,6,8,10,12}");
 }
 
+template <int HN, int D, bool AOS>
+int launch_cf_t(mtg_ctx* ctx, const CostFdParams& p, const SolveCanonicalParams& sp, cudaStream_t s) {
+  const int block = 128, grid = (p.nb + block - 1) / block;
+  if (grid == 0) return MTG_OK;
+  coeffs_from_free_kernel<HN, D, AOS><<<grid, block, 0, s>>>(p, sp);
+  ++ctx->launches;
+  MTG_CUDA_TRY(cudaGetLastError());
+  return MTG_OK;
+}
+template <int HN, bool AOS>
+int launch_cf_d(mtg_ctx* ctx, int D, const CostFdParams& p, const SolveCanonicalParams& sp, cudaStream_t s) {
+  switch (D) {
+    case 1: return launch_cf_t<HN, 1, AOS>(ctx, p, sp, s);
+    case 2: return launch_cf_t<HN, 2, AOS>(ctx, p, sp, s);
+    case 3: return launch_cf_t<HN, 3, AOS>(ctx, p, sp, s);
+    case 4: return launch_cf_t<HN, 4, AOS>(ctx, p, sp, s);
+  }
+  return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "D must be 1..4");
+}
+template <bool AOS>
+int launch_cf_n(mtg_ctx* ctx, int N, int D, const CostFdParams& p, const SolveCanonicalParams& sp, cudaStream_t s) {
+  switch (N) {
+    case 4: return launch_cf_d<2, AOS>(ctx, D, p, sp, s);
+    case 6: return launch_cf_d<3, AOS>(ctx, D, p, sp, s);
+    case 8: return launch_cf_d<4, AOS>(ctx, D, p, sp, s);
+    case 10: return launch_cf_d<5, AOS>(ctx, D, p, sp, s);
+    case 12: return launch_cf_d<6, AOS>(ctx, D, p, sp, s);
+  }
+  return fail(ctx, MTG_ERR_UNSUPPORTED, "supported N: {4,6,8,10,12}");
+}
+
 }  // namespace
+
+extern "C" int mtg_set_free_constraints_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* positions,
+                                              const double* end_derivatives, const double* seg_times,
+                                              const double* free_constraints, double* coeffs, double* cost,
+                                              uint32_t* status, void* stream_) {
+  int rc = validate_desc(ctx, desc);
+  if (rc) return rc;
+  if (!positions || !seg_times || !coeffs)
+    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "positions, seg_times and coeffs are required");
+  if (desc->K > 1 && !free_constraints)
+    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "free_constraints (d_p) is required when K > 1");
+  if (desc->B == 0) return MTG_OK;
+  MTG_CUDA_TRY(cudaSetDevice(ctx->device));
+  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int B = desc->B, K = desc->K, D = desc->D, N = desc->N, NF = N / 2 - 1;
+  const bool aos = desc->layout == MTG_LAYOUT_AOS;
+  CostFdParams p = {};
+  SolveCanonicalParams sp = {};
+  p.K = sp.K = K;
+  p.derivative = sp.derivative = desc->derivative_to_optimize;
+  auto launch = [&](cudaStream_t st) {
+    sp.B = p.B; sp.b0 = p.b0; sp.nb = p.nb;
+    return aos ? launch_cf_n<true>(ctx, N, D, p, sp, st) : launch_cf_n<false>(ctx, N, D, p, sp, st);
+  };
+  if (desc->memory == MTG_MEM_DEVICE) {
+    p.positions = positions; p.end_derivatives = end_derivatives; p.seg_times = seg_times;
+    p.free_constraints = free_constraints; p.status = status;
+    sp.coeffs = coeffs; sp.cost = cost; sp.vec_ok = ((uintptr_t)coeffs % 16 == 0) ? 1 : 0;
+    p.B = B; p.b0 = 0; p.nb = B;
+    return launch(stream);
+  }
+  const size_t rec_free = (size_t)std::max(K - 1, 0) * NF * D;
+  std::vector<HostTensor> ts = {
+      {positions, (size_t)(K + 1) * D, 8, true, false, nullptr},
+      {end_derivatives, (size_t)2 * NF * D, 8, true, false, nullptr},
+      {seg_times, (size_t)K, 8, true, false, nullptr},
+      {rec_free ? free_constraints : nullptr, rec_free, 8, true, false, nullptr},
+      {coeffs, (size_t)K * D * N, 8, false, false, nullptr},
+      {cost, 1, 8, false, true, nullptr},
+      {status, 1, 4, false, true, nullptr}};
+  return run_chunked(ctx, stream, (size_t)B, aos, ts, [&](int nb, int C, cudaStream_t st) {
+    p.positions = (const double*)ts[0].dev; p.end_derivatives = (const double*)ts[1].dev;
+    p.seg_times = (const double*)ts[2].dev; p.free_constraints = (const double*)ts[3].dev;
+    sp.coeffs = (double*)ts[4].dev; sp.cost = (double*)ts[5].dev; p.status = (uint32_t*)ts[6].dev;
+    sp.vec_ok = 1;
+    p.B = C; p.b0 = 0; p.nb = nb;
+    return launch(st);
+  });
+}
 
 extern "C" int mtg_cost_time_fd_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* positions,
                                       const double* end_derivatives, const double* seg_times,

@@ -162,5 +162,55 @@ __global__ void __launch_bounds__(128) cost_time_fd_kernel(const CostFdParams p)
   }
 }
 
+// setFreeConstraints + updateSegmentsFromCompactConstraints + computeCost (LIN_I:489-498, 254-275,
+// 113-130): coefficients and cost of a trajectory whose free derivatives d_p are GIVEN (the
+// optimiser-driven path of the non-linear layer, NL_I:1309-1310). One thread per trajectory.
+template <int HN, int D, bool AOS>
+__global__ void __launch_bounds__(128) coeffs_from_free_kernel(const CostFdParams p, const SolveCanonicalParams sp) {
+  constexpr int NF = HN - 1;
+  const int local = blockIdx.x * blockDim.x + threadIdx.x;
+  if (local >= p.nb) return;
+  const int b = p.b0 + local;
+  const size_t B = (size_t)p.B;
+  const int K = p.K;
+  const size_t rec_pos = (size_t)(K + 1) * D, rec_end = (size_t)2 * NF * D, rec_free = (size_t)D * (K - 1) * NF;
+  uint32_t st = 0;
+  auto vertex = [&](int v, double (&d)[D][HN]) {
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim) {
+      d[dim][0] = p.positions[at<AOS>((size_t)v * D + dim, rec_pos, B, b)];
+#pragma unroll
+      for (int m = 1; m < HN; ++m) {
+        double x;
+        if (v == 0 || v == K)
+          x = p.end_derivatives
+                  ? p.end_derivatives[at<AOS>((size_t)((v == 0 ? 0 : 1) * NF + (m - 1)) * D + dim, rec_end, B, b)]
+                  : 0.0;
+        else
+          x = p.free_constraints[at<AOS>((size_t)(dim * (K - 1) + (v - 1)) * NF + (m - 1), rec_free, B, b)];
+        d[dim][m] = x;
+      }
+    }
+  };
+  double ds[D][HN], de[D][HN];
+  vertex(0, ds);
+  double cost = 0.0;
+  for (int i = 0; i < K; ++i) {
+    double T = p.seg_times[at<AOS>((size_t)i, (size_t)K, B, b)];
+    if (!(T > 0.0) || !(T < 1.7e308)) {  // LIN_I:296 CHECK_GT(segment_time, 0)
+      st |= 1u;
+      T = 1.0;
+    }
+    vertex(i + 1, de);
+    cost += emit_segment<HN, D, AOS>(sp, i, b, true, T, ds, de);
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim)
+#pragma unroll
+      for (int m = 0; m < HN; ++m) ds[dim][m] = de[dim][m];
+  }
+  if (sp.cost) sp.cost[b] = 0.5 * cost;
+  if (p.status) p.status[b] = st;
+}
+
 }  // namespace mtg
 #endif

@@ -119,3 +119,29 @@ def test_floor_and_errors(po):
 
     with pytest.raises(m.MtgError):
         gpu_fd(pos, times, free, 0.0, True)
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_set_free_constraints_round_trip(po, layout):
+    """setFreeConstraints (LIN_I:489-498): feeding the solved d_p back reproduces the solve's coefficients
+    bit for bit (same code path) and its cost to rounding, a perturbed d_p matches the oracle's
+    coefficients-from-constraints (P8c) and raises the cost (d_p is the minimiser)."""
+    c = ctx()
+    pos, times = random_problems(po, 256, 10, 3, seed0=600)
+    conv_in = soa if layout == "soa" else np.ascontiguousarray
+    p, t = dev(conv_in(pos)), dev(conv_in(times))
+    sol = c.solve_batch(p, t, want_free=True, layout=layout)
+    r = c.set_free_constraints_batch(p, t, sol["free"], layout=layout)
+    conv = aos if layout == "soa" else (lambda x: x)
+    assert np.array_equal(host(r["coeffs"]), host(sol["coeffs"]))
+    assert np.allclose(host(r["cost"]), host(sol["cost"]), rtol=1e-14, atol=0)   # segment sums in another order
+    free = conv(host(sol["free"])).copy()
+    free2 = free * (1.0 + 0.05 * np.random.RandomState(2).normal(size=free.shape))
+    r2 = c.set_free_constraints_batch(p, t, dev(conv_in(free2)), layout=layout)
+    assert np.all(host(r2["cost"]) > host(sol["cost"]))
+    c2 = conv(host(r2["coeffs"]))
+    for b in range(0, 256, 32):
+        mask, values = po.canonical_mask_values(pos[b])
+        ref = po.coeffs_from_free_constraints(N, times[b], mask, values, free2[b].reshape(-1))
+        den = np.abs(ref).max(axis=-1)
+        assert (np.abs(c2[b] - ref).max(axis=-1) / den).max() < 1e-9

@@ -1,0 +1,32 @@
+"""-m gpu: the C++ class API (include/mav_tube_trajectory_generation/*.h, the drop-in mirror of the
+reference's Vertex / Segment / Trajectory / PolynomialOptimization<N>) exercised by a C++ program in
+the style of the reference's gtest suite. The CPU suite only checks that it compiles and links."""
+import os
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BIN = os.path.join(HERE, "cpp", "shim_check")
+
+
+def build():
+    subprocess.run(["bash", os.path.join(HERE, "cpp", "build_check.sh")], check=True, capture_output=True)
+
+
+def test_class_api_compiles_and_links():
+    import mav_tube_trajectory_generation_b200 as m
+
+    m._build.build()
+    build()
+    assert os.path.exists(BIN)
+
+
+@pytest.mark.gpu
+def test_class_api_on_gpu():
+    if not os.path.exists(BIN):
+        build()
+    r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    print(r.stderr)
+    assert r.returncode == 0 and "SHIM OK" in r.stdout, r.stdout + r.stderr
