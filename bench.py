@@ -48,6 +48,25 @@ SWEEP_BATCH = 1_000_000                             # BASELINE configs[3]: 1M tr
 SWEEP_SAMPLES = 1000
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Only the result line may reach stdout (the driver parses it): everything libraries print
+    there (e.g. NCCL's version banner) is sent to stderr; emit() writes to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def make_workload(batch, seed):
     """positions [K+1,D,B], times [K,B] (SoA, batch innermost), float64."""
     rng = np.random.RandomState(seed)
@@ -174,7 +193,7 @@ def run_reference(args, rank, world):
                                    "reference itself cannot be built here"},
         "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def sweep_section(ctx, peak, batch=None):
@@ -252,6 +271,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--sweep-batch", type=int, default=SWEEP_BATCH, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -311,6 +331,7 @@ def main():
     # ---- device-resident throughput (CUDA events on the launching stream)
     for i in range(args.warmup):
         step(i)
+    sweep.gather_argmin(best=best)      # warm-up of the collective too (NCCL connects lazily)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     n0 = ctx.launch_count
@@ -391,7 +412,7 @@ def main():
                                     "kind": "port",
                                     "sample": f"{sample} solves of the same workload in {secs:.2f} s wall, "
                                               "OpenMP over the batch (oracle port, dense QR, prints excluded)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if distributed:
         dist.destroy_process_group()
 
