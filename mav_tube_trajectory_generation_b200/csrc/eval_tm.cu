@@ -31,7 +31,8 @@ int launch_tm_t(mtg_ctx* ctx, const EvalParams& p, const double* geom, cudaStrea
   const size_t smem = (size_t)tm_layout(D, NT, want_acc, MODE == TM_FEAS_TUBE).per_warp * (kTmBlock / 32);
   auto kern = eval_tm_kernel<NT, D, MODE>;
   if (smem > 48 * 1024) MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (p.nb + kTmBlock - 1) / kTmBlock;
+  const int per_block = (kTmBlock / 32) * kTmTPW;  // trajectories per CTA
+  const int grid = (p.nb + per_block - 1) / per_block;
   if (grid == 0) return MTG_OK;
   kern<<<grid, kTmBlock, smem, s>>>(p, geom);
   ++ctx->launches;

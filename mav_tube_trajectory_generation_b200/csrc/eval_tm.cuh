@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(256) tube_setup_kernel(const EvalParams p, dou
 // waits on DRAM in steady state (one commit group per chunk; wait_group 1 retires all
 // but the newest). A chunk stops early if a third segment would start (tiny segments
 // or large dt).
+constexpr int kTmTPW = 16;               // trajectories per warp (phase-1 lanes in use): shared memory per warp scales with it
 constexpr int kTmR = 8;                  // consecutive samples per lane in phase 2
 constexpr int kTmG = 32 / (kTmChunk / kTmR);  // trajectories per phase-2 pass (8): 4 lanes each
 struct TmLayout {
@@ -130,13 +131,13 @@ __host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool
   L.traj_bytes = 2 * L.slot_bytes + 16;
   L.blk_ld = kTmR * D + 1;
   L.row_ld = (kTmChunk / kTmR) * L.blk_ld;
-  L.off_stage = 32 * kTmTauLd * 8;
+  L.off_stage = kTmTPW * kTmTauLd * 8;
   L.off_info = L.off_stage + kTmG * L.row_ld * 8;
-  L.off_off = L.off_info + 32 * 16;
-  L.off_flag = L.off_off + 32 * 8;
+  L.off_off = L.off_info + kTmTPW * 16;
+  L.off_flag = L.off_off + kTmTPW * 8;
   L.off_acc = L.off_flag + kTmG * 40;
-  L.off_slots = L.off_acc + (want_acc ? 32 * kTmTauLd * 8 : 0);
-  L.per_warp = L.off_slots + 32 * L.traj_bytes;
+  L.off_slots = L.off_acc + (want_acc ? kTmTPW * kTmTauLd * 8 : 0);
+  L.per_warp = L.off_slots + kTmTPW * L.traj_bytes;
   L.per_warp = (L.per_warp + 15) & ~15;
   return L;
 }
@@ -146,7 +147,7 @@ enum TmMode { TM_POSITION = 0, TM_DERIVATIVE = 1, TM_FEAS = 2, TM_FEAS_TUBE = 3 
 // Requirements (checked by the launcher, which otherwise falls back to the one-thread-per-
 // trajectory kernels of eval.cuh): AoS layout, N == NT, coeffs 16-byte aligned.
 template <int NT, int D, int MODE>
-__global__ void __launch_bounds__(32, 7) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
+__global__ void __launch_bounds__(32, 12) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr bool FEAS = MODE >= TM_FEAS;
   constexpr bool tube = MODE == TM_FEAS_TUBE;
@@ -166,10 +167,10 @@ __global__ void __launch_bounds__(32, 7) eval_tm_kernel(const EvalParams p, cons
   double* acc_s = reinterpret_cast<double*>(wbase + L.off_acc);
   unsigned char* slots = wbase + L.off_slots;
 
-  const int first = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;  // local index of lane 0's trajectory
+  const int first = (blockIdx.x * (blockDim.x >> 5) + warp) * kTmTPW;  // local index of lane 0's trajectory
   if (first >= p.nb) return;
   const int local = first + lane;
-  const bool valid = local < p.nb;
+  const bool valid = local < p.nb && lane < kTmTPW;
   const int b = p.b0 + (valid ? local : p.nb - 1);
   const int K = p.K;
   const size_t S = (size_t)p.max_samples;
@@ -247,7 +248,29 @@ __global__ void __launch_bounds__(32, 7) eval_tm_kernel(const EvalParams p, cons
       double* trow = tau_s + lane * kTmTauLd;
       double* arow = acc_s + lane * kTmTauLd;
       for (;;) {
-        // straight run inside the current segment
+        // straight run inside the current segment, four samples per trip while all four are
+        // certain (same adds, same order: tau_k and acc_k are the reference's values)
+        while (cnt + 4 <= limit) {
+          const double tau1 = tau + dt, acc1 = acc + dt;
+          const double tau2 = tau1 + dt, acc2 = acc1 + dt;
+          const double tau3 = tau2 + dt, acc3 = acc2 + dt;
+          const bool ok = (acc < t1) & !(tau > Ti) & (acc1 < t1) & !(tau1 > Ti) & (acc2 < t1) & !(tau2 > Ti) &
+                          (acc3 < t1) & !(tau3 > Ti);
+          if (!ok) break;
+          trow[cnt] = tau;
+          trow[cnt + 1] = tau1;
+          trow[cnt + 2] = tau2;
+          trow[cnt + 3] = tau3;
+          if (want_acc) {
+            arow[cnt] = acc;
+            arow[cnt + 1] = acc1;
+            arow[cnt + 2] = acc2;
+            arow[cnt + 3] = acc3;
+          }
+          tau = tau3 + dt;
+          acc = acc3 + dt;
+          cnt += 4;
+        }
         while (cnt < limit && acc < t1 && !(tau > Ti)) {
           trow[cnt] = tau;
           if (want_acc) arow[cnt] = acc;
@@ -287,8 +310,10 @@ __global__ void __launch_bounds__(32, 7) eval_tm_kernel(const EvalParams p, cons
         break;
       }
     }
-    info_s[lane] = make_int4(cnt, n, seg0, cross);
-    off_s[lane] = traj_off + (size_t)n;
+    if (lane < kTmTPW) {
+      info_s[lane] = make_int4(cnt, n, seg0, cross);
+      off_s[lane] = traj_off + (size_t)n;
+    }
     __syncwarp();
     if (!__any_sync(FULL, cnt > 0)) break;
 
@@ -296,7 +321,7 @@ __global__ void __launch_bounds__(32, 7) eval_tm_kernel(const EvalParams p, cons
     // trajectory, 8 trajectories per pass. The lane's coefficients stay in registers for its 8
     // samples; the one lane whose block contains the crossing reloads in the middle.
 #pragma unroll 1
-    for (int g = 0; g < 32 / G; ++g) {
+    for (int g = 0; g < kTmTPW / G; ++g) {
       const int r = g * G + q8;
       const int4 info = info_s[r];
       if (!__any_sync(FULL, info.x > 0)) continue;
