@@ -115,7 +115,6 @@ __global__ void __launch_bounds__(256) tube_setup_kernel(const EvalParams p, dou
 // waits on DRAM in steady state (one commit group per chunk; wait_group 1 retires all
 // but the newest). A chunk stops early if a third segment would start (tiny segments
 // or large dt).
-constexpr int kTmTPW = 16;               // trajectories per warp (phase-1 lanes in use): shared memory per warp scales with it
 constexpr int kTmR = 8;                  // consecutive samples per lane in phase 2
 constexpr int kTmG = 32 / (kTmChunk / kTmR);  // trajectories per phase-2 pass (8): 4 lanes each
 struct TmLayout {
@@ -125,7 +124,11 @@ struct TmLayout {
   int row_ld;       // doubles per trajectory row of the staging tile: 4 * blk_ld
   int off_stage, off_info, off_off, off_flag, off_acc, off_slots, per_warp;
 };
-__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube) {
+// TPW = trajectories per warp (phase-1 lanes in use): the shared memory of a warp scales with it.
+// 16 doubles the resident warps of the latency-bound position sweep; the fp64-bound feasibility
+// sweep prefers full phase-1 lanes (32).
+__host__ __device__ constexpr int tm_tpw(int mode) { return mode >= 2 ? 32 : 16; }
+__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, int kTmTPW) {
   TmLayout L;
   L.slot_bytes = D * NT * 8 + (tube ? kTubeGeomLd * 8 : 0);
   L.traj_bytes = 2 * L.slot_bytes + 16;
@@ -147,17 +150,17 @@ enum TmMode { TM_POSITION = 0, TM_DERIVATIVE = 1, TM_FEAS = 2, TM_FEAS_TUBE = 3 
 // Requirements (checked by the launcher, which otherwise falls back to the one-thread-per-
 // trajectory kernels of eval.cuh): AoS layout, N == NT, coeffs 16-byte aligned.
 template <int NT, int D, int MODE>
-__global__ void __launch_bounds__(32, 12) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
+__global__ void __launch_bounds__(32, (MODE >= 2 ? 7 : 12)) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr bool FEAS = MODE >= TM_FEAS;
   constexpr bool tube = MODE == TM_FEAS_TUBE;
   constexpr int Q = D * NT / 2;  // 16-byte pieces of one segment's coefficients
-  constexpr int R = kTmR, G = kTmG;
+  constexpr int R = kTmR, G = kTmG, kTmTPW = tm_tpw(MODE);
   static_assert(!tube || D == 3, "the tube predicate is 3-D");
   extern __shared__ __align__(16) unsigned char tm_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool want_acc = (!FEAS) && p.sampling_times != nullptr;
-  const TmLayout L = tm_layout(D, NT, want_acc, tube);
+  const TmLayout L = tm_layout(D, NT, want_acc, tube, kTmTPW);
   unsigned char* wbase = tm_smem + (size_t)warp * L.per_warp;
   double* tau_s = reinterpret_cast<double*>(wbase);
   double* stage = reinterpret_cast<double*>(wbase + L.off_stage);
