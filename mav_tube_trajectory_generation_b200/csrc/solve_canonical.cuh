@@ -229,14 +229,14 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
 
   const size_t rec_pos = (size_t)(K + 1) * D, rec_t = (size_t)K, rec_end = (size_t)2 * NF * D;
   auto pos = [&](int v, int dim) { return p.positions[at<AOS>((size_t)v * D + dim, rec_pos, B, b)]; };
-  auto seg_time = [&](int i) {
-    double T = p.seg_times[at<AOS>((size_t)i, rec_t, B, b)];
+  auto checked_time = [&](double T) {
     if (!(T > 0.0) || !(T < 1.7e308)) {  // LIN_I:296 CHECK_GT(segment_time, 0)
       st |= 1u;
       T = 1.0;
     }
     return T;
   };
+  auto seg_time = [&](int i) { return checked_time(p.seg_times[at<AOS>((size_t)i, rec_t, B, b)]); };
   // chain -> original indices
   auto V = [&](int j) { return side ? K - j : j; };
   auto SG = [&](int c) { return side ? K - 1 - c : c; };
@@ -295,6 +295,16 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
     p_cur[dim] = sdt[dim][0];
     p_next[dim] = pos(V(1), dim);
   }
+  // inputs of step j are requested during step j-1: the loads (and the division inside
+  // segment_powers that waits on them) are off the critical path of the elimination
+  double T_ahead = 1.0, p_ahead[D];
+#pragma unroll
+  for (int dim = 0; dim < D; ++dim) p_ahead[dim] = 0.0;
+  if (n_own >= 1) {
+    T_ahead = p.seg_times[at<AOS>((size_t)SG(1), rec_t, B, b)];
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim) p_ahead[dim] = pos(V(2), dim);
+  }
 #pragma unroll 1
   for (int j = 1;; ++j) {
     const bool own = (j <= n_own);
@@ -306,9 +316,14 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
       p_cur[dim] = p_next[dim];
     }
     if (own) {
-      segment_powers<HN>(seg_time(SG(j)), d, pr);
+      segment_powers<HN>(checked_time(T_ahead), d, pr);
 #pragma unroll
-      for (int dim = 0; dim < D; ++dim) p_next[dim] = pos(V(j + 1), dim);
+      for (int dim = 0; dim < D; ++dim) p_next[dim] = p_ahead[dim];
+      if (j + 1 <= n_own) {
+        T_ahead = p.seg_times[at<AOS>((size_t)SG(j + 1), rec_t, B, b)];
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) p_ahead[dim] = pos(V(j + 2), dim);
+      }
     }
     // contribution of the chain segment on the left of vertex j
 #pragma unroll
@@ -447,9 +462,11 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
 
   // ---------------------------------------------------------------- backward
   double xs[D][HN];
+  double T_back = p.seg_times[at<AOS>((size_t)SG(n_own), rec_t, B, b)];  // requested one step ahead, as above
 #pragma unroll 1
   for (int c = n_own; c >= 0; --c) {
-    const double T = seg_time(SG(c));
+    const double T = checked_time(T_back);
+    if (c > 0) T_back = p.seg_times[at<AOS>((size_t)SG(c - 1), rec_t, B, b)];
     if (c == 0) {
 #pragma unroll
       for (int dim = 0; dim < D; ++dim)
