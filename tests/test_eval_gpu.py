@@ -311,3 +311,45 @@ def test_feasibility_limits_scale_with_times(po):
     assert np.all((out[1.0][2] == 500) | (out[1.0][2] == 501))
     assert np.allclose(out[2.0][0], out[1.0][0] / 2, rtol=1e-9)
     assert np.allclose(out[2.0][1], out[1.0][1] / 4, rtol=1e-9)
+
+
+def test_sweep_at_scale_two_kernels_agree(po):
+    """BASELINE config 4 at 1/8 size (131,072 trajectories x ~1000 samples): the two independent
+    implementations of the sweep — one thread per trajectory with SoA outputs (eval.cuh) and the
+    warp-cooperative kernel with trajectory-contiguous outputs (eval_tm.cuh) — replay the same serial
+    recurrence and the same FMA chains, so sample counts, flags and every sample agree BIT FOR BIT;
+    plus the size-independent facts: 1000 or 1001 samples, the first sample is the start vertex."""
+    import torch
+
+    B = 131072
+    base_pos, base_t = random_problems(po, 256, 10, 3, seed0=4000)
+    rng = np.random.RandomState(11)
+    pos = np.repeat(base_pos, B // 256, axis=0) + rng.normal(0, 0.3, size=(B, 11, 3))
+    times = np.repeat(base_t, B // 256, axis=0) * rng.uniform(0.7, 1.6, size=(B, 10))
+    c = ctx()
+    p_soa, t_soa = dev(soa(pos)), dev(soa(times))
+    sol = c.solve_batch(p_soa, t_soa)
+    coeffs_aos = sol["coeffs"].permute(3, 0, 1, 2).contiguous()
+    t_aos = t_soa.t().contiguous()
+    p_aos = p_soa.permute(2, 0, 1).contiguous()
+    tm = c.max_time_batch(t_soa)
+    S = 1010
+    radii_aos = torch.full((B, 10, 2), 0.4, dtype=torch.float64, device="cuda")
+    radii_soa = radii_aos.permute(1, 2, 0).contiguous()
+    a = c.feasibility_batch(coeffs_aos, t_aos, 0.0, tm, tm / 1000, 3.0, 5.0, positions=p_aos, radii=radii_aos,
+                            max_samples=S, layout="aos", want_samples=True)
+    s = c.feasibility_batch(sol["coeffs"], t_soa, 0.0, tm, tm / 1000, 3.0, 5.0, positions=p_soa, radii=radii_soa,
+                            max_samples=S, layout="soa", want_samples=True)
+    n = a["n_samples"]
+    assert torch.equal(n, s["n_samples"]) and int(a["status"].max()) == 0 and int(s["status"].max()) == 0
+    assert bool(((n == 1000) | (n == 1001)).all()) and int((n == 1001).sum()) > 0
+    valid = torch.arange(S, device="cuda")[None, :] < n[:, None]                       # [B, S]
+    sa, ss = a["samples"], s["samples"].permute(2, 0, 1)                                # [B, S, 3]
+    assert torch.equal(torch.where(valid[:, :, None], sa, torch.zeros_like(sa)),
+                       torch.where(valid[:, :, None], ss, torch.zeros_like(ss)))
+    fa, fs = a["flags"], s["flags"].t()
+    assert torch.equal(torch.where(valid, fa, torch.zeros_like(fa)), torch.where(valid, fs, torch.zeros_like(fs)))
+    assert torch.equal(a["max_v"], s["max_v"]) and torch.equal(a["max_a"], s["max_a"])
+    assert torch.equal(a["feasible"], s["feasible"])
+    assert float((sa[:, 0, :] - p_aos[:, 0, :]).abs().max()) < 1e-9                    # starts at vertex 0
+    assert int((fa[valid] & 4).sum()) > 0                                               # some samples inside the tube
