@@ -125,6 +125,20 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc,
                     const double* seg_times, double* coeffs, double* cost,
                     double* free_constraints, uint32_t* status, void* stream);
 
+/* mtg_solve_generic_batch: the same solve for an ARBITRARY constraint pattern shared by the batch
+ * — the general setupConstraintReorderingMatrix [LIN_I:171-252]: any subset of the derivatives
+ * 0..N/2-1 may be fixed at any vertex.
+ *  mask   [(K+1)][N/2] uint8, HOST pointer (small, shared by all B trajectories): 1 = fixed
+ *  values [K+1][N/2][D]  in, records: the fixed values (entries of free derivatives are ignored)
+ *  free_constraints [D][n_free]  out or NULL: d_p as getFreeConstraints orders it (per dimension,
+ *                    by vertex then derivative, LIN_H:289-296); n_free = number of zeros in mask
+ * status: MTG_ST_NOT_SPD when a pivot of R_pp is not positive or cancels below 1e-11 of its
+ * pre-elimination diagonal (an under-determined pattern, e.g. no position fixed anywhere with a
+ * derivative cost; deficiency hidden by rounding is not detectable). Other tensors as mtg_solve_batch. */
+int mtg_solve_generic_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const uint8_t* mask,
+                            const double* values, const double* seg_times, double* coeffs, double* cost,
+                            double* free_constraints, uint32_t* status, void* stream);
+
 /* mtg_set_free_constraints_batch: setFreeConstraints(d_p) + updateSegmentsFromCompactConstraints
  * + computeCost [LIN_I:489-498, 254-275, 113-130]: coefficients and cost of trajectories whose free
  * derivatives are GIVEN (the optimiser-driven call of the non-linear layer, NL_I:1309-1310).

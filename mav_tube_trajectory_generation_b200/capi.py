@@ -73,6 +73,7 @@ def load() -> C.CDLL:
     lib.mtg_argmin_allgather.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.POINTER(C.c_double),
                                          C.POINTER(C.c_int64), vp]
     lib.mtg_set_free_constraints_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, u32p, vp]
+    lib.mtg_solve_generic_batch.argtypes = [vp, C.POINTER(ProblemDesc), vp, dp, dp, dp, dp, dp, u32p, vp]
     lib.mtg_max_time_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, vp]
     lib.mtg_eval_range_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, C.c_int, C.c_int,
                                          dp, dp, vp, vp, u32p, vp]
@@ -208,6 +209,32 @@ class Context:
                                        _ptr(seg_times), _ptr(coeffs), _ptr(cost), _ptr(free),
                                        _ptr(status), self._stream(mode, stream))
         self._check(rc, "mtg_solve_batch")
+        return dict(coeffs=coeffs, cost=cost, free=free, status=status)
+
+    def solve_generic_batch(self, mask, values, seg_times, N: int = 10, derivative: int = 4, layout: str = "soa",
+                            want_free=True, stream=None):
+        """mtg_solve_generic_batch. mask [K+1, N/2] uint8 numpy (shared by the batch); values soa
+        [K+1, N/2, D, B] / aos [B, K+1, N/2, D]; seg_times soa [K, B] / aos [B, K]."""
+        aos = layout == "aos"
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        h = N // 2
+        if aos:
+            B, Kp1, hh, D = values.shape
+        else:
+            Kp1, hh, D, B = values.shape
+        assert hh == h and mask.shape == (Kp1, h)
+        K = Kp1 - 1
+        n_free = int((mask == 0).sum())
+        mode = self._mode(values)
+        desc = ProblemDesc(B, K, D, N, derivative, mode, LAYOUT_AOS if aos else LAYOUT_SOA)
+        coeffs = self._empty(values, (B, K, D, N) if aos else (K, D, N, B))
+        cost = self._empty(values, (B,))
+        status = self._empty(values, (B,), "u4")
+        free = self._empty(values, (B, D, n_free) if aos else (D, n_free, B)) if (want_free and n_free) else None
+        rc = self._lib.mtg_solve_generic_batch(self._h, C.byref(desc), mask.ctypes.data, _ptr(values), _ptr(seg_times),
+                                               _ptr(coeffs), _ptr(cost), _ptr(free), _ptr(status),
+                                               self._stream(mode, stream))
+        self._check(rc, "mtg_solve_generic_batch")
         return dict(coeffs=coeffs, cost=cost, free=free, status=status)
 
     def set_free_constraints_batch(self, positions, seg_times, free, end_derivatives=None, N: int = 10,
