@@ -4,13 +4,15 @@
 // setFreeConstraints(), computeCost() and computeMaximumOfMagnitude() run on the GPU through the
 // C ABI (B = 1); callers with many problems use the `Batch` statics or the C ABI directly.
 //
-// Supported constraint pattern (what createRandomVertices / makeStartOrEnd produce, and what
-// mtg_solve_batch implements): first and last vertex constrain derivatives 0..N/2-1 (any values),
-// interior vertices constrain position only. Other patterns make setupFromVertices return false.
+// Constraint patterns: the pattern createRandomVertices / makeStartOrEnd produce (first and last
+// vertex constrain derivatives 0..N/2-1, interior vertices position only) takes the two-lane
+// kernel behind mtg_solve_batch; every other pattern (any subset of derivatives 0..N/2-1 at any
+// vertex, LIN_I:171-252) takes mtg_solve_generic_batch.
 #ifndef MTG_SHIM_POLYNOMIAL_OPTIMIZATION_LINEAR_H_
 #define MTG_SHIM_POLYNOMIAL_OPTIMIZATION_LINEAR_H_
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <vector>
 
@@ -52,23 +54,23 @@ class PolynomialOptimization {
     MTG_SHIM_CHECK(segment_times.size() + 1 == vertices.size(), "segment_times.size() + 1 == vertices.size()");  // :66-67
     const int h = N / 2;
     const size_t K = segment_times.size();
-    // keep constraints of order <= N/2-1 only (LIN_I:74-95) and check the pattern
+    // keep constraints of order <= N/2-1 only (LIN_I:74-95); record the fixed / free pattern
     Vertex::Vector kept;
+    mask_.assign((K + 1) * h, 0);
+    canonical_ = true;
+    size_t n_fixed = 0;
     for (size_t v = 0; v < vertices.size(); ++v) {
       MTG_SHIM_CHECK((size_t)vertices[v].D() == dimension_, "vertex dimension");
       Vertex vx(dimension_);
       for (Vertex::Constraints::const_iterator it = vertices[v].cBegin(); it != vertices[v].cEnd(); ++it)
-        if (it->first >= 0 && it->first <= kHighestDerivativeToOptimize) vx.addConstraint(it->first, it->second);
+        if (it->first >= 0 && it->first <= kHighestDerivativeToOptimize) {
+          vx.addConstraint(it->first, it->second);
+          mask_[v * h + it->first] = 1;
+          ++n_fixed;
+        }
       const bool end = (v == 0 || v == K);
-      bool ok = vx.hasConstraint(derivative_order::POSITION) &&
-                vx.getNumberOfConstraints() == (size_t)(end ? h : 1);
-      if (!ok) {
-        std::fprintf(stderr,
-                     "PolynomialOptimization (B200): vertex %zu has a constraint pattern outside the batched "
-                     "solver's (ends: derivatives 0..%d, interior: position only)\n",
-                     v, h - 1);
-        return false;
-      }
+      if (!(vx.hasConstraint(derivative_order::POSITION) && vx.getNumberOfConstraints() == (size_t)(end ? h : 1)))
+        canonical_ = false;
       kept.push_back(vx);
     }
     vertices_ = kept;
@@ -76,8 +78,8 @@ class PolynomialOptimization {
     n_vertices_ = vertices.size();
     n_segments_ = K;
     n_all_constraints_ = K * N;
-    n_fixed_constraints_ = (K - 1) + 2 * h;
-    n_free_constraints_ = (K - 1) * (h - 1);
+    n_fixed_constraints_ = n_fixed;
+    n_free_constraints_ = (K + 1) * h - n_fixed;
     segments_.assign(n_segments_, Segment(N, (int)dimension_));
     for (size_t d = 0; d < dimension_; ++d) free_constraints_compact_[d] = VectorXd::Zero(n_free_constraints_);
     cost_ = 0.0;
@@ -100,15 +102,24 @@ class PolynomialOptimization {
   bool solveLinear() {
     MTG_SHIM_CHECK(derivative_to_optimize_ >= 0 && derivative_to_optimize_ <= kHighestDerivativeToOptimize,
                    "setupFromVertices first");  // :339-340
-    std::vector<double> pos, endd;
-    packVertices(&pos, &endd);
-    const int K = (int)n_segments_, D = (int)dimension_, h = N / 2;
-    std::vector<double> coeffs((size_t)K * D * N), free((size_t)D * (K - 1) * (h - 1) + 1);
+    const int K = (int)n_segments_, D = (int)dimension_;
+    std::vector<double> coeffs((size_t)K * D * N), free((size_t)D * n_free_constraints_ + 1);
     uint32_t status = 0;
     mtg_problem_desc d = runtime::desc(1, K, D, N, derivative_to_optimize_);
-    runtime::check_rc(mtg_solve_batch(runtime::context(), &d, pos.data(), endd.data(), segment_times_.data(),
-                                      coeffs.data(), &cost_, free.data(), &status, nullptr),
-                      "mtg_solve_batch");
+    if (canonical_) {
+      std::vector<double> pos, endd;
+      packVertices(&pos, &endd);
+      runtime::check_rc(mtg_solve_batch(runtime::context(), &d, pos.data(), endd.data(), segment_times_.data(),
+                                        coeffs.data(), &cost_, free.data(), &status, nullptr),
+                        "mtg_solve_batch");
+    } else {
+      std::vector<double> values;
+      packValues(nullptr, &values);
+      runtime::check_rc(mtg_solve_generic_batch(runtime::context(), &d, mask_.data(), values.data(),
+                                                segment_times_.data(), coeffs.data(), &cost_, free.data(), &status,
+                                                nullptr),
+                        "mtg_solve_generic_batch");
+    }
     if (status & MTG_ST_NOT_SPD)
       std::fprintf(stderr, "PolynomialOptimization (B200): R_pp is numerically not positive definite\n");
     for (int dim = 0; dim < D; ++dim)
@@ -150,7 +161,8 @@ class PolynomialOptimization {
     for (size_t dim = 0; dim < dimension_; ++dim) {
       size_t q = 0;
       for (int v = 0; v <= K; ++v)
-        for (int k = 0; k < ((v == 0 || v == K) ? h : 1); ++k) {
+        for (int k = 0; k < h; ++k) {
+          if (!mask_[v * h + k]) continue;
           VectorXd c;
           vertices_[v].getConstraint(k, &c);
           (*fixed_constraints)[dim][q++] = c[dim];
@@ -163,18 +175,13 @@ class PolynomialOptimization {
     for (const VectorXd& v : free_constraints)
       MTG_SHIM_CHECK((size_t)v.size() == n_free_constraints_, "number of free constraints");
     free_constraints_compact_ = free_constraints;
-    std::vector<double> pos, endd;
-    packVertices(&pos, &endd);
     const int K = (int)n_segments_, D = (int)dimension_;
-    std::vector<double> coeffs((size_t)K * D * N), free;
-    for (int dim = 0; dim < D; ++dim)
-      for (size_t q = 0; q < n_free_constraints_; ++q) free.push_back(free_constraints[dim][q]);
-    free.push_back(0.0);
+    std::vector<double> coeffs((size_t)K * D * N), full;
+    packValues(&free_constraints, &full);  // C [d_f; d_p]: the full endpoint derivatives of every vertex
     mtg_problem_desc d = runtime::desc(1, K, D, N, derivative_to_optimize_);
-    runtime::check_rc(mtg_set_free_constraints_batch(runtime::context(), &d, pos.data(), endd.data(),
-                                                     segment_times_.data(), free.data(), coeffs.data(), &cost_,
-                                                     nullptr, nullptr),
-                      "mtg_set_free_constraints_batch");
+    runtime::check_rc(mtg_coeffs_from_derivatives_batch(runtime::context(), &d, full.data(), segment_times_.data(),
+                                                        coeffs.data(), &cost_, nullptr, nullptr),
+                      "mtg_coeffs_from_derivatives_batch");
     unpackSegments(coeffs);
   }
 
@@ -324,13 +331,31 @@ class PolynomialOptimization {
  protected:
   // row r of C / of blockdiag(H): segment r / N, local index r % N: < h = (start vertex, k), >= h = (end vertex, k)
   size_t columnOfRow(size_t r) const {
-    const size_t h = N / 2, K = n_segments_;
+    const size_t h = N / 2;
     const size_t seg = r / N, l = r % N;
     const size_t v = seg + (l >= h ? 1 : 0), k = l % h;
-    if (v == 0) return k;
-    if (v == K) return (K - 1) + h + k;
-    if (k == 0) return h - 1 + v;
-    return n_fixed_constraints_ + (h - 1) * (v - 1) + (k - 1);
+    // fixed constraints first, then free ones, each ordered by (vertex, derivative) (LIN_H:289-296)
+    size_t fixed_before = 0, free_before = 0;
+    for (size_t q = 0; q < v * h + k; ++q) (mask_[q] ? fixed_before : free_before) += 1;
+    return mask_[v * h + k] ? fixed_before : n_fixed_constraints_ + free_before;
+  }
+  // values [K+1][h][D]: the fixed constraints and, if given, the free derivatives merged in
+  void packValues(const std::vector<VectorXd>* free_constraints, std::vector<double>* values) const {
+    const int h = N / 2, K = (int)n_segments_, D = (int)dimension_;
+    values->assign((size_t)(K + 1) * h * D, 0.0);
+    size_t q = 0;
+    for (int v = 0; v <= K; ++v)
+      for (int k = 0; k < h; ++k) {
+        if (mask_[v * h + k]) {
+          VectorXd c;
+          vertices_[v].getConstraint(k, &c);
+          for (int dim = 0; dim < D; ++dim) (*values)[((size_t)v * h + k) * D + dim] = c[dim];
+        } else {
+          if (free_constraints)
+            for (int dim = 0; dim < D; ++dim) (*values)[((size_t)v * h + k) * D + dim] = (*free_constraints)[dim][q];
+          ++q;
+        }
+      }
   }
   void blockDiagonal(MatrixXd* out, bool inverse) const {
     MTG_SHIM_CHECK(out != nullptr, "output is null");
@@ -374,6 +399,8 @@ class PolynomialOptimization {
   Segment::Vector segments_;
   std::vector<double> segment_times_;
   std::vector<VectorXd> free_constraints_compact_;
+  std::vector<uint8_t> mask_;  // [(K+1)][N/2]: 1 = fixed
+  bool canonical_ = true;
   size_t dimension_;
   int derivative_to_optimize_;
   size_t n_vertices_, n_segments_, n_all_constraints_, n_fixed_constraints_, n_free_constraints_;

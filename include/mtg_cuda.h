@@ -148,6 +148,14 @@ int mtg_set_free_constraints_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, c
                                    const double* free_constraints, double* coeffs, double* cost,
                                    uint32_t* status, void* stream);
 
+/* mtg_coeffs_from_derivatives_batch: updateSegmentsFromCompactConstraints + computeCost
+ * [LIN_I:254-275, 113-130] for ANY constraint pattern: the caller merges fixed and free entries into
+ * the full endpoint derivatives of every vertex (what C [d_f; d_p] is), derivatives [K+1][N/2][D];
+ * coeffs = A(T)^-1 [d(v_i); d(v_i+1)] per segment, cost = 0.5 sum c^T Q c. */
+int mtg_coeffs_from_derivatives_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* derivatives,
+                                      const double* seg_times, double* coeffs, double* cost,
+                                      uint32_t* status, void* stream);
+
 /* ------------------------------------- P9: finite-difference time perturbations
  * Replaces the per-segment perturbation loop of the reference's non-linear layer,
  * getCostAndGradientTime [impl/polynomial_optimization_nonlinear_impl.h:2495-2584,

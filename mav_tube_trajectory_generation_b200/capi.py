@@ -74,6 +74,7 @@ def load() -> C.CDLL:
                                          C.POINTER(C.c_int64), vp]
     lib.mtg_set_free_constraints_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, u32p, vp]
     lib.mtg_solve_generic_batch.argtypes = [vp, C.POINTER(ProblemDesc), vp, dp, dp, dp, dp, dp, u32p, vp]
+    lib.mtg_coeffs_from_derivatives_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, u32p, vp]
     lib.mtg_max_time_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, vp]
     lib.mtg_eval_range_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, C.c_int, C.c_int,
                                          dp, dp, vp, vp, u32p, vp]
@@ -236,6 +237,26 @@ class Context:
                                                self._stream(mode, stream))
         self._check(rc, "mtg_solve_generic_batch")
         return dict(coeffs=coeffs, cost=cost, free=free, status=status)
+
+    def coeffs_from_derivatives_batch(self, derivatives, seg_times, N: int = 10, derivative: int = 4,
+                                      layout: str = "soa", stream=None):
+        """mtg_coeffs_from_derivatives_batch. derivatives soa [K+1, N/2, D, B] / aos [B, K+1, N/2, D]."""
+        aos = layout == "aos"
+        if aos:
+            B, Kp1, h, D = derivatives.shape
+        else:
+            Kp1, h, D, B = derivatives.shape
+        K = Kp1 - 1
+        mode = self._mode(derivatives)
+        desc = ProblemDesc(B, K, D, N, derivative, mode, LAYOUT_AOS if aos else LAYOUT_SOA)
+        coeffs = self._empty(derivatives, (B, K, D, N) if aos else (K, D, N, B))
+        cost = self._empty(derivatives, (B,))
+        status = self._empty(derivatives, (B,), "u4")
+        rc = self._lib.mtg_coeffs_from_derivatives_batch(self._h, C.byref(desc), _ptr(derivatives), _ptr(seg_times),
+                                                         _ptr(coeffs), _ptr(cost), _ptr(status),
+                                                         self._stream(mode, stream))
+        self._check(rc, "mtg_coeffs_from_derivatives_batch")
+        return dict(coeffs=coeffs, cost=cost, status=status)
 
     def set_free_constraints_batch(self, positions, seg_times, free, end_derivatives=None, N: int = 10,
                                    derivative: int = 4, layout: str = "soa", stream=None):

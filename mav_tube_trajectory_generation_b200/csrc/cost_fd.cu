@@ -123,6 +123,78 @@ extern "C" int mtg_set_free_constraints_batch(mtg_ctx* ctx, const mtg_problem_de
   });
 }
 
+namespace {
+template <int HN, int D, bool AOS>
+int launch_cd_t(mtg_ctx* ctx, const double* derivs, const SolveCanonicalParams& sp, cudaStream_t s) {
+  const int block = 128, grid = (sp.nb + block - 1) / block;
+  if (grid == 0) return MTG_OK;
+  coeffs_from_derivatives_kernel<HN, D, AOS><<<grid, block, 0, s>>>(derivs, sp);
+  ++ctx->launches;
+  MTG_CUDA_TRY(cudaGetLastError());
+  return MTG_OK;
+}
+template <int HN, bool AOS>
+int launch_cd_d(mtg_ctx* ctx, int D, const double* derivs, const SolveCanonicalParams& sp, cudaStream_t s) {
+  switch (D) {
+    case 1: return launch_cd_t<HN, 1, AOS>(ctx, derivs, sp, s);
+    case 2: return launch_cd_t<HN, 2, AOS>(ctx, derivs, sp, s);
+    case 3: return launch_cd_t<HN, 3, AOS>(ctx, derivs, sp, s);
+    case 4: return launch_cd_t<HN, 4, AOS>(ctx, derivs, sp, s);
+  }
+  return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "D must be 1..4");
+}
+template <bool AOS>
+int launch_cd_n(mtg_ctx* ctx, int N, int D, const double* derivs, const SolveCanonicalParams& sp, cudaStream_t s) {
+  switch (N) {
+    case 4: return launch_cd_d<2, AOS>(ctx, D, derivs, sp, s);
+    case 6: return launch_cd_d<3, AOS>(ctx, D, derivs, sp, s);
+    case 8: return launch_cd_d<4, AOS>(ctx, D, derivs, sp, s);
+    case 10: return launch_cd_d<5, AOS>(ctx, D, derivs, sp, s);
+    case 12: return launch_cd_d<6, AOS>(ctx, D, derivs, sp, s);
+  }
+  return fail(ctx, MTG_ERR_UNSUPPORTED, "supported N: {4,6,8,10,12}");
+}
+}  // namespace
+
+extern "C" int mtg_coeffs_from_derivatives_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* derivatives,
+                                                 const double* seg_times, double* coeffs, double* cost,
+                                                 uint32_t* status, void* stream_) {
+  int rc = validate_desc(ctx, desc);
+  if (rc) return rc;
+  if (!derivatives || !seg_times || !coeffs)
+    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "derivatives, seg_times and coeffs are required");
+  if (desc->B == 0) return MTG_OK;
+  MTG_CUDA_TRY(cudaSetDevice(ctx->device));
+  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int B = desc->B, K = desc->K, D = desc->D, N = desc->N;
+  const bool aos = desc->layout == MTG_LAYOUT_AOS;
+  SolveCanonicalParams sp = {};
+  sp.K = K;
+  sp.derivative = desc->derivative_to_optimize;
+  auto launch = [&](const double* dv, cudaStream_t st) {
+    return aos ? launch_cd_n<true>(ctx, N, D, dv, sp, st) : launch_cd_n<false>(ctx, N, D, dv, sp, st);
+  };
+  if (desc->memory == MTG_MEM_DEVICE) {
+    sp.seg_times = seg_times; sp.coeffs = coeffs; sp.cost = cost; sp.status = status;
+    sp.B = B; sp.b0 = 0; sp.nb = B; sp.vec_ok = ((uintptr_t)coeffs % 16 == 0) ? 1 : 0;
+    return launch(derivatives, stream);
+  }
+  std::vector<HostTensor> ts = {
+      {derivatives, (size_t)(K + 1) * (N / 2) * D, 8, true, false, nullptr},
+      {seg_times, (size_t)K, 8, true, false, nullptr},
+      {coeffs, (size_t)K * D * N, 8, false, false, nullptr},
+      {cost, 1, 8, false, true, nullptr},
+      {status, 1, 4, false, true, nullptr}};
+  return run_chunked(ctx, stream, (size_t)B, aos, ts, [&](int nb, int C, cudaStream_t st) {
+    sp.seg_times = (const double*)ts[1].dev; sp.coeffs = (double*)ts[2].dev; sp.cost = (double*)ts[3].dev;
+    sp.status = (uint32_t*)ts[4].dev;
+    sp.B = C; sp.b0 = 0; sp.nb = nb; sp.vec_ok = 1;
+    return launch((const double*)ts[0].dev, st);
+  });
+}
+
 extern "C" int mtg_cost_time_fd_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* positions,
                                       const double* end_derivatives, const double* seg_times,
                                       const double* free_constraints, double increment_time, int central,

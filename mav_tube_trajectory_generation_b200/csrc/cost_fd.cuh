@@ -212,5 +212,44 @@ __global__ void __launch_bounds__(128) coeffs_from_free_kernel(const CostFdParam
   if (p.status) p.status[b] = st;
 }
 
+// Coefficients and cost from the FULL endpoint derivatives of every vertex (fixed and free entries
+// merged by the caller): updateSegmentsFromCompactConstraints + computeCost for any constraint
+// pattern (LIN_I:254-275, 113-130). derivs: elem ((v*HN + k)*D + dim), rec (K+1)*HN*D.
+template <int HN, int D, bool AOS>
+__global__ void __launch_bounds__(128) coeffs_from_derivatives_kernel(const double* __restrict__ derivs,
+                                                                      const SolveCanonicalParams sp) {
+  const int local = blockIdx.x * blockDim.x + threadIdx.x;
+  if (local >= sp.nb) return;
+  const int b = sp.b0 + local;
+  const size_t B = (size_t)sp.B;
+  const int K = sp.K;
+  const size_t rec_v = (size_t)(K + 1) * HN * D;
+  uint32_t st = 0;
+  auto vertex = [&](int v, double (&d)[D][HN]) {
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim)
+#pragma unroll
+      for (int m = 0; m < HN; ++m) d[dim][m] = derivs[at<AOS>((size_t)(v * HN + m) * D + dim, rec_v, B, b)];
+  };
+  double ds[D][HN], de[D][HN];
+  vertex(0, ds);
+  double cost = 0.0;
+  for (int i = 0; i < K; ++i) {
+    double T = sp.seg_times[at<AOS>((size_t)i, (size_t)K, B, b)];
+    if (!(T > 0.0) || !(T < 1.7e308)) {  // LIN_I:296 CHECK_GT(segment_time, 0)
+      st |= 1u;
+      T = 1.0;
+    }
+    vertex(i + 1, de);
+    cost += emit_segment<HN, D, AOS>(sp, i, b, true, T, ds, de);
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim)
+#pragma unroll
+      for (int m = 0; m < HN; ++m) ds[dim][m] = de[dim][m];
+  }
+  if (sp.cost) sp.cost[b] = 0.5 * cost;
+  if (sp.status) sp.status[b] = st;
+}
+
 }  // namespace mtg
 #endif

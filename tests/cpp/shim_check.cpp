@@ -157,12 +157,60 @@ int main() {
   random_problem(1, 10, 102);
   random_problem(3, 1, 104);
   random_problem(3, 50, 106);
-  // unsupported constraint pattern: an interior velocity constraint
+  // a general constraint pattern (interior velocity fixed, free goal derivatives) takes the generic solver:
+  // constraints met, C^4 continuity, optimality of d_p, ConstraintPacking identities
   {
-    Vertex::Vector v = createRandomVertices(4, 3, VectorXd::Constant(3, -1.0), VectorXd::Constant(3, 1.0), 1);
-    v[1].addConstraint(derivative_order::VELOCITY, 0.0);
+    Vertex::Vector v = createRandomVertices(4, 6, VectorXd::Constant(3, -5.0), VectorXd::Constant(3, 5.0), 7);
+    v[2].addConstraint(derivative_order::VELOCITY, 0.5);
+    v[4].addConstraint(derivative_order::VELOCITY, VectorXd::Constant(3, -0.25));
+    for (int k = 2; k <= 4; ++k) v[6].removeConstraint(k);
+    std::vector<double> times = estimateSegmentTimes(v, 3.0, 5.0);
     PolynomialOptimization<10> opt(3);
-    EXPECT(!opt.setupFromVertices(v, estimateSegmentTimes(v, 3.0, 5.0)));
+    EXPECT(opt.setupFromVertices(v, times));
+    EXPECT(opt.getNumberFixedConstraints() == 5 + 2 + 5 + 2 && opt.getNumberFreeConstraints() == 35 - 14);  // start, goal, 5 positions, 2 velocities
+    EXPECT(opt.solveLinear());
+    Segment::Vector segs;
+    opt.getSegments(&segs);
+    double worst = 0.0;
+    for (int i = 0; i < 6; ++i)
+      for (int der = 0; der <= 4; ++der) {
+        const VectorXd a = segs[i].evaluate(0.0, der), b = segs[i].evaluate(times[i], der);
+        VectorXd want;
+        if (v[i].getConstraint(der, &want))
+          for (int d = 0; d < 3; ++d) worst = std::fmax(worst, std::fabs(a[d] - want[d]));
+        if (v[i + 1].getConstraint(der, &want))
+          for (int d = 0; d < 3; ++d) worst = std::fmax(worst, std::fabs(b[d] - want[d]));
+        if (i + 1 < 6) {
+          const VectorXd n = segs[i + 1].evaluate(0.0, der);
+          for (int d = 0; d < 3; ++d) worst = std::fmax(worst, std::fabs(b[d] - n[d]));
+        }
+      }
+    EXPECT(worst < 1e-6);
+    std::vector<VectorXd> d_p;
+    opt.getFreeConstraints(&d_p);
+    const double cost0 = opt.computeCost();
+    std::vector<VectorXd> bumped = d_p;
+    bumped[1][3] += 0.05;
+    opt.setFreeConstraints(bumped);
+    EXPECT(opt.computeCost() > cost0);
+    opt.setFreeConstraints(d_p);
+    EXPECT(std::fabs(opt.computeCost() - cost0) <= 1e-12 * cost0);
+    // 0.5 d^T R d with the host-assembled R and the general column map
+    std::vector<VectorXd> d_f;
+    opt.getFixedConstraints(&d_f);
+    MatrixXd R;
+    opt.getR(&R);
+    const size_t nf = opt.getNumberFixedConstraints(), np = opt.getNumberFreeConstraints();
+    double J = 0.0;
+    for (int dim = 0; dim < 3; ++dim) {
+      std::vector<double> d_all(nf + np);
+      for (size_t q = 0; q < nf; ++q) d_all[q] = d_f[dim][q];
+      for (size_t q = 0; q < np; ++q) d_all[nf + q] = d_p[dim][q];
+      for (size_t r = 0; r < nf + np; ++r)
+        for (size_t c = 0; c < nf + np; ++c) J += d_all[r] * R(r, c) * d_all[c];
+    }
+    EXPECT(std::fabs(0.5 * J - cost0) <= 1e-6 * cost0);
+    std::printf("general pattern: cost %.9g, checkPath %.2e, n_fixed %zu, n_free %zu\n", cost0, worst, nf, np);
   }
   if (failures) {
     std::printf("SHIM FAILED: %d check(s)\n", failures);

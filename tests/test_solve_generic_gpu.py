@@ -133,3 +133,25 @@ def test_two_vertices_fully_constrained_and_underdetermined(po):
     values, times = make_values(po, 4, K, 3, mask, seed=5)
     coeffs, _, _, status = gpu_generic(mask, values, times, 4)
     assert np.any(status & 2) and np.all(np.isfinite(coeffs))
+
+
+def test_coeffs_from_derivatives_round_trip(po):
+    """C [d_f; d_p] -> coefficients (LIN_I:254-275) for a general pattern: merging the solved free
+    derivatives back into the fixed ones reproduces the solve's coefficients and cost."""
+    K, D, B = 8, 3, 64
+    mask = PATTERNS["mixed"](K)
+    values, times = make_values(po, B, K, D, mask, seed=9)
+    coeffs, cost, free, status = gpu_generic(mask, values, times, 4)
+    full = values.copy()
+    q = 0
+    for v in range(K + 1):
+        for k in range(H):
+            if not mask[v, k]:
+                full[:, v, k, :] = free[:, :, q]
+                q += 1
+    c = ctx()
+    r = c.coeffs_from_derivatives_batch(dev(soa(full)), dev(soa(times)))
+    assert np.array_equal(aos(host(r["coeffs"])), coeffs)
+    assert np.allclose(host(r["cost"]), cost, rtol=1e-14, atol=0)
+    ra = c.coeffs_from_derivatives_batch(np.ascontiguousarray(full), np.ascontiguousarray(times), layout="aos")
+    assert np.array_equal(ra["coeffs"], coeffs)
