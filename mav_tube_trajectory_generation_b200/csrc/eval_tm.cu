@@ -27,7 +27,7 @@ constexpr int kTubeChunk = 65536;       // trajectories per launch pair when a t
 
 template <int NT, int D, int MODE>
 int launch_tm_t(mtg_ctx* ctx, const EvalParams& p, const double* geom, cudaStream_t s) {
-  const bool want_acc = MODE < TM_FEAS && p.sampling_times != nullptr;
+  const bool want_acc = MODE == TM_DERIVATIVE && p.sampling_times != nullptr;
   const size_t smem = (size_t)tm_layout(D, NT, want_acc, MODE == TM_FEAS_TUBE, tm_tpw(MODE)).per_warp * (kTmBlock / 32);
   auto kern = eval_tm_kernel<NT, D, MODE>;
   if (smem > 48 * 1024) MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -68,7 +68,9 @@ bool eval_tm_supported(const EvalParams& p) {
 int launch_eval_tm(mtg_ctx* ctx, int D, bool feasibility, const EvalParams& p_in, cudaStream_t s) {
   EvalParams p = p_in;
   if (!feasibility)
-    return p.derivative == 0 ? launch_tm_n<TM_POSITION>(ctx, D, p, nullptr, s)
+    // the lean position kernel has no sampling_times / segment_idx outputs; TM_DERIVATIVE handles every
+    // derivative order (B(0, j) = 1: bit-identical values for order 0)
+    return (p.derivative == 0 && !p.sampling_times && !p.segment_idx) ? launch_tm_n<TM_POSITION>(ctx, D, p, nullptr, s)
                              : launch_tm_n<TM_DERIVATIVE>(ctx, D, p, nullptr, s);
   p.v2_lim = sq_limit(p.v_max);
   p.a2_lim = sq_limit(p.a_max);

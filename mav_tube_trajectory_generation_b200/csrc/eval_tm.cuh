@@ -122,7 +122,7 @@ struct TmLayout {
   int traj_bytes;   // 2 slots + {T of slot 0, T of slot 1}
   int blk_ld;       // doubles per lane block in the staging tile: 8*D + 1 (bank skew)
   int row_ld;       // doubles per trajectory row of the staging tile: 4 * blk_ld
-  int off_stage, off_info, off_off, off_flag, off_acc, off_slots, per_warp;
+  int off_stage, off_info, off_off, off_cnt, off_flag, off_acc, off_slots, per_warp;
 };
 // TPW = trajectories per warp (phase-1 lanes in use): the shared memory of a warp scales with it.
 // 16 doubles the resident warps of the latency-bound position sweep; the fp64-bound feasibility
@@ -137,7 +137,8 @@ __host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool
   L.off_stage = kTmTPW * kTmTauLd * 8;
   L.off_info = L.off_stage + kTmG * L.row_ld * 8;
   L.off_off = L.off_info + kTmTPW * 16;
-  L.off_flag = L.off_off + kTmTPW * 8;
+  L.off_cnt = L.off_off + kTmTPW * 8;
+  L.off_flag = L.off_cnt + kTmTPW * 4;
   L.off_acc = L.off_flag + kTmG * 40;
   L.off_slots = L.off_acc + (want_acc ? kTmTPW * kTmTauLd * 8 : 0);
   L.per_warp = L.off_slots + kTmTPW * L.traj_bytes;
@@ -159,7 +160,8 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 7 : 12)) eval_tm_kernel(const
   static_assert(!tube || D == 3, "the tube predicate is 3-D");
   extern __shared__ __align__(16) unsigned char tm_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool want_acc = (!FEAS) && p.sampling_times != nullptr;
+  constexpr bool EXTRA = MODE == TM_DERIVATIVE;  // sampling_times / segment_idx outputs exist in this mode only
+  const bool want_acc = EXTRA && p.sampling_times != nullptr;
   const TmLayout L = tm_layout(D, NT, want_acc, tube, kTmTPW);
   unsigned char* wbase = tm_smem + (size_t)warp * L.per_warp;
   double* tau_s = reinterpret_cast<double*>(wbase);
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 7 : 12)) eval_tm_kernel(const
   int4* info_s = reinterpret_cast<int4*>(wbase + L.off_info);
   unsigned char* flag_s = wbase + L.off_flag;
   size_t* off_s = reinterpret_cast<size_t*>(wbase + L.off_off);
+  int* cnt_s = reinterpret_cast<int*>(wbase + L.off_cnt);
   double* acc_s = reinterpret_cast<double*>(wbase + L.off_acc);
   unsigned char* slots = wbase + L.off_slots;
 
@@ -316,6 +319,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 7 : 12)) eval_tm_kernel(const
     if (lane < kTmTPW) {
       info_s[lane] = make_int4(cnt, n, seg0, cross);
       off_s[lane] = traj_off + (size_t)n;
+      cnt_s[lane] = cnt;
     }
     __syncwarp();
     if (!__any_sync(FULL, cnt > 0)) break;
@@ -475,20 +479,21 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 7 : 12)) eval_tm_kernel(const
       // (cnt == 0 rows fall out through the predicates; everything else is branch-free)
 #pragma unroll
       for (int t = 0; t < G; ++t) {
-        const int4 it = info_s[g * G + t];
+        const int cnt_t = cnt_s[g * G + t];
         const size_t o = off_s[g * G + t];
         if (p.samples) {
           double* out = p.samples + o * D + lane;
           const double* row = stage + t * L.row_ld;
-          const int total = it.x * D;
+          const int total = cnt_t * D;
 #pragma unroll
           for (int q = 0; q < D; ++q)
             if (lane + 32 * q < total) out[32 * q] = row[skew[q]];
         }
-        if (lane < it.x) {
-          if (FEAS) {
-            if (p.flags) p.flags[o + lane] = flag_s[t * 40 + lane];
-          } else {
+        if (FEAS) {
+          if (p.flags && lane < cnt_t) p.flags[o + lane] = flag_s[t * 40 + lane];
+        } else if (EXTRA) {
+          if (lane < cnt_t) {
+            const int4 it = info_s[g * G + t];
             if (want_acc) p.sampling_times[o + lane] = acc_s[(g * G + t) * kTmTauLd + lane];
             if (p.segment_idx) p.segment_idx[o + lane] = it.z + (lane >= it.w ? 1 : 0);
           }
