@@ -255,14 +255,14 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 7 : 12)) eval_tm_kernel(const
       double* arow = acc_s + lane * kTmTauLd;
       for (;;) {
         // straight run inside the current segment, four samples per trip while all four are
-        // certain (same adds, same order: tau_k and acc_k are the reference's values)
+        // certain (same adds in the same order: tau_k and acc_k are the reference's values)
         while (cnt + 4 <= limit) {
           const double tau1 = tau + dt, acc1 = acc + dt;
           const double tau2 = tau1 + dt, acc2 = acc1 + dt;
           const double tau3 = tau2 + dt, acc3 = acc2 + dt;
-          const bool ok = (acc < t1) & !(tau > Ti) & (acc1 < t1) & !(tau1 > Ti) & (acc2 < t1) & !(tau2 > Ti) &
-                          (acc3 < t1) & !(tau3 > Ti);
-          if (!ok) break;
+          // dt > 0 and rounding is monotone, so tau <= tau1 <= tau2 <= tau3 and likewise acc: the last
+          // sample's two tests imply the other six
+          if (!((acc3 < t1) & !(tau3 > Ti))) break;
           trow[cnt] = tau;
           trow[cnt + 1] = tau1;
           trow[cnt + 2] = tau2;
