@@ -46,11 +46,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.LIB):
-        raise MtgError(f"{_build.LIB} is missing: run __graft_entry__.build() "
+    path = os.environ.get("MTG_CUDA_LIB", _build.LIB)   # override: A/B measurements of two builds in one run
+    if not os.path.exists(path):
+        raise MtgError(f"{path} is missing: run __graft_entry__.build() "
                        "(python -m mav_tube_trajectory_generation_b200._build). "
                        "There is no CPU fallback.")
-    lib = C.CDLL(_build.LIB)
+    lib = C.CDLL(path)
     vp, dp, u32p = C.c_void_p, C.c_void_p, C.c_void_p
     lib.mtg_abi_version.restype = C.c_int
     lib.mtg_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]

@@ -1,0 +1,4 @@
+for i in 1 2; do
+for v in A B; do
+  echo "variant $v"; MTG_CUDA_LIB=$PWD/mav_tube_trajectory_generation_b200/libmtg_cuda_$v.so python tools/bench_sweep.py --layout aos --batch 262144 2>&1 | grep -E "eval_range|feasibility\(pos" | cut -c1-160
+done; done
