@@ -127,7 +127,7 @@ struct TmLayout {
 // TPW = trajectories per warp (phase-1 lanes in use): the shared memory of a warp scales with it.
 // 16 doubles the resident warps of the latency-bound position sweep; the fp64-bound feasibility
 // sweep prefers full phase-1 lanes (32).
-__host__ __device__ constexpr int tm_tpw(int mode) { return mode >= 2 ? 32 : 16; }
+__host__ __device__ constexpr int tm_tpw(int mode) { return mode >= 2 ? 16 : 16; }
 __host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, int kTmTPW) {
   TmLayout L;
   L.slot_bytes = D * NT * 8 + (tube ? kTubeGeomLd * 8 : 0);
@@ -151,7 +151,7 @@ enum TmMode { TM_POSITION = 0, TM_DERIVATIVE = 1, TM_FEAS = 2, TM_FEAS_TUBE = 3 
 // Requirements (checked by the launcher, which otherwise falls back to the one-thread-per-
 // trajectory kernels of eval.cuh): AoS layout, N == NT, coeffs 16-byte aligned.
 template <int NT, int D, int MODE>
-__global__ void __launch_bounds__(32, (MODE >= 2 ? 7 : 12)) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
+__global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr bool FEAS = MODE >= TM_FEAS;
   constexpr bool tube = MODE == TM_FEAS_TUBE;
