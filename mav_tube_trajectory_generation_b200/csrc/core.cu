@@ -36,6 +36,7 @@ int ensure_tables(mtg_ctx* ctx, int N, int derivative) {
   std::memcpy(h.H1, t.H1, sizeof(h.H1));
   std::memcpy(h.Ainv1, t.Ainv1, sizeof(h.Ainv1));
   std::memcpy(h.W, t.W, sizeof(h.W));
+  std::memcpy(h.Lt, t.Lt, sizeof(h.Lt));
   std::memcpy(h.base, t.base, sizeof(h.base));
   for (int j = 0; j < MTG_TAB_LD; ++j) h.inv_factorial[j] = 1.0 / t.base[j * MTG_BASE_LD + j];
   h.N = N;

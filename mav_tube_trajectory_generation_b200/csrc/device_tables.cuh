@@ -10,6 +10,7 @@ struct DevTables {
   double H1[MTG_TAB_LD * MTG_TAB_LD];
   double Ainv1[MTG_TAB_LD * MTG_TAB_LD];
   double W[MTG_TAB_LD * MTG_TAB_LD];      // H1 = W^T W, (N-d) x N
+  double Lt[MTG_TAB_LD * MTG_TAB_LD];     // W = Lt Ainv1[d.., :], upper triangular (N-d) x (N-d)
   double base[MTG_BASE_LD * MTG_BASE_LD];
   double inv_factorial[MTG_TAB_LD];  // 1/B(j,j) = 1/j!  (the A(0) diagonal inverse, LIN_I:152-155)
   int N;

@@ -9,8 +9,8 @@ using namespace mtg;
 namespace {
 
 // -------------------------------------------------------------- solve launch
-template <int HN, int D, bool AOS>
-int launch_solve_canonical_t(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, cudaStream_t stream) {
+template <int HN, int D, bool AOS, int DT>
+int launch_solve_canonical_dt(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, cudaStream_t stream) {
   constexpr int NF = HN - 1;
   constexpr int SLOTS = NF * NF + NF * D;
   // two lanes per trajectory; each parks (G_j, z_j) of all but the last vertex it eliminates
@@ -34,7 +34,7 @@ int launch_solve_canonical_t(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, c
     return fail(ctx, MTG_ERR_UNSUPPORTED,
                 "solve_canonical: K too large for the shared-memory sweep state; use mtg_solve_generic_batch");
   const size_t smem = per_thread * block;
-  auto kern = mtg::solve_canonical_kernel<HN, D, AOS>;
+  auto kern = mtg::solve_canonical_kernel<HN, D, AOS, DT>;
   if (smem > 48 * 1024)  // per device and per instantiation; a cheap host-side call
     MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
   const long long threads = 2LL * p.nb;
@@ -44,6 +44,14 @@ int launch_solve_canonical_t(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, c
   ++ctx->launches;
   MTG_CUDA_TRY(cudaGetLastError());
   return MTG_OK;
+}
+
+// the default cost derivative N/2 - 1 (kHighestDerivativeToOptimize, LIN_H:51) gets its own instantiation
+template <int HN, int D, bool AOS>
+int launch_solve_canonical_t(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, cudaStream_t stream) {
+  // (only for N = 10, the reference's default PolynomialOptimization<10>: keeps the build short)
+  if (HN == 5 && p.derivative == HN - 1) return launch_solve_canonical_dt<HN, D, AOS, (HN == 5 ? HN - 1 : -1)>(ctx, p, stream);
+  return launch_solve_canonical_dt<HN, D, AOS, -1>(ctx, p, stream);
 }
 
 template <int HN, bool AOS>

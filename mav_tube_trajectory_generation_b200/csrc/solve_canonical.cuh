@@ -82,11 +82,14 @@ __device__ __forceinline__ void segment_powers(double T, int derivative, double 
 #define MTG_H1(r, c) c_tab.H1[(r) * MTG_TAB_LD + (c)]
 #define MTG_AI(r, c) c_tab.Ainv1[(r) * MTG_TAB_LD + (c)]
 #define MTG_W(r, c) c_tab.W[(r) * MTG_TAB_LD + (c)]
+#define MTG_LT(r, c) c_tab.Lt[(r) * MTG_TAB_LD + (c)]
 
 // Writes the N coefficients of every dimension of one segment (original
 // orientation: ds at the segment start, de at its end) and returns the segment's
 // cost contribution  T^(1-2d) * sum_dim |W dhat|^2  (without the 1/2).
-template <int HN, int D, bool AOS>
+// DT >= 0: the cost derivative as a compile-time constant (the triangular cost loop then has no
+// predicated-off slots); DT = -1: taken from p.derivative.
+template <int HN, int D, bool AOS, int DT = -1>
 __device__ __forceinline__ double emit_segment(const SolveCanonicalParams& p, int seg, int b, bool active,
                                                double T, const double (&ds)[D][HN],
                                                const double (&de)[D][HN]) {
@@ -99,7 +102,8 @@ __device__ __forceinline__ double emit_segment(const SolveCanonicalParams& p, in
   double uh = u;  // u^HN
 #pragma unroll
   for (int m = 1; m < HN; ++m) uh *= u;
-  const int nq = N - p.derivative;
+  const int dcost = DT >= 0 ? DT : p.derivative;
+  const int nq = N - dcost;
   double quad = 0.0;
   const size_t rec = (size_t)p.K * D * N;
 #pragma unroll
@@ -111,9 +115,14 @@ __device__ __forceinline__ double emit_segment(const SolveCanonicalParams& p, in
       dh[m] = tp[m] * ds[dim][m];
       dh[HN + m] = tp[m] * de[dim][m];
     }
-    double c[N];
+    // chat_j = c_j T^j: the scaled coefficients. Lower half straight from the start derivatives,
+    // upper half through A(1)^-1; c_j = chat_j T^-j.
+    double c[N], chat[N];
 #pragma unroll
-    for (int j = 0; j < HN; ++j) c[j] = ds[dim][j] * c_tab.inv_factorial[j];
+    for (int j = 0; j < HN; ++j) {
+      c[j] = ds[dim][j] * c_tab.inv_factorial[j];
+      chat[j] = (j == 0 ? ds[dim][0] : dh[j]) * c_tab.inv_factorial[j];
+    }
     double us = uh;
 #pragma unroll
     for (int j = HN; j < N; ++j) {
@@ -123,6 +132,7 @@ __device__ __forceinline__ double emit_segment(const SolveCanonicalParams& p, in
         acc = fma(MTG_AI(j, m), dh[m], acc);
         acc = fma(MTG_AI(j, HN + m), dh[HN + m], acc);
       }
+      chat[j] = acc;
       c[j] = acc * us;
       us *= u;
     }
@@ -142,22 +152,21 @@ __device__ __forceinline__ double emit_segment(const SolveCanonicalParams& p, in
         for (int j = 0; j < N; ++j) out[(size_t)j * p.B] = c[j];
       }
     }
+    // cost: |W dhat|^2 = |Lt chat[d..]|^2 — a sum of squares (no cancellation across terms), and the
+    // triangular Lt costs (N-d)(N-d+1)/2 multiply-adds instead of the (N-d)(N-1) of W
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       if (i < nq) {
-        double w = MTG_W(i, HN) * dlt;
-        if (p.derivative == 0) w = fma(MTG_W(i, 0) + MTG_W(i, HN), ds[dim][0], w);
+        double w = 0.0;
 #pragma unroll
-        for (int m = 1; m < HN; ++m) {
-          w = fma(MTG_W(i, m), dh[m], w);
-          w = fma(MTG_W(i, HN + m), dh[HN + m], w);
-        }
+        for (int j = i; j < N; ++j)  // chat index j = dcost + a with a >= i
+          if (j >= dcost + i) w = fma(c_tab.Lt[i * MTG_TAB_LD + (j - dcost)], chat[j], w);
         quad = fma(w, w, quad);
       }
     }
   }
   double s = 1.0;  // T^(1-2d)
-  const int e0 = 1 - 2 * p.derivative;
+  const int e0 = 1 - 2 * dcost;
   if (e0 >= 0) {
     for (int i = 0; i < e0; ++i) s *= T;
   } else {
@@ -209,7 +218,7 @@ __device__ __forceinline__ void chol_solve(const double (&L)[NF][NF], const doub
   }
 }
 
-template <int HN, int D, bool AOS>
+template <int HN, int D, bool AOS, int DT = -1>
 __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCanonicalParams p) {
   constexpr int N = 2 * HN;
   constexpr int NF = HN - 1;               // free derivatives per interior vertex
@@ -224,7 +233,7 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
   const int b = p.b0 + (active ? pair : p.nb - 1);
   const int K = p.K;
   const size_t B = (size_t)p.B;
-  const int d = p.derivative;
+  const int d = DT >= 0 ? DT : p.derivative;
   uint32_t st = 0;
 
   const size_t rec_pos = (size_t)(K + 1) * D, rec_t = (size_t)K, rec_end = (size_t)2 * NF * D;
@@ -270,7 +279,7 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
       for (int m = 0; m < HN; ++m)  // lane B's constraints arrive in its reversed-time sign convention
         other[dim][m] = ((m & 1) ? -1.0 : 1.0) * __shfl_xor_sync(FULL, sdt[dim][m], 1);
     const double T = seg_time(0);
-    cost_acc = emit_segment<HN, D, AOS>(p, 0, b, active && side == 0, T, sdt, other);
+    cost_acc = emit_segment<HN, D, AOS, DT>(p, 0, b, active && side == 0, T, sdt, other);
     if (active && side == 0) {
       if (p.cost) p.cost[b] = 0.5 * cost_acc;
       if (p.status) p.status[b] = st;
@@ -516,7 +525,7 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
         ds[dim][mm] = side ? e : a;
         de[dim][mm] = side ? a : e;
       }
-    cost_acc += emit_segment<HN, D, AOS>(p, SG(c), b, active, T, ds, de);
+    cost_acc += emit_segment<HN, D, AOS, DT>(p, SG(c), b, active, T, ds, de);
 #pragma unroll
     for (int dim = 0; dim < D; ++dim)
 #pragma unroll

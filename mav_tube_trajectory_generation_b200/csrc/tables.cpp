@@ -113,7 +113,9 @@ bool compute_tables(int N, int derivative, Tables* out) {
     }
   out->N = N;
   out->derivative = d;
-  for (int i = 0; i < MTG_TAB_LD * MTG_TAB_LD; ++i) out->H1[i] = out->Ainv1[i] = out->W[i] = 0.0;
+  for (int i = 0; i < MTG_TAB_LD * MTG_TAB_LD; ++i) out->H1[i] = out->Ainv1[i] = out->W[i] = out->Lt[i] = 0.0;
+  for (int i = 0; i < nq; ++i)
+    for (int a = i; a < nq; ++a) out->Lt[i * MTG_TAB_LD + a] = static_cast<double>(L[a * nq + i]);
   for (int i = 0; i < nq; ++i)
     for (int m = 0; m < N; ++m) out->W[i * MTG_TAB_LD + m] = static_cast<double>(Wm[i * N + m]);
   for (int i = 0; i < N; ++i)

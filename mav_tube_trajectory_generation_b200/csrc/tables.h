@@ -15,6 +15,9 @@ struct Tables {
   // Q(1)[d.., d..] = L L^T. The cost is evaluated as a sum of squares |W dhat|^2,
   // which has no cancellation across terms (a direct dhat^T H1 dhat loses ~6 digits).
   double W[MTG_TAB_LD * MTG_TAB_LD];
+  // Lt(i, a) = L[a][i] for a >= i (upper triangular, (N-d) x (N-d)): |W dhat|^2 = |Lt chat|^2 with
+  // chat_j = c_j T^j the scaled coefficients, j = d..N-1 (the kernels have chat at hand)
+  double Lt[MTG_TAB_LD * MTG_TAB_LD];
   double base[MTG_BASE_LD * MTG_BASE_LD]; // base_coefficients_: B(n,i) = i!/(i-n)!
 };
 

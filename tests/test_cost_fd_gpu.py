@@ -87,7 +87,8 @@ def test_batch_matches_solve_cost_and_oracle(po, layout):
     free, cost = solve_free(pos, times)
     J, Jp, Jm, g, st = gpu_fd(pos, times, free, 0.1, True, layout=layout)
     assert np.all(st == 0)
-    assert np.all(np.abs(J - 2 * cost) <= 1e-12 * J)
+    # two evaluation orders of the same sum of squares: |W dhat|^2 here, |Lt chat|^2 in the solve's epilogue
+    assert np.all(np.abs(J - 2 * cost) <= 1e-10 * J)
     for b in range(0, B, 512):
         mask, values = po.canonical_mask_values(pos[b])
         J0, oJp, oJm, og = po.cost_time_fd(N, 4, times[b], mask, values, free[b].reshape(-1), 0.1, True)
