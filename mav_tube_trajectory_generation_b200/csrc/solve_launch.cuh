@@ -1,0 +1,82 @@
+// Launchers of solve_canonical_kernel, shared by the per-layout translation units.
+#ifndef MTG_SOLVE_LAUNCH_CUH_
+#define MTG_SOLVE_LAUNCH_CUH_
+
+#include "host_common.h"
+#include "solve_canonical.cuh"
+
+namespace mtg {
+namespace solve_launch {
+
+// -------------------------------------------------------------- solve launch
+template <int HN, int D, bool AOS, int DT>
+int launch_solve_canonical_dt(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, cudaStream_t stream) {
+  constexpr int NF = HN - 1;
+  constexpr int SLOTS = NF * NF + NF * D;
+  // two lanes per trajectory; each parks (G_j, z_j) of all but the last vertex it eliminates
+  const int K = p.K, m = K / 2;
+  const int n_own_max = std::max(K - 1 - m, m - 1);
+  const size_t per_thread = (size_t)std::max(n_own_max - 1, 0) * SLOTS * sizeof(double);
+  const size_t optin = ctx->smem_optin;
+  int block = 128;
+  if (const char* env = std::getenv("MTG_SOLVE_BLOCK")) {
+    block = std::max(2, std::min(128, std::atoi(env))) & ~1;
+  } else if (per_thread > 0) {
+    const size_t half_sm = (optin + 1024) / 2 - 1024;  // two CTAs per SM, 1 KB reserved each
+    if (per_thread * 128 <= half_sm)
+      block = 128;
+    else if (per_thread * 32 <= optin)
+      block = (int)std::min<size_t>(128, (optin / per_thread) / 32 * 32);
+    else
+      block = (int)(optin / per_thread) & ~1;
+  }
+  if (block < 2 || per_thread * block > optin)
+    return fail(ctx, MTG_ERR_UNSUPPORTED,
+                "solve_canonical: K too large for the shared-memory sweep state; use mtg_solve_generic_batch");
+  const size_t smem = per_thread * block;
+  auto kern = mtg::solve_canonical_kernel<HN, D, AOS, DT>;
+  if (smem > 48 * 1024)  // per device and per instantiation; a cheap host-side call
+    MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
+  const long long threads = 2LL * p.nb;
+  const int grid = (int)((threads + block - 1) / block);
+  if (grid == 0) return MTG_OK;
+  kern<<<grid, block, smem, stream>>>(p);
+  ++ctx->launches;
+  MTG_CUDA_TRY(cudaGetLastError());
+  return MTG_OK;
+}
+
+// the default cost derivative N/2 - 1 (kHighestDerivativeToOptimize, LIN_H:51) gets its own instantiation
+template <int HN, int D, bool AOS>
+int launch_solve_canonical_t(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, cudaStream_t stream) {
+  // (only for N = 10, the reference's default PolynomialOptimization<10>: keeps the build short)
+  if (HN == 5 && p.derivative == HN - 1) return launch_solve_canonical_dt<HN, D, AOS, (HN == 5 ? HN - 1 : -1)>(ctx, p, stream);
+  return launch_solve_canonical_dt<HN, D, AOS, -1>(ctx, p, stream);
+}
+
+template <int HN, bool AOS>
+int launch_solve_canonical_d(mtg_ctx* ctx, int D, const mtg::SolveCanonicalParams& p, cudaStream_t s) {
+  switch (D) {
+    case 1: return launch_solve_canonical_t<HN, 1, AOS>(ctx, p, s);
+    case 2: return launch_solve_canonical_t<HN, 2, AOS>(ctx, p, s);
+    case 3: return launch_solve_canonical_t<HN, 3, AOS>(ctx, p, s);
+    case 4: return launch_solve_canonical_t<HN, 4, AOS>(ctx, p, s);
+  }
+  return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "D must be 1..4");
+}
+
+template <bool AOS>
+int launch_solve_canonical_n(mtg_ctx* ctx, int N, int D, const mtg::SolveCanonicalParams& p, cudaStream_t s) {
+  switch (N) {
+    case 4: return launch_solve_canonical_d<2, AOS>(ctx, D, p, s);
+    case 6: return launch_solve_canonical_d<3, AOS>(ctx, D, p, s);
+    case 8: return launch_solve_canonical_d<4, AOS>(ctx, D, p, s);
+    case 10: return launch_solve_canonical_d<5, AOS>(ctx, D, p, s);
+    case 12: return launch_solve_canonical_d<6, AOS>(ctx, D, p, s);
+  }
+  return fail(ctx, MTG_ERR_UNSUPPORTED, "solve_canonical supports N in {4,6,8,10,12}");
+}
+
+}  // namespace solve_launch
+}  // namespace mtg
+#endif
