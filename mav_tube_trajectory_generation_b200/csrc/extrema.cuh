@@ -86,9 +86,11 @@ template <bool AOS>
 __global__ void __launch_bounds__(128) extrema_segment_kernel(const ExtremaParams p) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)p.nb * p.K) return;
-  // SoA: neighbouring threads take neighbouring trajectories of the same segment (coalesced loads)
-  const int local = AOS ? (int)(gid / p.K) : (int)(gid % p.nb);
-  const int seg = AOS ? (int)(gid % p.K) : (int)(gid / p.nb);
+  // neighbouring threads take neighbouring trajectories of the SAME segment in both layouts: the
+  // work of a root problem depends on the segment (the rest-to-rest end segments carry root
+  // clusters), so this keeps a warp's lanes in step; with SoA it also coalesces the loads
+  const int local = (int)(gid % p.nb);
+  const int seg = (int)(gid / p.nb);
   const int b = p.b0 + local;
   const size_t B = (size_t)p.B;
   const int N = p.N, D = p.D, d = p.derivative, K = p.K;
