@@ -1,26 +1,39 @@
-// Time-major sampled evaluation / feasibility sweep ("tm" kernels) — the path for
-// trajectory-contiguous sample outputs (the reference's own order: evaluateRange
-// fills one std::vector<VectorXd> per trajectory, trajectory.cpp:74-134).
+// Sampled evaluation / feasibility sweep with TRAJECTORY-CONTIGUOUS outputs ("tm" kernels): the
+// reference's own order — evaluateRange fills one std::vector<VectorXd> per trajectory
+// (trajectory.cpp:74-134).
 //
-// One WARP owns 32 trajectories and alternates two phases over chunks of 32 samples:
+// One WARP owns TPW (16 or 32) trajectories and alternates two phases over chunks of 32 samples:
 //
-//  phase 1  lane = trajectory. Every lane replays the reference's SERIAL sampling
-//           recurrence (acc += dt; tau += dt; tau -= T_i on a strict '>' crossing)
-//           for up to 32 samples of its trajectory and parks (tau, segment[, acc])
-//           in shared memory. Only DADDs and compares: the part of the algorithm
-//           that cannot be parallelised over samples costs ~3 fp64 ops per sample.
-//  phase 2  lane = sample. For each of the 32 trajectories in turn the warp
-//           evaluates 32 consecutive samples at once: broadcast 16-byte loads of the
-//           segment's coefficients, Horner (fused multiply-adds), and the D*32
-//           doubles of the sample rows leave the warp as whole, consecutive 256-byte
-//           stores (staged through shared memory). No divergence: a lane whose
-//           sample lies in the next segment simply reads another address.
+//  phase 1  lane = trajectory. Every lane replays the reference's SERIAL sampling recurrence
+//           (acc += dt; tau += dt; tau -= T_i on a strict '>' crossing, which emits no sample) for
+//           up to 32 samples of its trajectory and parks tau (and acc, if sampling_times is wanted)
+//           in shared memory — four samples per trip while no crossing or end is near (rounding is
+//           monotone, so the fourth sample's two tests cover the other three). This is the part of
+//           the algorithm that cannot be parallelised over samples: ~4 fp64 ops per sample.
+//  phase 2  4 lanes x 8 consecutive samples per trajectory, 8 trajectories per pass. A lane keeps
+//           its segment's coefficients in registers for its 8 samples (re-broadcasting them per
+//           sample costs 240 B/sample of shared-memory bandwidth: the wall an earlier lane =
+//           sample version hit) and advances the 8 Horner evaluations together: 24 independent FMA
+//           chains for D = 3. The blocks of a chunk are laid out so that none straddles a segment
+//           crossing (segment A owns the first ceil(cross/8) blocks, segment B starts a new one),
+//           so there is no divergence. Results are staged in a bank-skewed shared-memory tile and
+//           leave the warp as whole, consecutive 256-byte stores: D*32 doubles of ONE trajectory
+//           per row. (Storing the registers directly as 16-byte pieces writes half sectors and
+//           measured 36 % slower.)
 //
-// The warp is self-contained (only __syncwarp), so occupancy is a pure launch knob.
+// Segment records {coefficients, tube constants, duration} live in per-trajectory shared-memory
+// SLOT PAIRS: segment s sits in slot s & 1, is fetched ONCE with cp.async (LDGSTS) by the
+// trajectory's lane, and the next segment is prefetched right after a chunk has been evaluated, a
+// few chunks before it is needed, so neither phase waits on DRAM in steady state (one commit group
+// per chunk; wait_group 1 retires all but the newest). A chunk stops early if a third segment
+// would start (tiny segments or large dt).
+//
+// The warp is self-contained (only __syncwarp; one warp per CTA), so occupancy is set by the
+// shared memory of a warp alone: 19 kB at TPW = 16 (11 warps/SM).
 // Replaces (reference): Polynomial::evaluate polynomial.h:136-149, Segment::evaluate
-// segment.cpp:51-58, Trajectory::evaluateRange trajectory.cpp:74-134, the sampled
-// limit check test_utils.h:43-54 / NL_I:2686-2733 and the sampled form of the tube
-// geometry polynomial_optimization_qcqp_impl.h:357-474.
+// segment.cpp:51-58, Trajectory::evaluateRange trajectory.cpp:74-134, the sampled limit check
+// test_utils.h:43-54 / NL_I:2686-2733 and the sampled form of the tube geometry
+// polynomial_optimization_qcqp_impl.h:357-474.
 #ifndef MTG_EVAL_TM_CUH_
 #define MTG_EVAL_TM_CUH_
 
@@ -34,12 +47,6 @@ constexpr int kTmChunk = 32;              // samples per trajectory per chunk (=
 constexpr int kTmTauLd = kTmChunk + 1;    // odd stride in 8-byte words: conflict-free lane-major stores
 constexpr int kTubeGeomLd = 16;           // doubles per (trajectory, segment) tube record (one 128-B line)
 
-__device__ __forceinline__ double2 ldg_nc2(const double2* p) {
-  double2 v;
-  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
-}
-
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
@@ -51,14 +58,6 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 __device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-// max over the warp of non-negative doubles (bit patterns order like the values)
-__device__ __forceinline__ double warp_max_nonneg(double x) {
-  const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
-  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
-  return __hiloint2double((int)mhi, (int)mlo);
-}
 
 // trajectory.cpp:88-111: first segment whose accumulated end time exceeds t_start; on
 // success acc is the START time of that segment, computed as (sum_{j<=i} T_j) - T_i like
@@ -106,15 +105,8 @@ __global__ void __launch_bounds__(256) tube_setup_kernel(const EvalParams p, dou
 // FEAS = true : position samples (optional) + v/a/tube flags + per-trajectory maxima.
 // Every per-sample output is trajectory-contiguous: x[b * max_samples * width + n * width + ...].
 //
-// Shared memory per warp (TmLayout): tau[32][33] | staging tile | info[32] | flag rows |
-// acc[32][33] (only when sampling_times is requested) | per-trajectory SEGMENT SLOTS.
-// A slot pair holds the records {coefficients, tube constants} + durations of the two
-// segments a chunk may touch: segment s lives in slot s & 1, is fetched ONCE with
-// cp.async (LDGSTS) by the trajectory's lane, and the next segment is prefetched right
-// after a chunk has been evaluated, a few chunks before it is needed, so neither phase
-// waits on DRAM in steady state (one commit group per chunk; wait_group 1 retires all
-// but the newest). A chunk stops early if a third segment would start (tiny segments
-// or large dt).
+// Shared memory per warp (TmLayout): tau[TPW][33] | staging tile [8][4*(8 D + 1)] | info, offsets,
+// counts | flag rows | acc[TPW][33] (only when sampling_times is requested) | slot pairs [TPW].
 constexpr int kTmR = 8;                  // consecutive samples per lane in phase 2
 constexpr int kTmG = 32 / (kTmChunk / kTmR);  // trajectories per phase-2 pass (8): 4 lanes each
 struct TmLayout {

@@ -134,3 +134,41 @@ def test_tables_against_exact_rationals():
         for j in range(N):
             assert H1[i, j] == float(H[i][j])
             assert Ai1[i, j] == float(Ai[i][j])
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference runs without a GPU (it times the oracle port on the host cores) and
+    puts exactly one JSON object on stdout, with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "trajectories/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["config"]["workload"].startswith("configs[1]")
+
+
+def test_bench_workload_generator_matches_the_reference_recipe():
+    """make_workload: vertices in the +-10 m box, consecutive vertices further than 0.2 m apart
+    (vertex.cpp:65-72), Nfabian times (vertex.cpp:252-269) equal to the oracle's."""
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    from oracle import pyoracle as po
+
+    pos, times = bench.make_workload(512, seed=1)
+    assert pos.shape == (11, 3, 512) and times.shape == (10, 512)
+    assert np.abs(pos).max() <= 10.0
+    d = np.sqrt((np.diff(pos, axis=0) ** 2).sum(axis=1))
+    assert d.min() > 0.2
+    for b in (0, 17, 511):
+        assert np.allclose(times[:, b], po.estimate_segment_times_nfabian(pos[:, :, b], 3.0, 5.0), rtol=1e-14)
