@@ -114,7 +114,8 @@ int mtg_get_tables(int N, int derivative, double* H1, double* Ainv1);
  *                                    last ([1]) vertex; NULL = all zero (makeStartOrEnd,
  *                                    src/vertex.cpp:147-153)
  *  seg_times        [K]              in
- *  coeffs           [K][D][N]        out, increasing powers (polynomial.h:35-36)
+ *  coeffs           [K][D][N]        out or NULL, increasing powers (polynomial.h:35-36); NULL = a
+ *                                    cost-only solve (candidate sweeps: 8 instead of 2,408 bytes out)
  *  cost             [B]              out or NULL, computeCost() = 0.5 sum c^T Q c
  *  free_constraints [D][K-1][N/2-1]  out or NULL, d_p exactly as getFreeConstraints
  *                                    returns it: per dimension, vertex-major,

@@ -175,7 +175,7 @@ class Context:
     # ------------------------------------------------------------------ solve
     def solve_batch(self, positions, seg_times, end_derivatives=None, N: int = 10,
                     derivative: int = 4, layout: str = "soa", want_cost=True, want_free=False,
-                    want_status=True, out=None, stream=None):
+                    want_status=True, want_coeffs=True, out=None, stream=None):
         """mtg_solve_batch.
         layout "soa": positions [K+1,D,B], seg_times [K,B], end_derivatives [2,N/2-1,D,B];
                       returns coeffs [K,D,N,B], free [D,K-1,N/2-1,B]
@@ -195,8 +195,8 @@ class Context:
         desc = ProblemDesc(B, K, D, N, derivative, mode, LAYOUT_AOS if aos else LAYOUT_SOA)
         out = out or {}
         nf = N // 2 - 1
-        coeffs = out.get("coeffs")
-        if coeffs is None:
+        coeffs = out.get("coeffs") if want_coeffs else None
+        if want_coeffs and coeffs is None:
             coeffs = self._empty(positions, (B, K, D, N) if aos else (K, D, N, B))
         cost = out.get("cost") if want_cost else None
         if want_cost and cost is None:

@@ -25,8 +25,9 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* po
                     double* cost, double* free_constraints, uint32_t* status, void* stream_) {
   int rc = validate_desc(ctx, desc);
   if (rc) return rc;
-  if (!positions || !seg_times || !coeffs)
-    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "positions, seg_times and coeffs are required");
+  if (!positions || !seg_times) return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "positions and seg_times are required");
+  if (!coeffs && !cost && !free_constraints)
+    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "at least one of coeffs, cost and free_constraints is required");
   if (desc->B == 0) return MTG_OK;
   MTG_CUDA_TRY(cudaSetDevice(ctx->device));
   rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
@@ -49,7 +50,7 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* po
     p.B = B;
     p.b0 = 0;
     p.nb = B;
-    p.vec_ok = ((uintptr_t)coeffs % 16 == 0) ? 1 : 0;
+    p.vec_ok = (coeffs && (uintptr_t)coeffs % 16 == 0) ? 1 : 0;
     return launch_solve_canonical(ctx, N, D, aos, p, stream);
   }
 

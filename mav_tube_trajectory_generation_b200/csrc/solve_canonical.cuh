@@ -136,7 +136,7 @@ __device__ __forceinline__ double emit_segment(const SolveCanonicalParams& p, in
       c[j] = acc * us;
       us *= u;
     }
-    if (active) {
+    if (active && p.coeffs) {  // coeffs == nullptr: cost-only solve (candidate sweeps)
       if (AOS) {
         double* out = p.coeffs + (size_t)b * rec + (size_t)(seg * D + dim) * N;
         if (p.vec_ok) {

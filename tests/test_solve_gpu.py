@@ -282,3 +282,22 @@ def test_launch_counter_moves():
     pos = np.random.RandomState(1).uniform(-5, 5, size=(4, 3, 3))
     gpu_solve(pos, np.full((4, 2), 2.0), 4)
     assert c.launch_count == n0 + 1
+
+
+def test_cost_only_solve(po):
+    """coeffs = NULL: the sweep form of the solve (cost, status and d_p only); same numbers."""
+    pos, times = random_problems(po, 1000, 10, 3, seed0=888)
+    c = ctx()
+    p, t = dev(soa(pos)), dev(soa(times))
+    full = c.solve_batch(p, t, want_free=True)
+    lean = c.solve_batch(p, t, want_free=True, want_coeffs=False)
+    assert lean["coeffs"] is None
+    assert np.array_equal(host(lean["cost"]), host(full["cost"]))
+    assert np.array_equal(host(lean["free"]), host(full["free"]))
+    assert np.array_equal(host(lean["status"]), host(full["status"]))
+    hl = c.solve_batch(soa(pos), soa(times), want_coeffs=False)       # host-memory mode
+    assert np.array_equal(hl["cost"], host(full["cost"]))
+    import mav_tube_trajectory_generation_b200 as m
+
+    with pytest.raises(m.MtgError):
+        c.solve_batch(p, t, want_coeffs=False, want_cost=False, want_free=False)
