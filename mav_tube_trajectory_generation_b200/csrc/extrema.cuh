@@ -58,9 +58,11 @@ __device__ __forceinline__ double eval_deriv(const double* g, int n, int k, doub
 }
 
 // Root of the k-th derivative inside (a, b), where it is monotone and f(a) f(b) < 0.
-__device__ __forceinline__ double refine_root(const double* g, int n, int k, double a, double b, double fa,
+__device__ __forceinline__ double refine_root(const double* g, int n, int k, double a, double b, double fa, double fb,
                                               uint32_t& st) {
-  double t = 0.5 * (a + b);
+  // first iterate: the secant point of the bracket (the midpoint if it degenerates)
+  double t = a - fa * ((b - a) / (fb - fa));
+  if (!(t > a && t < b)) t = 0.5 * (a + b);
   for (int it = 0; it < kRootIters; ++it) {
     const double ft = eval_deriv(g, n, k, t);
     if (ft == 0.0) return t;
@@ -131,26 +133,48 @@ __global__ void __launch_bounds__(128) extrema_segment_kernel(const ExtremaParam
   double* prev = ra;
   double* cur = rb;
   const double lo = 0.0, hi = T;
+  // Per level two passes, so that the lanes of a warp stay in step: pass 1 only SCANS the partition
+  // and collects the brackets with a sign change; pass 2 refines bracket r of every lane together
+  // (lanes differ in where their sign changes sit, far less in how many there are).
+  double bu[kMaxG], bv[kMaxG], bfu[kMaxG], bfv[kMaxG];
   for (int k = n - 1; k >= 0; --k) {
-    int nc = 0;
+    int nb = 0;
     double u = lo, fu = eval_deriv(g, n, k, u);
     for (int q = 0; q <= na; ++q) {
       const double v = (q < na) ? prev[q] : hi;
       if (!(v > u)) continue;
       const double fv = eval_deriv(g, n, k, v);
-      if (fu == 0.0) {
-        if (nc == 0 || cur[nc - 1] != u) cur[nc++] = u;
+      if (fu == 0.0) {  // a root exactly on a partition point
+        if (nb == 0 || bu[nb - 1] != u || bfu[nb - 1] != 0.0) {
+          bu[nb] = u;
+          bv[nb] = u;
+          bfu[nb] = 0.0;
+          bfv[nb] = 0.0;
+          ++nb;
+        }
       } else if (fv != 0.0 && ((fu < 0.0) != (fv < 0.0))) {
-        cur[nc++] = refine_root(g, n, k, u, v, fu, st);
+        bu[nb] = u;
+        bv[nb] = v;
+        bfu[nb] = fu;
+        bfv[nb] = fv;
+        ++nb;
       }
       u = v;
       fu = fv;
     }
-    if (fu == 0.0 && (nc == 0 || cur[nc - 1] != u)) cur[nc++] = u;  // root exactly at t_end
+    if (fu == 0.0 && (nb == 0 || bu[nb - 1] != u || bfu[nb - 1] != 0.0)) {  // root exactly at t_end
+      bu[nb] = u;
+      bv[nb] = u;
+      bfu[nb] = 0.0;
+      bfv[nb] = 0.0;
+      ++nb;
+    }
+    for (int r = 0; r < nb; ++r)
+      cur[r] = (bfu[r] == 0.0) ? bu[r] : refine_root(g, n, k, bu[r], bv[r], bfu[r], bfv[r], st);
     double* tmp = prev;
     prev = cur;
     cur = tmp;
-    na = nc;
+    na = nb;
   }
   if (n < 1) na = 0;  // constant polynomial: no roots (rpoly_ak1.cpp:76-80)
 
