@@ -50,21 +50,27 @@ struct ExtremaParams {
   int B, b0, nb, K, N, D, derivative;
 };
 
-// k-th derivative of the polynomial with n+1 coefficients g[0..n] at t (polynomial.h:136-149)
-__device__ __forceinline__ double eval_deriv(const double* g, int n, int k, double t) {
+// sum_j a[j] t^j, j = 0..deg
+__device__ __forceinline__ double horner_n(const double* a, int deg, double t) {
   double r = 0.0;
-  for (int i = n; i >= k; --i) r = fma(r, t, c_tab.base[k * MTG_BASE_LD + i] * g[i]);
+  for (int j = deg; j >= 0; --j) r = fma(r, t, a[j]);
   return r;
 }
 
 // Root of the k-th derivative inside (a, b), where it is monotone and f(a) f(b) < 0.
-__device__ __forceinline__ double refine_root(const double* g, int n, int k, double a, double b, double fa, double fb,
-                                              uint32_t& st) {
+// pk / pk1: coefficients of that derivative (degree deg) and of the next one (degree deg - 1).
+__device__ __forceinline__ double refine_root(const double* pk, const double* pk1, int deg, double a, double b,
+                                              double fa, double fb, uint32_t& st) {
   // first iterate: the secant point of the bracket (the midpoint if it degenerates)
   double t = a - fa * ((b - a) / (fb - fa));
   if (!(t > a && t < b)) t = 0.5 * (a + b);
   for (int it = 0; it < kRootIters; ++it) {
-    const double ft = eval_deriv(g, n, k, t);
+    // value and slope in one sweep (two independent FMA chains)
+    double ft = pk[deg], dft = 0.0;
+    for (int j = deg - 1; j >= 0; --j) {
+      dft = fma(dft, t, pk1[j]);
+      ft = fma(ft, t, pk[j]);
+    }
     if (ft == 0.0) return t;
     if ((ft < 0.0) == (fa < 0.0)) {
       a = t;
@@ -74,7 +80,6 @@ __device__ __forceinline__ double refine_root(const double* g, int n, int k, dou
     }
     const double width = b - a;
     if (!(width > 4.5e-16 * fmax(fabs(a), fabs(b)))) return t;
-    const double dft = eval_deriv(g, n, k + 1, t);
     double tn = t - ft / dft;
     if (!(tn > a && tn < b)) tn = 0.5 * (a + b);
     if (tn == t) return t;
@@ -137,13 +142,27 @@ __global__ void __launch_bounds__(128) extrema_segment_kernel(const ExtremaParam
   // and collects the brackets with a sign change; pass 2 refines bracket r of every lane together
   // (lanes differ in where their sign changes sit, far less in how many there are).
   double bu[kMaxG], bv[kMaxG], bfu[kMaxG], bfv[kMaxG];
+  // coefficients of the current level's polynomial g^(k) and of g^(k+1), built once per level from
+  // the table row B(k, .) (polynomial.h:99-113): every evaluation is then a plain Horner sum
+  double ca[kMaxG], cb[kMaxG];
+  double* pk = ca;
+  double* pk1 = cb;
+  for (int j = 0; j < kMaxG; ++j) pk[j] = pk1[j] = 0.0;
+  if (n >= 1) pk[0] = c_tab.base[n * MTG_BASE_LD + n] * g[n];  // g^(n): a constant
   for (int k = n - 1; k >= 0; --k) {
+    {
+      double* tmpc = pk1;
+      pk1 = pk;
+      pk = tmpc;
+    }
+    const int deg = n - k;
+    for (int j = 0; j <= deg; ++j) pk[j] = c_tab.base[k * MTG_BASE_LD + j + k] * g[j + k];
     int nb = 0;
-    double u = lo, fu = eval_deriv(g, n, k, u);
+    double u = lo, fu = horner_n(pk, deg, u);
     for (int q = 0; q <= na; ++q) {
       const double v = (q < na) ? prev[q] : hi;
       if (!(v > u)) continue;
-      const double fv = eval_deriv(g, n, k, v);
+      const double fv = horner_n(pk, deg, v);
       if (fu == 0.0) {  // a root exactly on a partition point
         if (nb == 0 || bu[nb - 1] != u || bfu[nb - 1] != 0.0) {
           bu[nb] = u;
@@ -170,7 +189,7 @@ __global__ void __launch_bounds__(128) extrema_segment_kernel(const ExtremaParam
       ++nb;
     }
     for (int r = 0; r < nb; ++r)
-      cur[r] = (bfu[r] == 0.0) ? bu[r] : refine_root(g, n, k, bu[r], bv[r], bfu[r], bfv[r], st);
+      cur[r] = (bfu[r] == 0.0) ? bu[r] : refine_root(pk, pk1, deg, bu[r], bv[r], bfu[r], bfv[r], st);
     double* tmp = prev;
     prev = cur;
     cur = tmp;
