@@ -59,8 +59,9 @@ __device__ __forceinline__ double horner_n(const double* a, int deg, double t) {
 
 // Root of the k-th derivative inside (a, b), where it is monotone and f(a) f(b) < 0.
 // pk / pk1: coefficients of that derivative (degree deg) and of the next one (degree deg - 1).
+// tol: absolute width at which the bracket is good enough (0 for the final level: full precision).
 __device__ __forceinline__ double refine_root(const double* pk, const double* pk1, int deg, double a, double b,
-                                              double fa, double fb, uint32_t& st) {
+                                              double fa, double fb, double tol, uint32_t& st) {
   // first iterate: the secant point of the bracket (the midpoint if it degenerates)
   double t = a - fa * ((b - a) / (fb - fa));
   if (!(t > a && t < b)) t = 0.5 * (a + b);
@@ -79,10 +80,10 @@ __device__ __forceinline__ double refine_root(const double* pk, const double* pk
       b = t;
     }
     const double width = b - a;
-    if (!(width > 4.5e-16 * fmax(fabs(a), fabs(b)))) return t;
+    if (!(width > fmax(tol, 4.5e-16 * fmax(fabs(a), fabs(b))))) return t;
     double tn = t - ft / dft;
     if (!(tn > a && tn < b)) tn = 0.5 * (a + b);
-    if (tn == t) return t;
+    if (!(fabs(tn - t) > tol)) return tn;
     t = tn;
   }
   st |= 16u;  // MTG_ST_NO_CONVERGENCE (reference: rpoly prints and returns partial roots, RPOLY_C:372-377)
@@ -142,6 +143,9 @@ __global__ void __launch_bounds__(128) extrema_segment_kernel(const ExtremaParam
   // and collects the brackets with a sign change; pass 2 refines bracket r of every lane together
   // (lanes differ in where their sign changes sit, far less in how many there are).
   double bu[kMaxG], bv[kMaxG], bfu[kMaxG], bfv[kMaxG];
+  // roots of the upper levels only PARTITION [0, T] for the level below: 1e-12 T is plenty; the
+  // roots of g itself (k = 0) are refined to full precision
+  const double tol_upper = 1e-12 * T;
   // coefficients of the current level's polynomial g^(k) and of g^(k+1), built once per level from
   // the table row B(k, .) (polynomial.h:99-113): every evaluation is then a plain Horner sum
   double ca[kMaxG], cb[kMaxG];
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(128) extrema_segment_kernel(const ExtremaParam
       ++nb;
     }
     for (int r = 0; r < nb; ++r)
-      cur[r] = (bfu[r] == 0.0) ? bu[r] : refine_root(pk, pk1, deg, bu[r], bv[r], bfu[r], bfv[r], st);
+      cur[r] = (bfu[r] == 0.0) ? bu[r] : refine_root(pk, pk1, deg, bu[r], bv[r], bfu[r], bfv[r], k ? tol_upper : 0.0, st);
     double* tmp = prev;
     prev = cur;
     cur = tmp;
