@@ -59,6 +59,19 @@ __device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Bulk (TMA) store of a staged row: shared memory -> global memory, both 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_store(double* gdst, const double* smem_src, unsigned bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_src);
+  const size_t ga = __cvta_generic_to_global(gdst);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(ga), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+// the committed bulk stores have finished READING shared memory (the tile may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
+// orders this thread's shared-memory writes before later async-proxy (bulk copy) reads
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 // trajectory.cpp:88-111: first segment whose accumulated end time exceeds t_start; on
 // success acc is the START time of that segment, computed as (sum_{j<=i} T_j) - T_i like
 // the reference. false: t_start out of range (reference: LOG(ERROR) + empty result;
@@ -107,6 +120,20 @@ __global__ void __launch_bounds__(256) tube_setup_kernel(const EvalParams p, dou
 //
 // Shared memory per warp (TmLayout): tau[TPW][33] | staging tile [8][4*(8 D + 1)] | info, offsets,
 // counts | flag rows | acc[TPW][33] (only when sampling_times is requested) | slot pairs [TPW].
+#ifndef MTG_TM_BULK
+#define MTG_TM_BULK 0  // 1: staged rows leave through bulk (TMA) stores; 0: through 256-byte warp stores
+#endif
+constexpr bool kTmBulk = MTG_TM_BULK != 0;
+#ifndef MTG_TM_STAGES
+#define MTG_TM_STAGES 2  // staging tiles of the bulk path (2: a pass never waits for the previous pass's store)
+#endif
+constexpr int kTmStages = kTmBulk ? MTG_TM_STAGES : 1;
+#ifndef MTG_TM_TAUBLK
+#define MTG_TM_TAUBLK 1  // 1: phase 1 parks tau at block starts only, phase-2 lanes replay their 8 adds
+#endif
+// (position / derivative sweeps only: measured +6 % there, -10 % on the register-bound feasibility sweep)
+__host__ __device__ constexpr bool tm_taublk(int mode) { return MTG_TM_TAUBLK != 0 && mode < 2; }
+constexpr int kTmBlkLd = 5;              // parked block-start taus per trajectory (4) + 1: odd stride
 constexpr int kTmR = 8;                  // consecutive samples per lane in phase 2
 constexpr int kTmG = 32 / (kTmChunk / kTmR);  // trajectories per phase-2 pass (8): 4 lanes each
 struct TmLayout {
@@ -114,20 +141,28 @@ struct TmLayout {
   int traj_bytes;   // 2 slots + {T of slot 0, T of slot 1}
   int blk_ld;       // doubles per lane block in the staging tile: 8*D + 1 (bank skew)
   int row_ld;       // doubles per trajectory row of the staging tile: 4 * blk_ld
-  int off_stage, off_info, off_off, off_cnt, off_flag, off_acc, off_slots, per_warp;
+  int off_stage, off_info, off_off, off_cnt, off_flag, off_acc, off_slots, off_dt, per_warp;
 };
 // TPW = trajectories per warp (phase-1 lanes in use): the shared memory of a warp scales with it.
 // 16 doubles the resident warps of the latency-bound position sweep; the fp64-bound feasibility
 // sweep prefers full phase-1 lanes (32).
 __host__ __device__ constexpr int tm_tpw(int mode) { return mode >= 2 ? 16 : 16; }
-__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, int kTmTPW) {
+__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, int kTmTPW, bool kTmTauBlk) {
   TmLayout L;
   L.slot_bytes = D * NT * 8 + (tube ? kTubeGeomLd * 8 : 0);
   L.traj_bytes = 2 * L.slot_bytes + 16;
   L.blk_ld = kTmR * D + 1;
   L.row_ld = (kTmChunk / kTmR) * L.blk_ld;
-  L.off_stage = kTmTPW * kTmTauLd * 8;
-  L.off_info = L.off_stage + kTmG * L.row_ld * 8;
+  if (kTmBulk) {
+    // rows are stored exactly as they lie in global memory (+ one double of alignment slack);
+    // row_ld = 2 (mod 16) doubles spreads the 4 trajectories of a half-warp over distinct banks
+    L.blk_ld = kTmR * D;
+    L.row_ld = kTmChunk * D + 1;
+    while (L.row_ld % 16 != 2) ++L.row_ld;
+  }
+  L.off_dt = kTmTPW * (kTmTauBlk ? kTmBlkLd : kTmTauLd) * 8;
+  L.off_stage = L.off_dt + (kTmTauBlk ? kTmTPW * 8 : 0);
+  L.off_info = L.off_stage + kTmStages * kTmG * L.row_ld * 8;
   L.off_off = L.off_info + kTmTPW * 16;
   L.off_cnt = L.off_off + kTmTPW * 8;
   L.off_flag = L.off_cnt + kTmTPW * 4;
@@ -154,7 +189,8 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr bool EXTRA = MODE == TM_DERIVATIVE;  // sampling_times / segment_idx outputs exist in this mode only
   const bool want_acc = EXTRA && p.sampling_times != nullptr;
-  const TmLayout L = tm_layout(D, NT, want_acc, tube, kTmTPW);
+  constexpr bool kTmTauBlk = tm_taublk(MODE);
+  const TmLayout L = tm_layout(D, NT, want_acc, tube, kTmTPW, kTmTauBlk);
   unsigned char* wbase = tm_smem + (size_t)warp * L.per_warp;
   double* tau_s = reinterpret_cast<double*>(wbase);
   double* stage = reinterpret_cast<double*>(wbase + L.off_stage);
@@ -164,6 +200,8 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
   int* cnt_s = reinterpret_cast<int*>(wbase + L.off_cnt);
   double* acc_s = reinterpret_cast<double*>(wbase + L.off_acc);
   unsigned char* slots = wbase + L.off_slots;
+  double* dt_s = reinterpret_cast<double*>(wbase + L.off_dt);
+  constexpr int TAU_LD = kTmTauBlk ? kTmBlkLd : kTmTauLd;
 
   const int first = (blockIdx.x * (blockDim.x >> 5) + warp) * kTmTPW;  // local index of lane 0's trajectory
   if (first >= p.nb) return;
@@ -190,6 +228,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
   else
     tau = t0 - acc;
   if (!valid) done = true;
+  if (kTmTauBlk && lane < kTmTPW) dt_s[lane] = dt;
   double mv2 = 0.0, ma2 = 0.0;  // FEAS: running maxima of |v|^2, |a|^2 (lane = trajectory)
   unsigned all_bits = 7u;
 
@@ -197,6 +236,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
   int held0 = -1, held1 = -1;  // segment resident (or in flight) in slot 0 / 1
   int age0 = -1, age1 = -1;    // chunk index whose commit group carries that fetch
   int chunk = 0;
+  int tile = 0;  // staging tile of the next phase-2 pass (bulk path)
   unsigned char* my_slots = slots + (size_t)lane * L.traj_bytes;
   const double* my_coeffs = p.coeffs + (size_t)b * ((size_t)K * D * NT);
   const double* my_times = p.seg_times + (size_t)b * K;
@@ -243,8 +283,9 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
       Ti = duration(i);
       const int rows_left = p.max_samples - n;
       int limit = min(kTmChunk, rows_left);
-      double* trow = tau_s + lane * kTmTauLd;
+      double* trow = tau_s + lane * TAU_LD;
       double* arow = acc_s + lane * kTmTauLd;
+      int mark = 0, blk = 0;  // kTmTauBlk: next block-start sample, blocks parked so far
       for (;;) {
         // straight run inside the current segment, four samples per trip while all four are
         // certain (same adds in the same order: tau_k and acc_k are the reference's values)
@@ -255,10 +296,18 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
           // dt > 0 and rounding is monotone, so tau <= tau1 <= tau2 <= tau3 and likewise acc: the last
           // sample's two tests imply the other six
           if (!((acc3 < t1) & !(tau3 > Ti))) break;
-          trow[cnt] = tau;
-          trow[cnt + 1] = tau1;
-          trow[cnt + 2] = tau2;
-          trow[cnt + 3] = tau3;
+          if (kTmTauBlk) {
+            const int dm = mark - cnt;  // >= 0; blocks are 8 samples apart: at most one starts in this trip
+            if (dm < 4) {
+              trow[blk++] = dm == 0 ? tau : dm == 1 ? tau1 : dm == 2 ? tau2 : tau3;
+              mark += R;
+            }
+          } else {
+            trow[cnt] = tau;
+            trow[cnt + 1] = tau1;
+            trow[cnt + 2] = tau2;
+            trow[cnt + 3] = tau3;
+          }
           if (want_acc) {
             arow[cnt] = acc;
             arow[cnt + 1] = acc1;
@@ -270,7 +319,14 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
           cnt += 4;
         }
         while (cnt < limit && acc < t1 && !(tau > Ti)) {
-          trow[cnt] = tau;
+          if (kTmTauBlk) {
+            if (cnt == mark) {
+              trow[blk++] = tau;
+              mark += R;
+            }
+          } else {
+            trow[cnt] = tau;
+          }
           if (want_acc) arow[cnt] = acc;
           tau += dt;
           acc += dt;
@@ -293,6 +349,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
             break;  // a third segment: leave it to the next chunk
           } else {
             cross = cnt;
+            mark = cnt;  // segment B's blocks start at the crossing
             // phase 2 gives segment A the blocks [0, ceil(cross/8)) and segment B the rest:
             // no 8-sample block straddles the crossing (costs < 8 samples of this chunk)
             limit = min(limit, cross + R * (kTmChunk / R - (cross + R - 1) / R));
@@ -355,15 +412,36 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
       load_segment(info.z + (isB ? 1 : 0));
       double v2m = 0.0, a2m = 0.0;
       unsigned fand = 7u;
-      double* srow = stage + q8 * L.row_ld;
+      double* const tile_s = stage + (kTmStages > 1 ? tile * (G * L.row_ld) : 0);
+      if (kTmStages > 1) tile ^= 1;
+      double* srow = tile_s + q8 * L.row_ld;
+      if (kTmBulk) {
+        // a row starts on the 16-byte phase of its global destination: one double later if that is odd
+        const size_t e0 = ((size_t)(p.b0 + first + r) * S + (size_t)info.y) * D;
+        srow += (int)((((uintptr_t)p.samples >> 3) + e0) & 1);
+      }
       // JB samples advance together, one Horner step at a time: JB*D (position) or 3*JB*D
       // (feasibility) independent FMA chains cover the fp64 pipe latency from a single warp.
       constexpr int JB = FEAS ? 4 : R;
+      double tcur = 0.0, dt_r = 0.0;
+      if (kTmTauBlk) {
+        tcur = tau_s[r * TAU_LD + sb];
+        dt_r = dt_s[r];
+      }
 #pragma unroll
       for (int j0 = 0; j0 < R; j0 += JB) {
         double ta[JB];
+        if (kTmTauBlk) {
+          // the block's taus from its parked first one: the same adds in the same order as phase 1
 #pragma unroll
-        for (int j = 0; j < JB; ++j) ta[j] = tau_s[r * kTmTauLd + min(start + j0 + j, last)];
+          for (int j = 0; j < JB; ++j) {
+            ta[j] = tcur;
+            tcur += dt_r;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < JB; ++j) ta[j] = tau_s[r * kTmTauLd + min(start + j0 + j, last)];
+        }
         double x[JB][D];
         if (!FEAS) {
           if (MODE == TM_POSITION) {
@@ -440,12 +518,21 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
             }
           }
         }
+        if (kTmBulk && j0 == 0) {
+          // the previous pass's bulk stores must have read the tile before it is overwritten
+          if (lane < G) {
+            if (kTmStages > 1) bulk_wait_read1(); else bulk_wait_read();
+          }
+          __syncwarp();
+        }
+        if (!kTmBulk || p.samples) {
 #pragma unroll
-        for (int j = 0; j < JB; ++j) {
-          const int k = start + j0 + j;
-          if (j0 + j < count) {
+          for (int j = 0; j < JB; ++j) {
+            const int k = start + j0 + j;
+            if (j0 + j < count) {
 #pragma unroll
-            for (int dim = 0; dim < D; ++dim) srow[k * D + (k >> 3) + dim] = x[j][dim];
+              for (int dim = 0; dim < D; ++dim) srow[k * D + (kTmBulk ? 0 : (k >> 3)) + dim] = x[j][dim];
+            }
           }
         }
       }
@@ -466,16 +553,36 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
           all_bits &= of;
         }
       }
+      if (kTmBulk) fence_proxy_async_smem();
       __syncwarp();
+      if (kTmBulk && p.samples && lane < G) {
+        // staged rows -> global memory: lane t hands row t to the copy engine as ONE bulk store of its
+        // 16-byte-aligned body; an odd first / last double is stored directly
+        const int total = cnt_s[g * G + lane] * D;
+        if (total > 0) {
+          double* out = p.samples + off_s[g * G + lane] * D;
+          const int odd = (int)(((uintptr_t)out >> 3) & 1);
+          const double* row = tile_s + lane * L.row_ld + odd;
+          int e1 = total;
+          if ((odd + total) & 1) {
+            --e1;
+            out[e1] = row[e1];
+          }
+          if (odd) out[0] = row[0];
+          if (e1 > odd) bulk_store(out + odd, row + odd, (unsigned)(e1 - odd) * 8u);
+        }
+        bulk_commit();
+      }
       // staged rows -> global memory: whole consecutive 256-byte stores per trajectory
       // (cnt == 0 rows fall out through the predicates; everything else is branch-free)
+      if (!kTmBulk || FEAS || EXTRA)
 #pragma unroll
       for (int t = 0; t < G; ++t) {
         const int cnt_t = cnt_s[g * G + t];
         const size_t o = off_s[g * G + t];
-        if (p.samples) {
+        if (!kTmBulk && p.samples) {
           double* out = p.samples + o * D + lane;
-          const double* row = stage + t * L.row_ld;
+          const double* row = tile_s + t * L.row_ld;
           const int total = cnt_t * D;
 #pragma unroll
           for (int q = 0; q < D; ++q)
@@ -503,6 +610,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
     cp_async_commit();
   }
   cp_async_wait_all();
+  if (kTmBulk) bulk_wait_read();  // shared memory must outlive the bulk reads
   if (valid) {
     if (p.n_samples) p.n_samples[b] = n;
     if (p.status) p.status[b] = st;
