@@ -28,10 +28,10 @@ constexpr int kTubeChunk = 65536;       // trajectories per launch pair when a t
 template <int NT, int D, int MODE>
 int launch_tm_t(mtg_ctx* ctx, const EvalParams& p, const double* geom, cudaStream_t s) {
   const bool want_acc = MODE == TM_DERIVATIVE && p.sampling_times != nullptr;
-  const size_t smem = (size_t)tm_layout(D, NT, want_acc, MODE == TM_FEAS_TUBE, tm_tpw(MODE), tm_taublk(MODE)).per_warp * (kTmBlock / 32);
+  const size_t smem = (size_t)tm_layout(D, NT, want_acc, MODE == TM_FEAS_TUBE, tm_tpw(MODE), MODE).per_warp * (kTmBlock / 32);
   auto kern = eval_tm_kernel<NT, D, MODE>;
-  if (smem > 48 * 1024) MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_block = (kTmBlock / 32) * tm_tpw(MODE);  // trajectories per CTA
+  if (smem > 48 * 1024) MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (p.nb + per_block - 1) / per_block;
   if (grid == 0) return MTG_OK;
   kern<<<grid, kTmBlock, smem, s>>>(p, geom);

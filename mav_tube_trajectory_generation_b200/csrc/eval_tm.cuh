@@ -59,19 +59,6 @@ __device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// Bulk (TMA) store of a staged row: shared memory -> global memory, both 16-byte aligned, bytes % 16 == 0.
-__device__ __forceinline__ void bulk_store(double* gdst, const double* smem_src, unsigned bytes) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_src);
-  const size_t ga = __cvta_generic_to_global(gdst);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(ga), "r"(sa), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-// the committed bulk stores have finished READING shared memory (the tile may be overwritten)
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
-// orders this thread's shared-memory writes before later async-proxy (bulk copy) reads
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
 // trajectory.cpp:88-111: first segment whose accumulated end time exceeds t_start; on
 // success acc is the START time of that segment, computed as (sum_{j<=i} T_j) - T_i like
 // the reference. false: t_start out of range (reference: LOG(ERROR) + empty result;
@@ -120,14 +107,6 @@ __global__ void __launch_bounds__(256) tube_setup_kernel(const EvalParams p, dou
 //
 // Shared memory per warp (TmLayout): tau[TPW][33] | staging tile [8][4*(8 D + 1)] | info, offsets,
 // counts | flag rows | acc[TPW][33] (only when sampling_times is requested) | slot pairs [TPW].
-#ifndef MTG_TM_BULK
-#define MTG_TM_BULK 0  // 1: staged rows leave through bulk (TMA) stores; 0: through 256-byte warp stores
-#endif
-constexpr bool kTmBulk = MTG_TM_BULK != 0;
-#ifndef MTG_TM_STAGES
-#define MTG_TM_STAGES 2  // staging tiles of the bulk path (2: a pass never waits for the previous pass's store)
-#endif
-constexpr int kTmStages = kTmBulk ? MTG_TM_STAGES : 1;
 #ifndef MTG_TM_TAUBLK
 #define MTG_TM_TAUBLK 1  // 1: phase 1 parks tau at block starts only, phase-2 lanes replay their 8 adds
 #endif
@@ -147,22 +126,16 @@ struct TmLayout {
 // 16 doubles the resident warps of the latency-bound position sweep; the fp64-bound feasibility
 // sweep prefers full phase-1 lanes (32).
 __host__ __device__ constexpr int tm_tpw(int mode) { return mode >= 2 ? 16 : 16; }
-__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, int kTmTPW, bool kTmTauBlk) {
+__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, int kTmTPW, int mode) {
+  const bool kTmTauBlk = tm_taublk(mode);
   TmLayout L;
   L.slot_bytes = D * NT * 8 + (tube ? kTubeGeomLd * 8 : 0);
   L.traj_bytes = 2 * L.slot_bytes + 16;
   L.blk_ld = kTmR * D + 1;
   L.row_ld = (kTmChunk / kTmR) * L.blk_ld;
-  if (kTmBulk) {
-    // rows are stored exactly as they lie in global memory (+ one double of alignment slack);
-    // row_ld = 2 (mod 16) doubles spreads the 4 trajectories of a half-warp over distinct banks
-    L.blk_ld = kTmR * D;
-    L.row_ld = kTmChunk * D + 1;
-    while (L.row_ld % 16 != 2) ++L.row_ld;
-  }
   L.off_dt = kTmTPW * (kTmTauBlk ? kTmBlkLd : kTmTauLd) * 8;
   L.off_stage = L.off_dt + (kTmTauBlk ? kTmTPW * 8 : 0);
-  L.off_info = L.off_stage + kTmStages * kTmG * L.row_ld * 8;
+  L.off_info = L.off_stage + kTmG * L.row_ld * 8;
   L.off_off = L.off_info + kTmTPW * 16;
   L.off_cnt = L.off_off + kTmTPW * 8;
   L.off_flag = L.off_cnt + kTmTPW * 4;
@@ -178,7 +151,7 @@ enum TmMode { TM_POSITION = 0, TM_DERIVATIVE = 1, TM_FEAS = 2, TM_FEAS_TUBE = 3 
 // Requirements (checked by the launcher, which otherwise falls back to the one-thread-per-
 // trajectory kernels of eval.cuh): AoS layout, N == NT, coeffs 16-byte aligned.
 template <int NT, int D, int MODE>
-__global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
+__global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr bool FEAS = MODE >= TM_FEAS;
   constexpr bool tube = MODE == TM_FEAS_TUBE;
@@ -190,7 +163,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
   constexpr bool EXTRA = MODE == TM_DERIVATIVE;  // sampling_times / segment_idx outputs exist in this mode only
   const bool want_acc = EXTRA && p.sampling_times != nullptr;
   constexpr bool kTmTauBlk = tm_taublk(MODE);
-  const TmLayout L = tm_layout(D, NT, want_acc, tube, kTmTPW, kTmTauBlk);
+  const TmLayout L = tm_layout(D, NT, want_acc, tube, kTmTPW, MODE);
   unsigned char* wbase = tm_smem + (size_t)warp * L.per_warp;
   double* tau_s = reinterpret_cast<double*>(wbase);
   double* stage = reinterpret_cast<double*>(wbase + L.off_stage);
@@ -236,7 +209,6 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
   int held0 = -1, held1 = -1;  // segment resident (or in flight) in slot 0 / 1
   int age0 = -1, age1 = -1;    // chunk index whose commit group carries that fetch
   int chunk = 0;
-  int tile = 0;  // staging tile of the next phase-2 pass (bulk path)
   unsigned char* my_slots = slots + (size_t)lane * L.traj_bytes;
   const double* my_coeffs = p.coeffs + (size_t)b * ((size_t)K * D * NT);
   const double* my_times = p.seg_times + (size_t)b * K;
@@ -412,14 +384,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
       load_segment(info.z + (isB ? 1 : 0));
       double v2m = 0.0, a2m = 0.0;
       unsigned fand = 7u;
-      double* const tile_s = stage + (kTmStages > 1 ? tile * (G * L.row_ld) : 0);
-      if (kTmStages > 1) tile ^= 1;
-      double* srow = tile_s + q8 * L.row_ld;
-      if (kTmBulk) {
-        // a row starts on the 16-byte phase of its global destination: one double later if that is odd
-        const size_t e0 = ((size_t)(p.b0 + first + r) * S + (size_t)info.y) * D;
-        srow += (int)((((uintptr_t)p.samples >> 3) + e0) & 1);
-      }
+      double* srow = stage + q8 * L.row_ld;
       // JB samples advance together, one Horner step at a time: JB*D (position) or 3*JB*D
       // (feasibility) independent FMA chains cover the fp64 pipe latency from a single warp.
       constexpr int JB = FEAS ? 4 : R;
@@ -428,6 +393,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
         tcur = tau_s[r * TAU_LD + sb];
         dt_r = dt_s[r];
       }
+      double x[JB][D];
 #pragma unroll
       for (int j0 = 0; j0 < R; j0 += JB) {
         double ta[JB];
@@ -442,7 +408,6 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
 #pragma unroll
           for (int j = 0; j < JB; ++j) ta[j] = tau_s[r * kTmTauLd + min(start + j0 + j, last)];
         }
-        double x[JB][D];
         if (!FEAS) {
           if (MODE == TM_POSITION) {
 #pragma unroll
@@ -518,21 +483,12 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
             }
           }
         }
-        if (kTmBulk && j0 == 0) {
-          // the previous pass's bulk stores must have read the tile before it is overwritten
-          if (lane < G) {
-            if (kTmStages > 1) bulk_wait_read1(); else bulk_wait_read();
-          }
-          __syncwarp();
-        }
-        if (!kTmBulk || p.samples) {
 #pragma unroll
-          for (int j = 0; j < JB; ++j) {
-            const int k = start + j0 + j;
-            if (j0 + j < count) {
+        for (int j = 0; j < JB; ++j) {
+          const int k = start + j0 + j;
+          if (j0 + j < count) {
 #pragma unroll
-              for (int dim = 0; dim < D; ++dim) srow[k * D + (kTmBulk ? 0 : (k >> 3)) + dim] = x[j][dim];
-            }
+            for (int dim = 0; dim < D; ++dim) srow[k * D + (k >> 3) + dim] = x[j][dim];
           }
         }
       }
@@ -553,36 +509,16 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
           all_bits &= of;
         }
       }
-      if (kTmBulk) fence_proxy_async_smem();
       __syncwarp();
-      if (kTmBulk && p.samples && lane < G) {
-        // staged rows -> global memory: lane t hands row t to the copy engine as ONE bulk store of its
-        // 16-byte-aligned body; an odd first / last double is stored directly
-        const int total = cnt_s[g * G + lane] * D;
-        if (total > 0) {
-          double* out = p.samples + off_s[g * G + lane] * D;
-          const int odd = (int)(((uintptr_t)out >> 3) & 1);
-          const double* row = tile_s + lane * L.row_ld + odd;
-          int e1 = total;
-          if ((odd + total) & 1) {
-            --e1;
-            out[e1] = row[e1];
-          }
-          if (odd) out[0] = row[0];
-          if (e1 > odd) bulk_store(out + odd, row + odd, (unsigned)(e1 - odd) * 8u);
-        }
-        bulk_commit();
-      }
       // staged rows -> global memory: whole consecutive 256-byte stores per trajectory
       // (cnt == 0 rows fall out through the predicates; everything else is branch-free)
-      if (!kTmBulk || FEAS || EXTRA)
 #pragma unroll
       for (int t = 0; t < G; ++t) {
         const int cnt_t = cnt_s[g * G + t];
         const size_t o = off_s[g * G + t];
-        if (!kTmBulk && p.samples) {
+        if (p.samples) {
           double* out = p.samples + o * D + lane;
-          const double* row = tile_s + t * L.row_ld;
+          const double* row = stage + t * L.row_ld;
           const int total = cnt_t * D;
 #pragma unroll
           for (int q = 0; q < D; ++q)
@@ -610,7 +546,6 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : 12)) eval_tm_kernel(const
     cp_async_commit();
   }
   cp_async_wait_all();
-  if (kTmBulk) bulk_wait_read();  // shared memory must outlive the bulk reads
   if (valid) {
     if (p.n_samples) p.n_samples[b] = n;
     if (p.status) p.status[b] = st;
