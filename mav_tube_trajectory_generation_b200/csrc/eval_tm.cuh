@@ -259,8 +259,34 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
       double* arow = acc_s + lane * kTmTauLd;
       int mark = 0, blk = 0;  // kTmTauBlk: next block-start sample, blocks parked so far
       for (;;) {
-        // straight run inside the current segment, four samples per trip while all four are
-        // certain (same adds in the same order: tau_k and acc_k are the reference's values)
+        // straight run inside the current segment: a whole 8-sample block per trip while all eight
+        // samples are certain, then four per trip (same adds in the same order: tau_k and acc_k are the
+        // reference's values; dt > 0 and rounding is monotone, so the last sample's two tests imply the others)
+        while (cnt + R <= limit && (!kTmTauBlk || cnt == mark)) {
+          double tk[R], ak[R];
+          tk[0] = tau;
+          ak[0] = acc;
+#pragma unroll
+          for (int j = 1; j < R; ++j) {
+            tk[j] = tk[j - 1] + dt;
+            ak[j] = ak[j - 1] + dt;
+          }
+          if (!((ak[R - 1] < t1) & !(tk[R - 1] > Ti))) break;
+          if (kTmTauBlk) {
+            trow[blk++] = tau;
+            mark += R;
+          } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) trow[cnt + j] = tk[j];
+          }
+          if (want_acc) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) arow[cnt + j] = ak[j];
+          }
+          tau = tk[R - 1] + dt;
+          acc = ak[R - 1] + dt;
+          cnt += R;
+        }
         while (cnt + 4 <= limit) {
           const double tau1 = tau + dt, acc1 = acc + dt;
           const double tau2 = tau1 + dt, acc2 = acc1 + dt;
