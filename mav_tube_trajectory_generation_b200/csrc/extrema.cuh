@@ -57,39 +57,6 @@ __device__ __forceinline__ double horner_n(const double* a, int deg, double t) {
   return r;
 }
 
-// Root of the k-th derivative inside (a, b), where it is monotone and f(a) f(b) < 0.
-// pk / pk1: coefficients of that derivative (degree deg) and of the next one (degree deg - 1).
-// tol: absolute width at which the bracket is good enough (0 for the final level: full precision).
-__device__ __forceinline__ double refine_root(const double* pk, const double* pk1, int deg, double a, double b,
-                                              double fa, double fb, double tol, uint32_t& st) {
-  // first iterate: the secant point of the bracket (the midpoint if it degenerates)
-  double t = a - fa * ((b - a) / (fb - fa));
-  if (!(t > a && t < b)) t = 0.5 * (a + b);
-  for (int it = 0; it < kRootIters; ++it) {
-    // value and slope in one sweep (two independent FMA chains)
-    double ft = pk[deg], dft = 0.0;
-    for (int j = deg - 1; j >= 0; --j) {
-      dft = fma(dft, t, pk1[j]);
-      ft = fma(ft, t, pk[j]);
-    }
-    if (ft == 0.0) return t;
-    if ((ft < 0.0) == (fa < 0.0)) {
-      a = t;
-      fa = ft;
-    } else {
-      b = t;
-    }
-    const double width = b - a;
-    if (!(width > fmax(tol, 4.5e-16 * fmax(fabs(a), fabs(b))))) return t;
-    double tn = t - ft / dft;
-    if (!(tn > a && tn < b)) tn = 0.5 * (a + b);
-    if (!(fabs(tn - t) > tol)) return tn;
-    t = tn;
-  }
-  st |= 16u;  // MTG_ST_NO_CONVERGENCE (reference: rpoly prints and returns partial roots, RPOLY_C:372-377)
-  return t;
-}
-
 template <bool AOS>
 __global__ void __launch_bounds__(128) extrema_segment_kernel(const ExtremaParams p) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,8 +159,71 @@ __global__ void __launch_bounds__(128) extrema_segment_kernel(const ExtremaParam
       bfv[nb] = 0.0;
       ++nb;
     }
-    for (int r = 0; r < nb; ++r)
-      cur[r] = (bfu[r] == 0.0) ? bu[r] : refine_root(pk, pk1, deg, bu[r], bv[r], bfu[r], bfv[r], k ? tol_upper : 0.0, st);
+    // Refinement, flattened: ONE loop whose trip is one bracketed-Newton iteration of whichever bracket the
+    // lane is working on (the iterates of refine_root, unchanged). The lanes of a warp then wait for the
+    // largest SUM of iterations instead of the sum over brackets of the largest iteration count.
+    {
+      const double tol = k ? tol_upper : 0.0;
+      int r = 0, it = 0;
+      bool have = false;
+      double a = 0.0, bb = 0.0, fa = 0.0, t = 0.0;
+      for (;;) {
+        if (!have) {
+          while (r < nb && bfu[r] == 0.0) {  // a root exactly on a partition point
+            cur[r] = bu[r];
+            ++r;
+          }
+          if (r >= nb) break;
+          a = bu[r];
+          bb = bv[r];
+          fa = bfu[r];
+          const double fb = bfv[r];
+          t = a - fa * ((bb - a) / (fb - fa));  // first iterate: the secant point (the midpoint if it degenerates)
+          if (!(t > a && t < bb)) t = 0.5 * (a + bb);
+          it = 0;
+          have = true;
+        }
+        // value and slope in one sweep (two independent FMA chains)
+        double ft = pk[deg], dft = 0.0;
+        for (int j = deg - 1; j >= 0; --j) {
+          dft = fma(dft, t, pk1[j]);
+          ft = fma(ft, t, pk[j]);
+        }
+        bool fin = ft == 0.0;
+        double res = t;
+        if (!fin) {
+          if ((ft < 0.0) == (fa < 0.0)) {
+            a = t;
+            fa = ft;
+          } else {
+            bb = t;
+          }
+          const double width = bb - a;
+          if (!(width > fmax(tol, 4.5e-16 * fmax(fabs(a), fabs(bb))))) {
+            fin = true;
+          } else {
+            double tn = t - ft / dft;
+            if (!(tn > a && tn < bb)) tn = 0.5 * (a + bb);
+            if (!(fabs(tn - t) > tol)) {
+              fin = true;
+              res = tn;
+            } else {
+              t = tn;
+              if (++it >= kRootIters) {
+                st |= 16u;  // MTG_ST_NO_CONVERGENCE (reference: rpoly prints and returns partial roots, RPOLY_C:372-377)
+                fin = true;
+                res = t;
+              }
+            }
+          }
+        }
+        if (fin) {
+          cur[r] = res;
+          ++r;
+          have = false;
+        }
+      }
+    }
     double* tmp = prev;
     prev = cur;
     cur = tmp;
