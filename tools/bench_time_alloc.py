@@ -61,6 +61,25 @@ def main():
     secs = e0.elapsed_time(e1) / reps * 1e-3
     launches = (ctx.launch_count - n0) // reps
     evals = B * args.iters * (1 + (2 * K if central else K))
+    # the same sweep captured ONCE in a CUDA graph (the library only enqueues kernels on the caller's stream,
+    # so a whole 20-iteration sweep is capturable) and replayed: what is left is kernel time, not launch latency
+    graph_ms, graph_err, t_graph = None, None, None
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            t_graph, _ = run()
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        graph_ms = e0.elapsed_time(e1) / reps
+        if not torch.equal(t_graph, t_final):
+            graph_err = "graph replay differs from the eager sweep"
+    except Exception as exc:  # noqa: BLE001 - reported, not fatal: the eager numbers stand
+        graph_err = f"{type(exc).__name__}: {exc}"[:200]
     # open-loop parity on the last iteration's inputs
     _, hist = run(record=True)
     tl, free, fd = hist[-1]
@@ -83,6 +102,10 @@ def main():
                                   f"{'central' if central else 'forward'} differences, increment {args.inc}",
                       "cost_evaluations_per_s": evals / secs, "ms_per_sweep": secs * 1e3,
                       "ms_per_iteration": secs * 1e3 / args.iters, "gpu_launches_per_sweep": int(launches),
+                      "cuda_graph": {"ms_per_sweep": graph_ms,
+                                     "ms_per_iteration": None if graph_ms is None else graph_ms / args.iters,
+                                     "cost_evaluations_per_s": None if graph_ms is None else evals / (graph_ms * 1e-3),
+                                     "error": graph_err},
                       "mean_total_time_before": float(t0.sum(0).mean()), "mean_total_time_after": float(t_final.sum(0).mean()),
                       "open_loop_parity_vs_oracle_rel": worst,
                       "note": "parity bar vs the oracle is 1e-7 (the reference's dense d^T R d is itself ~5e-8 "
