@@ -38,44 +38,10 @@ __device__ __forceinline__ void warp_reduce(double& c, long long& i) {
 
 constexpr int kArgminBlock = 256;
 
-// stage 1: grid-stride scan -> one pair per block; stage 2 (one block): pairs (+ the running best) -> out
-__global__ void __launch_bounds__(kArgminBlock) argmin_stage_kernel(const double* __restrict__ cost,
-                                                                    const uint32_t* __restrict__ status,
-                                                                    long long n, long long offset,
-                                                                    const Best* __restrict__ partial_in, int n_partial,
-                                                                    const Best* __restrict__ running, Best* out) {
-  __shared__ double sc[kArgminBlock / 32];
-  __shared__ long long si[kArgminBlock / 32];
-  double c = INFINITY;
-  long long i = -1;
-  const long long inf_idx = 0x7fffffffffffffffLL;
-  i = inf_idx;
-  if (partial_in) {
-    for (int q = threadIdx.x; q < n_partial; q += blockDim.x) {
-      const Best b = partial_in[q];
-      if (better(b.cost, b.idx, c, i)) {
-        c = b.cost;
-        i = b.idx;
-      }
-    }
-    if (running && threadIdx.x == 0) {
-      const Best b = *running;
-      if (b.idx >= 0 && better(b.cost, b.idx, c, i)) {
-        c = b.cost;
-        i = b.idx;
-      }
-    }
-  } else {
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
-      const double v = cost[q];
-      if (status && status[q] != 0u) continue;  // failed solves never win
-      if (!(v == v)) continue;                  // NaN
-      if (better(v, offset + q, c, i)) {
-        c = v;
-        i = offset + q;
-      }
-    }
-  }
+constexpr long long kInfIdx = 0x7fffffffffffffffLL;  // "nothing yet": ordered last
+
+// block-wide reduction of (c, i); the result is valid in thread 0
+__device__ __forceinline__ void block_reduce(double& c, long long& i, double* sc, long long* si) {
   warp_reduce(c, i);
   if ((threadIdx.x & 31) == 0) {
     sc[threadIdx.x >> 5] = c;
@@ -84,15 +50,68 @@ __global__ void __launch_bounds__(kArgminBlock) argmin_stage_kernel(const double
   __syncthreads();
   if (threadIdx.x < 32) {
     c = threadIdx.x < kArgminBlock / 32 ? sc[threadIdx.x] : INFINITY;
-    i = threadIdx.x < kArgminBlock / 32 ? si[threadIdx.x] : inf_idx;
+    i = threadIdx.x < kArgminBlock / 32 ? si[threadIdx.x] : kInfIdx;
     warp_reduce(c, i);
-    if (threadIdx.x == 0) {
-      Best b;
-      b.cost = c;
-      b.idx = (i == inf_idx) ? -1 : i;
-      if (!partial_in && b.idx < 0) b.idx = inf_idx;  // keep "nothing yet" ordered last among partials
-      out[partial_in ? 0 : blockIdx.x] = b;
+  }
+  __syncthreads();
+}
+
+// ONE launch: every block scans its grid-stride share and publishes one pair; the block that draws the
+// last ticket folds the pairs (+ the running best) into out. atomicInc wraps the ticket back to zero, so
+// the counter needs no reset between launches.
+__global__ void __launch_bounds__(kArgminBlock) argmin_kernel(const double* __restrict__ cost,
+                                                              const uint32_t* __restrict__ status, long long n,
+                                                              long long offset, Best* partial, unsigned* ticket,
+                                                              const Best* __restrict__ running, Best* out) {
+  __shared__ double sc[kArgminBlock / 32];
+  __shared__ long long si[kArgminBlock / 32];
+  __shared__ bool last;
+  double c = INFINITY;
+  long long i = kInfIdx;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+    const double v = cost[q];
+    if (status && status[q] != 0u) continue;  // failed solves never win
+    if (!(v == v)) continue;                  // NaN
+    if (better(v, offset + q, c, i)) {
+      c = v;
+      i = offset + q;
     }
+  }
+  block_reduce(c, i, sc, si);
+  if (threadIdx.x == 0) {
+    Best b;
+    b.cost = c;
+    b.idx = i;
+    partial[blockIdx.x] = b;
+    __threadfence();
+    last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  c = INFINITY;
+  i = kInfIdx;
+  for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
+    const double pc = __ldcg(&partial[q].cost);  // written by other blocks: read through L2
+    const long long pi = __ldcg(&partial[q].idx);
+    if (better(pc, pi, c, i)) {
+      c = pc;
+      i = pi;
+    }
+  }
+  if (running && threadIdx.x == 0) {
+    const Best b = *running;
+    if (b.idx >= 0 && better(b.cost, b.idx, c, i)) {
+      c = b.cost;
+      i = b.idx;
+    }
+  }
+  block_reduce(c, i, sc, si);
+  if (threadIdx.x == 0) {
+    Best b;
+    b.cost = c;
+    b.idx = (i == kInfIdx) ? -1 : i;
+    *out = b;
   }
 }
 
@@ -152,13 +171,16 @@ int local_argmin(mtg_ctx* ctx, const double* cost, const uint32_t* status, long 
                  int accumulate, Best* best_dev, cudaStream_t s) {
   const int max_blocks = 4 * std::max(ctx->sm_count, 1);
   const int blocks = (int)std::max<long long>(1, std::min<long long>(max_blocks, (n + kArgminBlock - 1) / kArgminBlock));
-  DeviceBuffer* scratch = ctx->scratch_for(s);
-  if (scratch->ensure((size_t)max_blocks * sizeof(Best))) return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of the argmin scratch failed");
-  Best* partial = (Best*)scratch->ptr;
-  argmin_stage_kernel<<<blocks, kArgminBlock, 0, s>>>(cost, status, n, offset, nullptr, 0, nullptr, partial);
-  argmin_stage_kernel<<<1, kArgminBlock, 0, s>>>(nullptr, nullptr, 0, 0, partial, blocks, accumulate ? best_dev : nullptr,
-                                                best_dev);
-  ctx->launches += 2;
+  DeviceBuffer* state = ctx->argmin_state_for(s);
+  if (!state->ptr) {
+    if (state->ensure(256 + (size_t)max_blocks * sizeof(Best))) return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of the argmin state failed");
+    MTG_CUDA_TRY(cudaMemset(state->ptr, 0, 256));  // the ticket counter (first 4 bytes), once
+  }
+  unsigned* ticket = (unsigned*)state->ptr;
+  Best* partial = (Best*)((char*)state->ptr + 256);
+  argmin_kernel<<<blocks, kArgminBlock, 0, s>>>(cost, status, n, offset, partial, ticket, accumulate ? best_dev : nullptr,
+                                               best_dev);
+  ctx->launches += 1;
   MTG_CUDA_TRY(cudaGetLastError());
   return MTG_OK;
 }

@@ -57,6 +57,15 @@ struct mtg_ctx {
     stream_scratch.emplace_back(s, DeviceBuffer());
     return &stream_scratch.back().second;
   }
+  // per-stream argmin state: block partials + the ticket counter of the single-launch reduction (zeroed once;
+  // the kernel leaves it at zero). Never shared with the scratch above, which other kernels overwrite.
+  std::vector<std::pair<cudaStream_t, DeviceBuffer>> stream_argmin;
+  DeviceBuffer* argmin_state_for(cudaStream_t s) {
+    for (auto& e : stream_argmin)
+      if (e.first == s) return &e.second;
+    stream_argmin.emplace_back(s, DeviceBuffer());
+    return &stream_argmin.back().second;
+  }
   void* nccl = nullptr;             // lazily created NCCL state (argmin gather)
 };
 
