@@ -43,7 +43,7 @@ BYTES_PER_TRAJ = BYTES_IN + BYTES_OUT               # 2,752  
 FLOP_PER_TRAJ_REF = 8.8e4                           # reference formulation
 N_ROTATE = 4                                        # rotating buffer sets: 4 x 180 MB > L2 (126 MB)
 METRIC = "min-snap trajectories solved/sec (N=10, 10 seg, 3D)"
-TRAFFIC_PER_LAUNCH = 122.66e6                      # bytes: dram read 22.63 MB + write 100.03 MB (profiles/r01_solve_full.txt)
+TRAFFIC_PER_LAUNCH = 122.82e6  # dram__bytes_read.sum + dram__bytes_write.sum of one 65,536-solve launch (profiles/r01_solve_full.txt)
 SWEEP_BATCH = 1_000_000                             # BASELINE configs[3]: 1M trajectories x 1000 samples
 SWEEP_SAMPLES = 1000
 
