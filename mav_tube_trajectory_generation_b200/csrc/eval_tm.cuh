@@ -2,14 +2,17 @@
 // reference's own order — evaluateRange fills one std::vector<VectorXd> per trajectory
 // (trajectory.cpp:74-134).
 //
-// One WARP owns TPW (16 or 32) trajectories and alternates two phases over chunks of 32 samples:
+// One WARP owns TPW = 16 trajectories and alternates two phases over chunks of 32 samples:
 //
 //  phase 1  lane = trajectory. Every lane replays the reference's SERIAL sampling recurrence
 //           (acc += dt; tau += dt; tau -= T_i on a strict '>' crossing, which emits no sample) for
-//           up to 32 samples of its trajectory and parks tau (and acc, if sampling_times is wanted)
-//           in shared memory — four samples per trip while no crossing or end is near (rounding is
-//           monotone, so the fourth sample's two tests cover the other three). This is the part of
-//           the algorithm that cannot be parallelised over samples: ~4 fp64 ops per sample.
+//           up to 32 samples of its trajectory — a whole 8-sample block per trip while no crossing
+//           or end is near, then four, then one (rounding is monotone, so the last sample's two
+//           tests cover the others). The position / derivative sweeps park only tau of each block's
+//           FIRST sample (the phase-2 lane replays the block's adds: same operations, same bits); the
+//           feasibility sweeps, which are register-bound, park every tau (and acc goes to shared
+//           memory whenever sampling_times is wanted). This is the part of the algorithm that cannot
+//           be parallelised over samples: ~4 fp64 ops per sample.
 //  phase 2  4 lanes x 8 consecutive samples per trajectory, 8 trajectories per pass. A lane keeps
 //           its segment's coefficients in registers for its 8 samples (re-broadcasting them per
 //           sample costs 240 B/sample of shared-memory bandwidth: the wall an earlier lane =
@@ -29,7 +32,7 @@
 // would start (tiny segments or large dt).
 //
 // The warp is self-contained (only __syncwarp; one warp per CTA), so occupancy is set by the
-// shared memory of a warp alone: 19 kB at TPW = 16 (11 warps/SM).
+// shared memory of a warp alone: 15.9 kB for the position sweep (13 warps/SM).
 // Replaces (reference): Polynomial::evaluate polynomial.h:136-149, Segment::evaluate
 // segment.cpp:51-58, Trajectory::evaluateRange trajectory.cpp:74-134, the sampled limit check
 // test_utils.h:43-54 / NL_I:2686-2733 and the sampled form of the tube geometry
