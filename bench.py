@@ -43,7 +43,11 @@ BYTES_PER_TRAJ = BYTES_IN + BYTES_OUT               # 2,752  
 FLOP_PER_TRAJ_REF = 8.8e4                           # reference formulation
 N_ROTATE = 4                                        # rotating buffer sets: 4 x 180 MB > L2 (126 MB)
 METRIC = "min-snap trajectories solved/sec (N=10, 10 seg, 3D)"
-TRAFFIC_PER_LAUNCH = 122.82e6  # dram__bytes_read.sum + dram__bytes_write.sum of one 65,536-solve launch (profiles/r01_solve_full.txt)
+# dram__bytes_read.sum + dram__bytes_write.sum of one 65,536-solve launch: a CONSTANT from the named ncu capture
+# (ncu cannot run inside the bench), not measured in this run
+TRAFFIC_PER_LAUNCH = 122.82e6
+TRAFFIC_SOURCE = "constant from profiles/r01_solve_full.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+SOLVE_KERNEL_NAME = "solve_canonical_kernel<5,3,false>"
 SWEEP_BATCH = 1_000_000                             # BASELINE configs[3]: 1M trajectories x 1000 samples
 SWEEP_SAMPLES = 1000
 
@@ -167,7 +171,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 1024
+    sample = 32768   # >= 0.1 s of all-core work per step: the rate no longer swings with thread start-up
     from oracle import pyoracle as po
 
     pos, times = make_workload(sample, 777)
@@ -248,7 +252,63 @@ def sweep_section(ctx, peak, batch=None):
     out["extrema_v_and_a"] = {"value": 2 * K_SEG * B / secs, "unit": "root problems/s (degree 15 and 13)",
                               "ms": secs * 1e3}
     out["gpu_launches"] = int(ctx.launch_count - n0)
+    out["parity_sample"] = sweep_parity_sample(ctx, sol["coeffs"], t, p, radii, tmax, dt, Smax, samples, flags,
+                                               r["n_samples"])
     return out
+
+
+def sweep_parity_sample(ctx, coeffs, t, p, radii, tmax, dt, Smax, samples, flags, n_samples, stride=4096):
+    """Every `stride`-th trajectory of the sweep that was just timed against the oracle: sample count,
+    sampling times and segment index bit-exact (the reference's serial recurrence), sample values to
+    1e-12 of the polynomial's scale, flags identical except within 1e-9 of a limit. `samples` / `flags`
+    are the buffers the timed feasibility call filled."""
+    import torch
+
+    from oracle import pyoracle as po
+
+    idx = torch.arange(0, coeffs.shape[0], stride, device="cuda")
+    sub = lambda x: x.index_select(0, idx).contiguous()  # noqa: E731
+    c_s, t_s, p_s, r_s, tm_s, dt_s = sub(coeffs), sub(t), sub(p), sub(radii), sub(tmax), sub(dt)
+    # the subset once more with sampling times and segment indices (not outputs of the timed calls)
+    rr = ctx.eval_range_batch(c_s, t_s, 0.0, tm_s, dt_s, 0, Smax, layout="aos", want_times=True, want_segments=True)
+    full_rows = sub(samples).cpu().numpy()
+    full_flags = sub(flags).cpu().numpy()
+    full_n = sub(n_samples).cpu().numpy()
+    rows, acc, seg, n = (rr[k].cpu().numpy() for k in ("samples", "sampling_times", "segment_idx", "n_samples"))
+    ch, th, ph, rh, tmh, dth = (x.cpu().numpy() for x in (c_s, t_s, p_s, r_s, tm_s, dt_s))
+    res = {"trajectories": int(idx.numel()), "stride": stride, "count_mismatch": 0, "time_mismatch": 0,
+           "segment_mismatch": 0, "value_err_max_rel": 0.0, "flag_mismatch_away_from_limits": 0,
+           "subset_rows_bit_identical_to_full_run": True}
+    for b in range(idx.numel()):
+        ref = po.traj_evaluate_range(ch[b], th[b], 0.0, tmh[b], dth[b], 0)
+        k = ref[0].shape[0]
+        if n[b] != k or full_n[b] != k:
+            res["count_mismatch"] += 1
+            continue
+        res["time_mismatch"] += int(not np.array_equal(acc[b, :k], ref[1]))
+        res["segment_mismatch"] += int(not np.array_equal(seg[b, :k], ref[2]))
+        if not np.array_equal(rows[b, :k], full_rows[b, :k]):
+            res["subset_rows_bit_identical_to_full_run"] = False
+        scale = np.abs(ch[b]).reshape(K_SEG, DIM, NCOEF) * (th[b][:, None, None] ** np.arange(NCOEF))
+        res["value_err_max_rel"] = max(res["value_err_max_rel"],
+                                       float(np.abs(full_rows[b, :k] - ref[0]).max() / scale.sum(-1).max()))
+        f = po.feasibility_sweep(ch[b], th[b], ph[b], rh[b], 3.0, 5.0, 0.0, tmh[b], dth[b])
+        v = po.traj_evaluate_range(ch[b], th[b], 0.0, tmh[b], dth[b], 1)[0]
+        a = po.traj_evaluate_range(ch[b], th[b], 0.0, tmh[b], dth[b], 2)[0]
+        nv, na = np.sqrt((v ** 2).sum(1)), np.sqrt((a ** 2).sum(1))
+        g = po.tube_geometry(ph[b], rh[b])[ref[2]]
+        x = ref[0]
+        y = np.einsum("nij,nj->ni", g[:, :9].reshape(-1, 3, 3), x) + g[:, 9:12]
+        q = (y ** 2).sum(1)
+        al_s = -np.einsum("ni,ni->n", g[:, 12:15], x - g[:, 15:18])
+        al_e = np.einsum("ni,ni->n", g[:, 12:15], x - g[:, 18:21])
+        near = ((np.abs(nv - 3.0) < 3e-9) | (np.abs(na - 5.0) < 5e-9) | (np.abs(al_s) < 1e-9) | (np.abs(al_e) < 1e-9)
+                | (np.abs(q - g[:, 21] ** 2) < 1e-9 * np.maximum(1.0, q)))
+        res["flag_mismatch_away_from_limits"] += int(((full_flags[b, :k] != f[1]) & ~near).sum())
+    res["ok"] = (res["count_mismatch"] == 0 and res["time_mismatch"] == 0 and res["segment_mismatch"] == 0
+                 and res["value_err_max_rel"] <= 1e-12 and res["flag_mismatch_away_from_limits"] == 0
+                 and res["subset_rows_bit_identical_to_full_run"])
+    return res
 
 
 def workload_config(n_gpus):
@@ -258,6 +318,86 @@ def workload_config(n_gpus):
             "parallelism": f"batch sharded over {n_gpus} GPU(s); one 16-byte argmin all-gather per rank at the "
                            "end of the timed region",
             "l2": f"inputs+outputs rotate over {N_ROTATE} buffer sets of 180 MB (> 126 MB L2)"}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU set NVML reports as local to the GPU (its NUMA node) BEFORE any pinned
+    host buffer is allocated (first touch places the pages): with one rank per GPU the host staging of the
+    end-to-end path then stays off the inter-socket link. Best effort; returns what was done."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis and all(x.strip().isdigit() for x in vis.split(",")):
+            index = int(vis.split(",")[index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to GPU {index}"
+    except Exception as exc:  # noqa: BLE001
+        return f"unchanged ({type(exc).__name__})"
+    return "unchanged"
+
+
+def time_alloc_section(ctx):
+    """BASELINE configs[2]: segment-time allocation driven by batched finite-difference time perturbations,
+    4,096 trajectories x 20 iterations. Per iteration: one solve (d_p), the nominal + 2K central perturbed
+    costs with d_p held fixed (mtg_cost_time_fd_batch = the loop of NL_I:2495-2584), then the driver-side
+    update T <- max(0.1, T - step). Eager, then the whole sweep captured once in a CUDA graph and replayed."""
+    import torch
+
+    B, iters, inc = 4096, 20, 0.1
+    pos, times = make_workload(B, seed=3)
+    p, t0 = torch.from_numpy(pos).cuda(), torch.from_numpy(times).cuda()
+    w_d, w_t, eta = 1.0, 1.0, 0.02
+
+    def run():
+        t = t0.clone()
+        for _ in range(iters):
+            sol = ctx.solve_batch(p, t, want_free=True)
+            fd = ctx.cost_time_fd_batch(p, t, sol["free"], inc, central=True)
+            g = w_d * fd["grad"] + w_t
+            t = torch.clamp(t - eta * g / (g.abs().amax(dim=0, keepdim=True) + 1e-300) * t, min=0.1)
+        return t
+
+    run()
+    torch.cuda.synchronize()
+    n0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        t_final = run()
+    e1.record()
+    torch.cuda.synchronize()
+    eager_ms = e0.elapsed_time(e1) / reps
+    launches = (ctx.launch_count - n0) // reps
+    evals = B * iters * (1 + 2 * K_SEG)
+    out = {"workload": f"configs[2]: {B} trajectories x {iters} iterations, central differences, increment {inc}",
+           "unit": "cost evaluations/s", "eager": {"value": evals / (eager_ms * 1e-3), "ms_per_iteration": eager_ms / iters},
+           "gpu_launches_per_sweep": int(launches)}
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            t_graph = run()
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        gms = e0.elapsed_time(e1) / reps
+        out["cuda_graph"] = {"value": evals / (gms * 1e-3), "ms_per_iteration": gms / iters,
+                             "bit_identical_to_eager": bool(torch.equal(t_graph, t_final))}
+    except Exception as exc:  # noqa: BLE001 - reported, the eager number stands
+        out["cuda_graph"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    return out
 
 
 def main():
@@ -282,6 +422,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    numa = bind_to_gpu_numa_node(local_rank)   # before torch allocates pinned memory
     import torch
     import torch.distributed as dist
 
@@ -295,6 +436,13 @@ def main():
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = m.Context(local_rank)
+    comm_ok = None
+    if distributed:
+        # the product's own communicator (mtg_nccl_init): rank 0's unique id travels over the host channel
+        uid = [ctx.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.nccl_init(uid[0], rank, world)
+        comm_ok = True
     B = args.batch
 
     # ---- synthetic inputs: N_ROTATE distinct sets resident in HBM + one pinned host set
@@ -311,7 +459,8 @@ def main():
                 "cost": torch.empty((B,), dtype=torch.float64).pin_memory(),
                 "status": torch.empty((B,), dtype=torch.int32).pin_memory()}
 
-    best = torch.zeros(2, dtype=torch.int64, device="cuda")   # device pair {cost, global index}
+    best = torch.zeros(2, dtype=torch.int64, device="cuda")          # running device pair {cost, global index}
+    best_global = torch.zeros(2, dtype=torch.int64, device="cuda")   # the gathered + folded pair
     start, _ = sweep.shard_range(B * world, rank, world)
 
     def step(i, fresh=False):
@@ -329,27 +478,43 @@ def main():
             torch.cuda.synchronize()
 
     # ---- device-resident throughput (CUDA events on the launching stream)
+    # Everything with a host cost (NVML, the sampler thread, event objects) is set up on EVERY rank before the
+    # barrier, so that no rank enters the timed region late.
+    sampler = ClockSampler(local_rank)
+    ev0, ev_c, ev1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     for i in range(args.warmup):
         step(i)
-    sweep.gather_argmin(best=best)      # warm-up of the collective too (NCCL connects lazily)
+    ctx.best_allgather(best, out=best_global)   # warm-up of the collective too (NCCL connects lazily)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     n0 = ctx.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # device-side rendezvous: the timed region starts behind a collective on the launch stream, so the GPUs
+    # leave it together (the host barrier alone leaves tens of microseconds of rank-arrival skew, which a
+    # 20-step region of 1.6 ms would count as collective time)
+    ctx.best_allgather(best, out=best_global)
     ev0.record()
     for i in range(args.steps):
         step(i, fresh=(i == 0))
-    best_cost, best_idx = sweep.gather_argmin(best=best)     # the sweep's only exchange (16 B / rank)
+    ev_c.record()
+    ctx.best_allgather(best, out=best_global)   # the sweep's only exchange: mtg_best_allgather, 16 B per rank
     ev1.record()
     barrier()
-    launches = ctx.launch_count - n0
-    ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count - n0 - 1        # the rendezvous launch is outside the timed region
+    ms_total, ms_compute = ev0.elapsed_time(ev1), ev0.elapsed_time(ev_c)
+    clocks = sampler.stop()
+    best_cost, best_idx = ctx.decode_best(best_global)   # read back AFTER the timed region
     bad = int(sum(int(o["status"].max().item()) for o in dev_out))
-    ms_t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    per_rank = torch.tensor([ms_total, ms_compute], dtype=torch.float64, device="cuda")
     if distributed:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_total = float(ms_t.item())
+        allr = torch.empty((world, 2), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, per_rank)
+        # every rank must hold the same global pair
+        chk = torch.empty((world, 2), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(chk, best_global)
+        comm_ok = bool((chk == chk[0:1]).all().item())
+    else:
+        allr = per_rank[None, :]
+    allr = allr.cpu().numpy()
+    ms_total = float(allr[:, 0].max())
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
@@ -395,12 +560,22 @@ def main():
         torch.cuda.synchronize()
         kernel_s = k0.elapsed_time(k1) / reps * 1e-3
         achieved = BYTES_PER_TRAJ * B / kernel_s / 1e9
+        fp64_peak = ctx.probe_fp64_fma(reps=5)       # measured DFMA roof of this GPU (TFLOP/s)
+        ref_tflops = FLOP_PER_TRAJ_REF * B / kernel_s / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world), "gpu_launches": int(launches),
             "status_nonzero": bad, "sweep_argmin": {"cost": best_cost, "candidate": best_idx},
+            "ranks": {"ms_total": [float(x) for x in allr[:, 0]], "ms_compute": [float(x) for x in allr[:, 1]],
+                      "collective_ms": float((allr[:, 0] - allr[:, 1]).max()),
+                      "skew_ms": float(allr[:, 1].max() - allr[:, 1].min()),
+                      "collective": "mtg_best_allgather (ncclAllGather on the library's communicator + device fold)"
+                                    if distributed else "mtg_best_allgather (single rank: device fold only)",
+                      "comm_nranks_ok": comm_ok, "host_affinity": numa,
+                      "note": "GPUs enter the timed region behind a collective on the launch stream; the pair is "
+                              "read back after the region"},
             "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": BYTES_IN * B,
                     "d2h_bytes_per_step": (BYTES_OUT + 4) * B, "steps": e2e_steps,
                     "note": "mtg_solve_batch(MTG_MEM_HOST) on pinned buffers: chunked H2D/kernel/D2H "
@@ -410,24 +585,36 @@ def main():
                               "note": "same call with coeffs = NULL (cost + status only): the form a candidate sweep uses"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
-                         "kernel": "solve_canonical_kernel<5,3,false>", "kernel_ms": kernel_s * 1e3,
+                         "kernel": SOLVE_KERNEL_NAME, "kernel_ms": kernel_s * 1e3,
                          "kernel_share_of_step": kernel_s * 1e3 / ms_per_step,
                          "traffic": TRAFFIC_PER_LAUNCH if B == BATCH_PER_GPU else None,
-                         "traffic_source": "profiles/r01_solve_full.txt (ncu --set full, dram__bytes_read+write)",
+                         "traffic_source": TRAFFIC_SOURCE,
                          "algorithmic_bytes_per_trajectory": BYTES_PER_TRAJ,
-                         "fp64_gflops_reference_formulation": FLOP_PER_TRAJ_REF * B / kernel_s / 1e9},
+                         "fp64": {"peak_tflops": fp64_peak, "peak_source": "measured in this run: mtg_probe_fp64_fma "
+                                  "(register-only DFMA chains, CUDA events)",
+                                  "achieved_tflops_reference_formulation": ref_tflops,
+                                  "frac_reference_formulation": ref_tflops / fp64_peak,
+                                  "flop_per_trajectory_reference_formulation": FLOP_PER_TRAJ_REF,
+                                  "note": "8.8e4 flop is the reference's dense formulation (SURVEY 8d); the kernel "
+                                          "executes ~1.9e4 useful flop per trajectory through the closed forms, so the "
+                                          "fp64 pipe utilisation is the ncu figure in profiles/, not this ratio"}},
             "clocks": clocks,
         }
         if world == 1 and not args.no_sweep:
             line["sweep"] = sweep_section(ctx, peak, args.sweep_batch)
+            line["time_alloc"] = time_alloc_section(ctx)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = 32768
             rate, secs = cpu_port_rate(sample, threads)
+            rate1, secs1 = cpu_port_rate(4096, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "trajectories/s", "cores": threads,
                                     "kind": "port",
                                     "sample": f"{sample} solves of the same workload in {secs:.2f} s wall, "
-                                              "OpenMP over the batch (oracle port, dense QR, prints excluded)"}
+                                              "OpenMP over the batch (oracle port, dense QR, prints excluded)",
+                                    "single_thread": {"value": rate1, "cores": 1,
+                                                      "sample": f"4096 solves in {secs1:.2f} s: the reference itself "
+                                                                "is single-threaded"}}
         emit(line)
     if distributed:
         dist.destroy_process_group()

@@ -93,6 +93,11 @@ const char* mtg_last_error(const mtg_ctx* ctx);
 uint64_t mtg_launch_count(const mtg_ctx* ctx);
 int mtg_sync(mtg_ctx* ctx, void* stream);
 
+/* Measured fp64 roof of this device: a register-only DFMA micro-benchmark (8 independent chains per
+ * thread, 8 CTAs x 256 threads per SM), timed with CUDA events on `stream`. tflops = 2 x DFMA / s.
+ * (Diagnostics for the roofline report; no reference counterpart.) */
+int mtg_probe_fp64_fma(mtg_ctx* ctx, int reps, double* tflops, double* ms_per_launch, void* stream);
+
 /* Constant tables of (N, derivative): H1 = A(1)^-T Q(1) A(1)^-1 and A(1)^-1,
  * row-major N x N, computed in binary128 on the host and rounded once. These
  * replace computeQuadraticCostJacobian / setupMappingMatrix /
@@ -173,6 +178,9 @@ int mtg_coeffs_from_derivatives_batch(mtg_ctx* ctx, const mtg_problem_desc* desc
  *  J_minus   [K]   out or NULL, J_d with segment n shortened (central only)
  *  grad      [K]   out or NULL, dJ_d/dT_n: (J_plus - J_minus)/(2 inc) or (J_plus - J_nominal)/inc,
  *                  formed from the perturbed segment's own term (the other K-1 cancel exactly)
+ * status: MTG_ST_BAD_TIME also when a shortened time T[n] - increment_time is not positive (central
+ * mode, 0.1 < T[n] <= increment_time; the reference aborts in updateSegmentTimes, LIN_I:296):
+ * J_minus[n] and grad[n] are then NaN.
  * The caller applies the weights (w_d, w_t ...) of NL_I:2573. */
 int mtg_cost_time_fd_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* positions,
                            const double* end_derivatives, const double* seg_times,
@@ -196,7 +204,10 @@ int mtg_max_time_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double*
  * t_start) is replayed bit-exactly, so n_samples, sampling_times and segment_idx
  * equal the reference's; sample values use fused multiply-adds (value parity).
  *  t_start, t_end, dt [B]   per-trajectory range (the reference takes scalars per call)
- *  samples        [max_samples][D]  out or NULL   (rows >= n_samples[b] are not written)
+ *  samples        [max_samples][D]  out or NULL   (rows >= n_samples[b]: not written with device
+ *                                   pointers; UNSPECIFIED content with host pointers, where whole
+ *                                   staging records are copied back; the same holds for the other
+ *                                   per-sample outputs of this call and of mtg_feasibility_batch)
  *  sampling_times [max_samples]     out or NULL   (the reference's accumulated_time)
  *  segment_idx    [max_samples]     out or NULL
  *  n_samples      [B] int32         out or NULL
@@ -277,13 +288,20 @@ int mtg_extrema_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* 
  *
  * mtg_argmin_allgather: local argmin + ncclAllGather of the pairs over NVLink/NVSwitch +
  * final selection; returns the same (cost, index) on every rank through HOST pointers
- * (the stream is synchronised). Without an initialised communicator it is the local argmin. */
+ * (the stream is synchronised). Without an initialised communicator it is the local argmin.
+ *
+ * mtg_best_allgather: the same exchange WITHOUT a host round trip, for sweeps that keep a running
+ * best on the device (mtg_argmin_batch with accumulate): all-gathers the DEVICE pair best_local of
+ * every rank (ncclAllGather, 16 bytes per rank, enqueued on `stream`) and folds the pairs on the
+ * device into the DEVICE pair best_global — identical on every rank; nothing is synchronised, the
+ * caller reads best_global when it needs it. Without an initialised communicator: a copy. */
 int mtg_argmin_batch(mtg_ctx* ctx, const double* cost, const uint32_t* status, int64_t n,
                      int64_t global_offset, int accumulate, void* best, void* stream);
 int mtg_nccl_unique_id(mtg_ctx* ctx, uint8_t id[128]);
 int mtg_nccl_init(mtg_ctx* ctx, const uint8_t id[128], int rank, int world);
 int mtg_argmin_allgather(mtg_ctx* ctx, const double* cost, const uint32_t* status, int64_t n_local,
                          int64_t global_offset, double* best_cost, int64_t* best_idx, void* stream);
+int mtg_best_allgather(mtg_ctx* ctx, const void* best_local, void* best_global, void* stream);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,8 @@ def load() -> C.CDLL:
     lib.mtg_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
     lib.mtg_argmin_allgather.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.POINTER(C.c_double),
                                          C.POINTER(C.c_int64), vp]
+    lib.mtg_best_allgather.argtypes = [vp, vp, vp, vp]
+    lib.mtg_probe_fp64_fma.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
     lib.mtg_set_free_constraints_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, u32p, vp]
     lib.mtg_solve_generic_batch.argtypes = [vp, C.POINTER(ProblemDesc), vp, dp, dp, dp, dp, dp, u32p, vp]
     lib.mtg_coeffs_from_derivatives_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, u32p, vp]
@@ -344,6 +346,26 @@ class Context:
                                             C.byref(bc), C.byref(bi), self._stream(MTG_MEM_DEVICE, stream))
         self._check(rc, "mtg_argmin_allgather")
         return bc.value, bi.value
+
+    def best_allgather(self, best, out=None, stream=None):
+        """mtg_best_allgather: all-gather of the device pair `best` (as argmin_batch keeps it) over the
+        context's NCCL communicator and the final selection on the device, no host synchronisation;
+        returns the 2-element int64 CUDA tensor holding the global pair (decode with `decode_best`)."""
+        import torch
+
+        if out is None:
+            out = torch.zeros(2, dtype=torch.int64, device=best.device)
+        rc = self._lib.mtg_best_allgather(self._h, _ptr(best), _ptr(out), self._stream(MTG_MEM_DEVICE, stream))
+        self._check(rc, "mtg_best_allgather")
+        return out
+
+    def probe_fp64_fma(self, reps: int = 5, stream=None):
+        """Measured fp64 FMA throughput of this device in TFLOP/s (DFMA micro-benchmark)."""
+        tf, ms = C.c_double(0.0), C.c_double(0.0)
+        rc = self._lib.mtg_probe_fp64_fma(self._h, int(reps), C.byref(tf), C.byref(ms),
+                                          self._stream(MTG_MEM_DEVICE, stream))
+        self._check(rc, "mtg_probe_fp64_fma")
+        return tf.value
 
     # ------------------------------------------------------------- evaluation
     def _shape_kdn(self, coeffs, aos):

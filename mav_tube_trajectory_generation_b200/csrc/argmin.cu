@@ -115,6 +115,27 @@ __global__ void __launch_bounds__(kArgminBlock) argmin_kernel(const double* __re
   }
 }
 
+// Final selection of the sharded sweep ON THE DEVICE: folds the `world` gathered pairs into one (same
+// total order as everywhere else). One warp; the pairs were written by NCCL on this stream.
+__global__ void fold_pairs_kernel(const Best* __restrict__ pairs, int world, Best* out) {
+  double c = INFINITY;
+  long long i = kInfIdx;
+  for (int q = threadIdx.x; q < world; q += 32) {
+    const Best b = pairs[q];
+    if (b.idx >= 0 && b.idx != kInfIdx && b.cost == b.cost && better(b.cost, b.idx, c, i)) {
+      c = b.cost;
+      i = b.idx;
+    }
+  }
+  warp_reduce(c, i);
+  if (threadIdx.x == 0) {
+    Best b;
+    b.cost = c;
+    b.idx = (i == kInfIdx) ? -1 : i;
+    *out = b;
+  }
+}
+
 // ---------------------------------------------------------------- NCCL, bound at run time
 typedef struct ncclComm* ncclComm_t;
 typedef struct {
@@ -238,6 +259,25 @@ int mtg_nccl_init(mtg_ctx* ctx, const uint8_t id[128], int rank, int world) {
   api->world = world;
   if (api->gathered) cudaFree(api->gathered);
   MTG_CUDA_TRY(cudaMalloc((void**)&api->gathered, sizeof(Best) * (size_t)(world + 1)));
+  return MTG_OK;
+}
+
+int mtg_best_allgather(mtg_ctx* ctx, const void* best_local, void* best_global, void* stream_) {
+  if (!ctx) return MTG_ERR_INVALID_ARGUMENT;
+  if (!best_local || !best_global) return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "best_local and best_global are required");
+  MTG_CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream_;
+  NcclApi* api = (NcclApi*)ctx->nccl;
+  const int world = (api && api->comm) ? api->world : 1;
+  const Best* pairs = (const Best*)best_local;
+  if (world > 1) {
+    const int nrc = api->AllGather(best_local, api->gathered, sizeof(Best), kNcclChar, api->comm, s);
+    if (nrc) return nccl_fail(ctx, api, nrc, "ncclAllGather");
+    pairs = api->gathered;
+  }
+  fold_pairs_kernel<<<1, 32, 0, s>>>(pairs, world, (Best*)best_global);
+  ctx->launches += 1;
+  MTG_CUDA_TRY(cudaGetLastError());
   return MTG_OK;
 }
 

@@ -6,29 +6,59 @@
 namespace mtg {
 
 namespace {
-std::mutex g_tab_mutex;
+std::recursive_mutex g_tab_mutex;
 int g_tab_N[64];
 int g_tab_d[64];
+bool g_base_done[64];
 bool g_tab_init = false;
 std::vector<TableUploader>& uploaders() {
   static std::vector<TableUploader> v;
   return v;
 }
+std::vector<BaseUploader>& base_uploaders() {
+  static std::vector<BaseUploader> v;
+  return v;
+}
+void init_state() {
+  if (g_tab_init) return;
+  for (int i = 0; i < 64; ++i) {
+    g_tab_N[i] = g_tab_d[i] = -1;
+    g_base_done[i] = false;
+  }
+  g_tab_init = true;
+}
 }  // namespace
 
 void register_table_uploader(TableUploader f) { uploaders().push_back(f); }
+void register_base_uploader(BaseUploader f) { base_uploaders().push_back(f); }
 
-// Makes (N, derivative) the resident constant tables of this device in every
-// kernel translation unit. A switch is rare: the device is drained first so no
-// in-flight kernel sees a torn table.
-int ensure_tables(mtg_ctx* ctx, int N, int derivative) {
-  std::lock_guard<std::mutex> lock(g_tab_mutex);
-  if (!g_tab_init) {
-    for (int i = 0; i < 64; ++i) g_tab_N[i] = g_tab_d[i] = -1;
-    g_tab_init = true;
-  }
+int ensure_base(mtg_ctx* ctx) {
+  std::lock_guard<std::recursive_mutex> lock(g_tab_mutex);
+  init_state();
+  const int dev = ctx->device & 63;
+  if (g_base_done[dev]) return MTG_OK;
+  Tables t;
+  if (!compute_tables(2, 0, &t)) return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "base table");
+  DevBase h;
+  std::memcpy(h.base, t.base, sizeof(h.base));
+  for (BaseUploader f : base_uploaders()) MTG_CUDA_TRY(f(&h));
+  MTG_CUDA_TRY(cudaDeviceSynchronize());  // the copies have landed before any kernel of any stream can start
+  g_base_done[dev] = true;
+  return MTG_OK;
+}
+
+namespace {
+// Makes (N, derivative) the resident table set of this device in every kernel translation unit.
+// Called with g_tab_mutex held.
+int switch_tables(mtg_ctx* ctx, int N, int derivative, cudaStream_t stream) {
+  init_state();
   const int dev = ctx->device & 63;
   if (g_tab_N[dev] == N && g_tab_d[dev] == derivative) return MTG_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+    return fail(ctx, MTG_ERR_UNSUPPORTED,
+                "the (N, derivative) tables must be resident before stream capture: run one call with this "
+                "(N, derivative_to_optimize) outside the capture first");
   Tables t;
   if (!compute_tables(N, derivative, &t))
     return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "invalid (N, derivative_to_optimize)");
@@ -37,15 +67,25 @@ int ensure_tables(mtg_ctx* ctx, int N, int derivative) {
   std::memcpy(h.Ainv1, t.Ainv1, sizeof(h.Ainv1));
   std::memcpy(h.W, t.W, sizeof(h.W));
   std::memcpy(h.Lt, t.Lt, sizeof(h.Lt));
-  std::memcpy(h.base, t.base, sizeof(h.base));
   for (int j = 0; j < MTG_TAB_LD; ++j) h.inv_factorial[j] = 1.0 / t.base[j * MTG_BASE_LD + j];
   h.N = N;
   h.derivative = derivative;
-  MTG_CUDA_TRY(cudaDeviceSynchronize());
+  MTG_CUDA_TRY(cudaDeviceSynchronize());  // drain: no in-flight kernel sees a torn table
+  g_tab_N[dev] = g_tab_d[dev] = -1;
   for (TableUploader f : uploaders()) MTG_CUDA_TRY(f(&h));
+  MTG_CUDA_TRY(cudaDeviceSynchronize());  // landed: non-blocking streams are not ordered behind the copy
   g_tab_N[dev] = N;
   g_tab_d[dev] = derivative;
   return MTG_OK;
+}
+}  // namespace
+
+TableGuard::TableGuard(mtg_ctx* ctx, int N, int derivative, cudaStream_t stream) : rc_(MTG_OK), locked_(true) {
+  g_tab_mutex.lock();
+  rc_ = switch_tables(ctx, N, derivative, stream);
+}
+TableGuard::~TableGuard() {
+  if (locked_) g_tab_mutex.unlock();
 }
 
 void destroy_nccl_state(mtg_ctx* ctx);  // argmin.cu
@@ -89,6 +129,10 @@ int mtg_create(int device, mtg_ctx** out) {
     delete ctx;
     return MTG_ERR_CUDA;
   }
+  if (mtg::ensure_base(ctx) != MTG_OK) {
+    delete ctx;
+    return MTG_ERR_CUDA;
+  }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   for (int i = 0; i < kStageSlots; ++i)
@@ -109,6 +153,7 @@ void mtg_destroy(mtg_ctx* ctx) {
     ctx->stage[i].release();
     if (ctx->stage_stream[i]) cudaStreamDestroy(ctx->stage_stream[i]);
   }
+  if (ctx->order_event) cudaEventDestroy(ctx->order_event);
   ctx->scratch.release();
   for (auto& e : ctx->stream_scratch) e.second.release();
   for (auto& e : ctx->stream_argmin) e.second.release();

@@ -84,8 +84,8 @@ extern "C" int mtg_set_free_constraints_batch(mtg_ctx* ctx, const mtg_problem_de
     return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "free_constraints (d_p) is required when K > 1");
   if (desc->B == 0) return MTG_OK;
   MTG_CUDA_TRY(cudaSetDevice(ctx->device));
-  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
-  if (rc) return rc;
+  TableGuard tables(ctx, desc->N, desc->derivative_to_optimize, (cudaStream_t)stream_);
+  if (tables.rc()) return tables.rc();
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = desc->B, K = desc->K, D = desc->D, N = desc->N, NF = N / 2 - 1;
   const bool aos = desc->layout == MTG_LAYOUT_AOS;
@@ -165,8 +165,8 @@ extern "C" int mtg_coeffs_from_derivatives_batch(mtg_ctx* ctx, const mtg_problem
     return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "derivatives, seg_times and coeffs are required");
   if (desc->B == 0) return MTG_OK;
   MTG_CUDA_TRY(cudaSetDevice(ctx->device));
-  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
-  if (rc) return rc;
+  TableGuard tables(ctx, desc->N, desc->derivative_to_optimize, (cudaStream_t)stream_);
+  if (tables.rc()) return tables.rc();
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = desc->B, K = desc->K, D = desc->D, N = desc->N;
   const bool aos = desc->layout == MTG_LAYOUT_AOS;
@@ -208,8 +208,8 @@ extern "C" int mtg_cost_time_fd_batch(mtg_ctx* ctx, const mtg_problem_desc* desc
   if (!(increment_time > 0.0)) return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "increment_time must be > 0");
   if (desc->B == 0) return MTG_OK;
   MTG_CUDA_TRY(cudaSetDevice(ctx->device));
-  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
-  if (rc) return rc;
+  TableGuard tables(ctx, desc->N, desc->derivative_to_optimize, (cudaStream_t)stream_);
+  if (tables.rc()) return tables.rc();
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = desc->B, K = desc->K, D = desc->D, N = desc->N, NF = N / 2 - 1;
   const bool aos = desc->layout == MTG_LAYOUT_AOS;

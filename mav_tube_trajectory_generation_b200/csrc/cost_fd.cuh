@@ -149,7 +149,11 @@ __global__ void __launch_bounds__(128) cost_time_fd_kernel(const CostFdParams p)
     if (p.J_plus) p.J_plus[o] = rest + qp;
     if (p.central) {
       const double Tm = (T <= 0.1) ? 0.1 : T - delta;
-      const double qm = segment_quadratic<HN, D>(Tm, p.derivative, ds, de);
+      // 0.1 < T <= increment_time: the shortened time is not positive. The reference aborts there
+      // (updateSegmentTimes, LIN_I:296 CHECK_GT(segment_time, 0)); here the item is flagged and gets NaN.
+      const bool bad = !(Tm > 0.0);
+      if (bad) st |= 1u;
+      const double qm = bad ? nan("") : segment_quadratic<HN, D>(Tm, p.derivative, ds, de);
       if (p.J_minus) p.J_minus[o] = rest + qm;
       if (p.grad) p.grad[o] = (qp - qm) / (2.0 * delta);
     } else {
@@ -160,6 +164,7 @@ __global__ void __launch_bounds__(128) cost_time_fd_kernel(const CostFdParams p)
 #pragma unroll
       for (int m = 0; m < HN; ++m) ds[dim][m] = de[dim][m];
   }
+  if (p.status && st) p.status[b] = st;
 }
 
 // setFreeConstraints + updateSegmentsFromCompactConstraints + computeCost (LIN_I:489-498, 254-275,

@@ -2,7 +2,7 @@
 #include "host_common.h"
 #include "eval.cuh"
 
-MTG_REGISTER_TABLES()
+MTG_REGISTER_BASE()
 
 using namespace mtg;
 
@@ -102,8 +102,6 @@ int mtg_eval_range_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const doubl
     return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "coeffs, seg_times, t_start, t_end and dt are required");
   if (desc->B == 0) return MTG_OK;
   MTG_CUDA_TRY(cudaSetDevice(ctx->device));
-  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
-  if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool aos = desc->layout == MTG_LAYOUT_AOS;
   const int B = desc->B, K = desc->K, D = desc->D, N = desc->N;
@@ -147,8 +145,6 @@ int mtg_eval_at_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* 
     return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "coeffs, seg_times, t and out are required");
   if (desc->B == 0 || M == 0) return MTG_OK;
   MTG_CUDA_TRY(cudaSetDevice(ctx->device));
-  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
-  if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool aos = desc->layout == MTG_LAYOUT_AOS;
   const int B = desc->B, K = desc->K, D = desc->D, N = desc->N;
@@ -201,8 +197,6 @@ int mtg_feasibility_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const doub
     return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "the tube check needs D == 3 and the vertex positions");
   if (desc->B == 0) return MTG_OK;
   MTG_CUDA_TRY(cudaSetDevice(ctx->device));
-  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
-  if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool aos = desc->layout == MTG_LAYOUT_AOS;
   const int B = desc->B, K = desc->K, D = desc->D, N = desc->N;

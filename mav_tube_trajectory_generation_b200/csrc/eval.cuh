@@ -84,7 +84,7 @@ __device__ __forceinline__ void load_segment(const EvalParams& p, int seg, int b
         double v = 0.0;
 #pragma unroll
         for (int j = 0; j < NT; ++j)  // select raw[i + derivative] without dynamic register indexing
-          if (j == i + derivative) v = raw[j] * c_tab.base[derivative * MTG_BASE_LD + j];
+          if (j == i + derivative) v = raw[j] * c_base.base[derivative * MTG_BASE_LD + j];
         c[dim][i] = v;
       }
     }
@@ -206,9 +206,9 @@ __global__ void __launch_bounds__(256) eval_at_kernel(const EvalAtParams p) {
     double r = 0.0;
     if (!out_of_range && p.derivative < N) {
       const size_t e0 = (size_t)(i * D + dim) * N;
-      r = c_tab.base[p.derivative * MTG_BASE_LD + (N - 1)] * p.coeffs[at<AOS>(e0 + N - 1, rec_c, B, b)];
+      r = c_base.base[p.derivative * MTG_BASE_LD + (N - 1)] * p.coeffs[at<AOS>(e0 + N - 1, rec_c, B, b)];
       for (int j = N - 2; j >= p.derivative; --j)
-        r = fma(r, tau, c_tab.base[p.derivative * MTG_BASE_LD + j] * p.coeffs[at<AOS>(e0 + j, rec_c, B, b)]);
+        r = fma(r, tau, c_base.base[p.derivative * MTG_BASE_LD + j] * p.coeffs[at<AOS>(e0 + j, rec_c, B, b)]);
     }
     p.out[at<AOS>((size_t)m * D + dim, (size_t)p.M * D, B, b)] = r;  // zeros when out of range (TRAJ_C:58-61)
   }

@@ -4,7 +4,7 @@
 #include "host_common.h"
 #include "eval_tm.cuh"
 
-MTG_REGISTER_TABLES()
+MTG_REGISTER_BASE()
 
 using namespace mtg;
 

@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
               if (jj >= der) {
                 double bc[D];
 #pragma unroll
-                for (int dim = 0; dim < D; ++dim) bc[dim] = c_tab.base[der * MTG_BASE_LD + jj] * c[dim][jj];
+                for (int dim = 0; dim < D; ++dim) bc[dim] = c_base.base[der * MTG_BASE_LD + jj] * c[dim][jj];
 #pragma unroll
                 for (int j = 0; j < JB; ++j)
 #pragma unroll

@@ -2,7 +2,7 @@
 #include "host_common.h"
 #include "extrema.cuh"
 
-MTG_REGISTER_TABLES()
+MTG_REGISTER_BASE()
 
 using namespace mtg;
 
@@ -52,8 +52,6 @@ extern "C" int mtg_extrema_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, con
     return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "derivative must satisfy 0 <= derivative < N - 1");
   if (desc->B == 0) return MTG_OK;
   MTG_CUDA_TRY(cudaSetDevice(ctx->device));
-  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
-  if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool aos = desc->layout == MTG_LAYOUT_AOS;
   const int B = desc->B, K = desc->K, D = desc->D, N = desc->N;

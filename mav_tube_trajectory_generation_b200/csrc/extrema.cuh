@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) extrema_segment_kernel(const ExtremaParam
   const int nd = N - d;  // coefficients of p^(d)
   for (int dim = 0; dim < D; ++dim)
     for (int j = 0; j < MTG_TAB_LD; ++j)
-      delta[dim][j] = (j < nd) ? c_tab.base[d * MTG_BASE_LD + j + d] *
+      delta[dim][j] = (j < nd) ? c_base.base[d * MTG_BASE_LD + j + d] *
                                      p.coeffs[at<AOS>((size_t)(seg * D + dim) * N + j + d, rec_c, B, b)]
                                : 0.0;
   // g: polynomial whose real roots in [0, T] are the candidate times
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) extrema_segment_kernel(const ExtremaParam
   double* pk = ca;
   double* pk1 = cb;
   for (int j = 0; j < kMaxG; ++j) pk[j] = pk1[j] = 0.0;
-  if (n >= 1) pk[0] = c_tab.base[n * MTG_BASE_LD + n] * g[n];  // g^(n): a constant
+  if (n >= 1) pk[0] = c_base.base[n * MTG_BASE_LD + n] * g[n];  // g^(n): a constant
   for (int k = n - 1; k >= 0; --k) {
     {
       double* tmpc = pk1;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(128) extrema_segment_kernel(const ExtremaParam
       pk = tmpc;
     }
     const int deg = n - k;
-    for (int j = 0; j <= deg; ++j) pk[j] = c_tab.base[k * MTG_BASE_LD + j + k] * g[j + k];
+    for (int j = 0; j <= deg; ++j) pk[j] = c_base.base[k * MTG_BASE_LD + j + k] * g[j + k];
     int nb = 0;
     double u = lo, fu = horner_n(pk, deg, u);
     for (int q = 0; q <= na; ++q) {

@@ -67,6 +67,7 @@ struct mtg_ctx {
     return &stream_argmin.back().second;
   }
   void* nccl = nullptr;             // lazily created NCCL state (argmin gather)
+  cudaEvent_t order_event = nullptr;  // host-memory mode: orders the staging streams behind the caller's stream
 };
 
 namespace mtg {
@@ -87,10 +88,34 @@ inline int cuda_fail(mtg_ctx* ctx, cudaError_t e, const char* where) {
 
 // core.cu
 int validate_desc(mtg_ctx* ctx, const mtg_problem_desc* d);
-int ensure_tables(mtg_ctx* ctx, int N, int derivative);
-// every kernel translation unit registers the uploader of its private c_tab copy
+// The per-(N, derivative) constant tables are ONE mutable set per device. TableGuard makes a launch
+// sequence safe against that: it takes the library-wide table lock, makes (N, derivative) resident
+// (a switch drains the device first, so no in-flight kernel sees a torn table, and synchronises again
+// after the upload, so no later kernel on any stream can start before the copy has landed) and keeps
+// the lock until it is destroyed, i.e. until every kernel of the call has been ENQUEUED. Two host
+// threads using different (N, derivative) on one device therefore serialise at the switch: a kernel
+// enqueued under one table set has finished before the other set is uploaded. A switch is refused while
+// `stream` is being captured (cudaDeviceSynchronize would invalidate the capture): run one call with
+// that (N, derivative) before capturing.
+class TableGuard {
+ public:
+  TableGuard(mtg_ctx* ctx, int N, int derivative, cudaStream_t stream);
+  ~TableGuard();
+  TableGuard(const TableGuard&) = delete;
+  TableGuard& operator=(const TableGuard&) = delete;
+  int rc() const { return rc_; }
+
+ private:
+  int rc_;
+  bool locked_;
+};
+// uploads the (N, derivative)-independent base table to this device once (mtg_create)
+int ensure_base(mtg_ctx* ctx);
+// every kernel translation unit registers the uploaders of its private c_tab / c_base copies
 typedef cudaError_t (*TableUploader)(const DevTables*);
+typedef cudaError_t (*BaseUploader)(const DevBase*);
 void register_table_uploader(TableUploader f);
+void register_base_uploader(BaseUploader f);
 #define MTG_REGISTER_TABLES()                                                               \
   namespace {                                                                               \
   cudaError_t upload_tables_(const mtg::DevTables* h) {                                     \
@@ -99,6 +124,15 @@ void register_table_uploader(TableUploader f);
   struct TableRegistrar_ {                                                                  \
     TableRegistrar_() { mtg::register_table_uploader(&upload_tables_); }                    \
   } table_registrar_;                                                                       \
+  }
+#define MTG_REGISTER_BASE()                                                                 \
+  namespace {                                                                               \
+  cudaError_t upload_base_(const mtg::DevBase* h) {                                         \
+    return cudaMemcpyToSymbol(mtg::c_base, h, sizeof(mtg::DevBase));                        \
+  }                                                                                         \
+  struct BaseRegistrar_ {                                                                   \
+    BaseRegistrar_() { mtg::register_base_uploader(&upload_base_); }                        \
+  } base_registrar_;                                                                        \
   }
 
 // eval_tm.cu: time-major sweep (trajectory-contiguous sample outputs, AoS layout)
@@ -161,7 +195,10 @@ int run_chunked(mtg_ctx* ctx, cudaStream_t user_stream, size_t B, bool aos, std:
   const int slots = std::min(kStageSlots, n_chunks);
   for (int s = 0; s < slots; ++s)
     if (ctx->stage[s].ensure(slot_bytes)) return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of staging buffers failed");
-  MTG_CUDA_TRY(cudaStreamSynchronize(user_stream));  // order after work queued on the caller's stream
+  // order the staging streams after work already queued on the caller's stream (no host wait)
+  if (!ctx->order_event) MTG_CUDA_TRY(cudaEventCreateWithFlags(&ctx->order_event, cudaEventDisableTiming));
+  MTG_CUDA_TRY(cudaEventRecord(ctx->order_event, user_stream));
+  for (int s = 0; s < slots; ++s) MTG_CUDA_TRY(cudaStreamWaitEvent(ctx->stage_stream[s], ctx->order_event, 0));
   for (int c = 0; c < n_chunks; ++c) {
     const int s = c % kStageSlots;
     cudaStream_t st = ctx->stage_stream[s];

@@ -30,8 +30,8 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* po
     return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "at least one of coeffs, cost and free_constraints is required");
   if (desc->B == 0) return MTG_OK;
   MTG_CUDA_TRY(cudaSetDevice(ctx->device));
-  rc = ensure_tables(ctx, desc->N, desc->derivative_to_optimize);
-  if (rc) return rc;
+  TableGuard tables(ctx, desc->N, desc->derivative_to_optimize, (cudaStream_t)stream_);
+  if (tables.rc()) return tables.rc();
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = desc->B, K = desc->K, D = desc->D, N = desc->N, NF = N / 2 - 1;
   const bool aos = desc->layout == MTG_LAYOUT_AOS;

@@ -69,8 +69,8 @@ extern "C" int mtg_solve_generic_batch(mtg_ctx* ctx, const mtg_problem_desc* des
   for (int i = 0; i < (K + 1) * h; ++i) n_free += mask[i] ? 0 : 1;
   if (B == 0) return MTG_OK;
   MTG_CUDA_TRY(cudaSetDevice(ctx->device));
-  rc = ensure_tables(ctx, N, desc->derivative_to_optimize);
-  if (rc) return rc;
+  TableGuard tables(ctx, N, desc->derivative_to_optimize, (cudaStream_t)stream_);
+  if (tables.rc()) return tables.rc();
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool aos = desc->layout == MTG_LAYOUT_AOS;
   SolveCanonicalParams p = {};

@@ -3,9 +3,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 tools/nccl_argmin_check.py
 Every rank solves its contiguous shard of a 1M-candidate sweep (BASELINE config 5, scaled by
---total), then the global argmin is formed twice: by mtg_argmin_allgather (the library's own
-NCCL communicator, bootstrapped with a unique id that rank 0 broadcasts) and by
-sweep.gather_argmin (torch.distributed). Both must agree with each other on every rank and with
+--total), then the global argmin is formed three times: by mtg_argmin_allgather (the library's own
+NCCL communicator, bootstrapped with a unique id that rank 0 broadcasts), by mtg_best_allgather
+(the same exchange without a host round trip) and by sweep.gather_argmin (torch.distributed). All must agree with each other on every rank and with
 the argmin of the concatenated costs gathered on rank 0."""
 import argparse
 import json
@@ -47,11 +47,12 @@ def main():
     torch.cuda.synchronize()
     best = ctx.argmin_batch(sol["cost"], status=sol["status"], global_offset=start)
     c2 = sweep.gather_argmin(best=best)
+    c3 = ctx.decode_best(ctx.best_allgather(best))       # mtg_best_allgather: gather + fold on the device
     # ground truth: all costs on rank 0
     sizes = [sweep.shard_range(args.total, r, world)[1] for r in range(world)]
     parts = [torch.empty(s, dtype=torch.float64, device="cuda") for s in sizes]
     dist.all_gather(parts, sol["cost"]) if len(set(sizes)) == 1 else None
-    ok = c1 == c2
+    ok = c1 == c2 and c1 == c3
     if len(set(sizes)) == 1:
         allc = torch.cat(parts).cpu().numpy()
         want = (float(allc.min()), int(np.flatnonzero(allc == allc.min())[0]))
