@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MTG_ABI_VERSION 1
+#define MTG_ABI_VERSION 2
 
 #define MTG_OK 0
 #define MTG_ERR_INVALID_ARGUMENT (-1) /* reference: glog CHECK abort            */
@@ -269,6 +269,47 @@ int mtg_extrema_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* 
                       const double* seg_times, int derivative, double* min_value, double* min_time,
                       int32_t* min_seg, double* max_value, double* max_time, int32_t* max_seg,
                       double* seg_max_value, double* seg_max_time, uint32_t* status, void* stream);
+
+/* mtg_extrema_candidates_batch: the candidate LISTS behind the extrema — E6:
+ * Segment::computeMinMaxMagnitudeCandidateTimes / computeMinMaxMagnitudeCandidates [src/segment.cpp:82-158],
+ * i.e. what PolynomialOptimization::computeSegmentMaximumMagnitudeCandidates [LIN_I:396-417] returns,
+ * and, with D = 1 (or a one-bit dim_mask), Polynomial::computeMinMaxCandidates /
+ * selectMinMaxCandidatesFromRoots [src/polynomial.cpp:32-83] with the candidate values of
+ * selectMinMaxFromCandidates [:116-143] — for every segment of every trajectory.
+ *  t_start, t_end [K]   in or NULL: the interval per segment (NULL = 0 and the segment time)
+ *  dim_mask             bit q set = dimension q takes part (`dimensions`, segment.cpp:82-86); 0 = all
+ *  cand_time  [K][max_candidates]  out or NULL: t_start, t_end, then the real sign-changing roots of
+ *             g in [t_start, t_end] in ASCENDING order (the reference lists them in Jenkins-Traub's
+ *             order of discovery, and also keeps even-multiplicity roots, which cannot be extrema)
+ *  cand_value [K][max_candidates]  out or NULL: |p^(derivative)(t)| over the selected dimensions
+ *  n_candidates [K] int32          out or NULL: candidates of the segment (entries beyond
+ *             max_candidates are dropped and MTG_ST_TRUNCATED is set)
+ *
+ * mtg_poly_real_roots_batch: R1 root-list interface — the real roots inside [t_lo, t_hi] of B
+ * polynomials with n_coeffs coefficients each (increasing powers): findRootsJenkinsTraub
+ * [src/rpoly/rpoly_ak1.cpp:70-117] followed by the real / in-range selection of
+ * selectMinMaxCandidatesFromRoots [src/polynomial.cpp:46-60]. Leading zero coefficients are
+ * stripped like findLastNonZeroCoeff [:57-68]; a constant polynomial has no roots. Roots come
+ * out ascending; only sign-changing roots are found (see mtg_extrema_batch). coeffs [n_coeffs]
+ * records in `layout`, t_lo / t_hi [B], roots [max_roots] records, n_roots [B].
+ *
+ * mtg_soft_constraint_batch: E5 soft form — evaluateMaximumMagnitudeAsSoftConstraint
+ * [NL_I:2735-2766] on top of evaluateMaximumMagnitudeConstraint [NL_I:2686-2733]: for the
+ * constraints c = (derivatives[c], limits[c]) (HOST arrays)
+ *   violations[c][b] = max_t |p^(derivatives[c])(t)| - limits[c]          (out or NULL, [n][B])
+ *   cost[b] = sum_c min(maximum_cost, exp(violations[c][b] / limits[c] * weight))
+ * Device pointers only (it sits inside optimiser loops). */
+int mtg_extrema_candidates_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                                 const double* seg_times, const double* t_start, const double* t_end,
+                                 int derivative, int dim_mask, int max_candidates, double* cand_time,
+                                 double* cand_value, int32_t* n_candidates, uint32_t* status, void* stream);
+int mtg_poly_real_roots_batch(mtg_ctx* ctx, int B, int n_coeffs, int memory, int layout, const double* coeffs,
+                              const double* t_lo, const double* t_hi, int max_roots, double* roots,
+                              int32_t* n_roots, uint32_t* status, void* stream);
+int mtg_soft_constraint_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                              const double* seg_times, int n_constraints, const int32_t* derivatives,
+                              const double* limits, double weight, double maximum_cost, double* cost,
+                              double* violations, uint32_t* status, void* stream);
 
 /* ------------------------------------------- candidate sweep: argmin of computeCost()
  * The reference picks the best of many candidate trajectories on the host, one

@@ -68,6 +68,12 @@ def load() -> C.CDLL:
                                            dp, dp, dp, dp, u32p, vp]
     lib.mtg_extrema_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, C.c_int, dp, dp, vp, dp, dp, vp, dp, dp,
                                       u32p, vp]
+    lib.mtg_extrema_candidates_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, C.c_int, C.c_int,
+                                                 C.c_int, dp, dp, vp, u32p, vp]
+    lib.mtg_poly_real_roots_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_int, dp, vp,
+                                              u32p, vp]
+    lib.mtg_soft_constraint_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, C.c_int, vp, dp, C.c_double,
+                                              C.c_double, dp, dp, u32p, vp]
     lib.mtg_argmin_batch.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.c_int, vp, vp]
     lib.mtg_nccl_unique_id.argtypes = [vp, C.c_char_p]
     lib.mtg_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
@@ -459,6 +465,55 @@ class Context:
         self._check(rc, "mtg_extrema_batch")
         out["seg_max_value"], out["seg_max_time"] = sv, st
         return out
+
+    def extrema_candidates_batch(self, coeffs, seg_times, derivative, t_start=None, t_end=None, dim_mask=0,
+                                 max_candidates=24, layout="soa", stream=None):
+        """mtg_extrema_candidates_batch: cand_time / cand_value soa [K,MC,B] / aos [B,K,MC], n_candidates
+        soa [K,B] / aos [B,K]. t_start / t_end: per-segment records shaped like seg_times, or None."""
+        aos, B, K, D, N, mode, desc = self._desc_for(coeffs, layout)
+        MC = max_candidates
+        ct = self._empty(coeffs, (B, K, MC) if aos else (K, MC, B))
+        cv = self._empty(coeffs, (B, K, MC) if aos else (K, MC, B))
+        nc = self._empty(coeffs, (B, K) if aos else (K, B), "i4")
+        status = self._empty(coeffs, (B,), "u4")
+        rc = self._lib.mtg_extrema_candidates_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(seg_times),
+                                                    _ptr(t_start), _ptr(t_end), derivative, int(dim_mask), MC,
+                                                    _ptr(ct), _ptr(cv), _ptr(nc), _ptr(status),
+                                                    self._stream(mode, stream))
+        self._check(rc, "mtg_extrema_candidates_batch")
+        return dict(cand_time=ct, cand_value=cv, n_candidates=nc, status=status)
+
+    def poly_real_roots_batch(self, coeffs, t_lo, t_hi, max_roots=24, layout="aos", stream=None):
+        """mtg_poly_real_roots_batch: coeffs aos [B,n] / soa [n,B] (increasing powers); roots aos [B,MR] /
+        soa [MR,B] ascending, n_roots [B]."""
+        aos = layout == "aos"
+        B, n = coeffs.shape if aos else coeffs.shape[::-1]
+        mode = self._mode(coeffs)
+        lo, hi = self._bvec(coeffs, t_lo, B), self._bvec(coeffs, t_hi, B)
+        roots = self._empty(coeffs, (B, max_roots) if aos else (max_roots, B))
+        nr = self._empty(coeffs, (B,), "i4")
+        status = self._empty(coeffs, (B,), "u4")
+        rc = self._lib.mtg_poly_real_roots_batch(self._h, B, n, mode, LAYOUT_AOS if aos else LAYOUT_SOA, _ptr(coeffs),
+                                                 _ptr(lo), _ptr(hi), max_roots, _ptr(roots), _ptr(nr), _ptr(status),
+                                                 self._stream(mode, stream))
+        self._check(rc, "mtg_poly_real_roots_batch")
+        return dict(roots=roots, n_roots=nr, status=status)
+
+    def soft_constraint_batch(self, coeffs, seg_times, derivatives, limits, weight, maximum_cost, layout="soa",
+                              want_violations=True, stream=None):
+        """mtg_soft_constraint_batch (CUDA tensors): cost [B], violations [n,B]."""
+        aos, B, K, D, N, mode, desc = self._desc_for(coeffs, layout)
+        n = len(derivatives)
+        der = (C.c_int32 * max(n, 1))(*[int(x) for x in derivatives])
+        lim = (C.c_double * max(n, 1))(*[float(x) for x in limits])
+        cost = self._empty(coeffs, (B,))
+        viol = self._empty(coeffs, (n, B)) if want_violations else None
+        status = self._empty(coeffs, (B,), "u4")
+        rc = self._lib.mtg_soft_constraint_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(seg_times), n, der, lim,
+                                                 float(weight), float(maximum_cost), _ptr(cost), _ptr(viol),
+                                                 _ptr(status), self._stream(mode, stream))
+        self._check(rc, "mtg_soft_constraint_batch")
+        return dict(cost=cost, violations=viol, status=status)
 
     def feasibility_batch(self, coeffs, seg_times, t_start, t_end, dt, v_max, a_max, positions=None,
                           radii=None, max_samples=1024, layout="soa", want_samples=False, want_flags=True,

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert "mtg_solve_batch" in names and "mtg_create" in names
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/mtg_cuda.h but not exported"
-    assert lib.mtg_abi_version() == 1
+    assert lib.mtg_abi_version() == 2
 
 
 def test_library_contains_sm100a_code_only():

@@ -125,3 +125,126 @@ def test_argument_errors():
     t = dev(np.ones((1, 4)))
     with pytest.raises(m.MtgError):   # LIN_I:400-401 CHECK(N - derivative - 1 > 0)
         c.extrema_batch(coeffs, t, 9)
+
+
+# ------------------------------------------------------------------ E6 candidate lists, R1 root lists, E5 soft form
+def test_candidate_lists_vs_reference_rpoly(po):
+    """computeSegmentMaximumMagnitudeCandidates (LIN_I:396-417) = Segment::computeMinMaxMagnitudeCandidateTimes
+    (segment.cpp:82-133): [t_start, t_end, real roots in range]. The oracle's roots come from the reference's
+    own Jenkins-Traub; the lists are compared as sets on the INTERIOR segments (the rest-to-rest end segments
+    carry numerically multiple roots whose list is solver dependent): same count, same
+    times to 1e-7 T, same values to 1e-9 of the maximum."""
+    B, K = 64, 10
+    pos, times = random_problems(po, B, K, 3, seed0=9100)
+    coeffs, _ = po.solve_canonical_batch(pos, times, n_threads=8)
+    c = ctx()
+    for layout in ("soa", "aos"):
+        conv_in = soa if layout == "soa" else np.ascontiguousarray
+        conv = aos if layout == "soa" else (lambda x: x)
+        for der in (1, 2):
+            r = c.extrema_candidates_batch(dev(conv_in(coeffs)), dev(conv_in(times)), der, layout=layout)
+            ct, cv, nc = conv(host(r["cand_time"])), conv(host(r["cand_value"])), conv(host(r["n_candidates"]))
+            assert np.all(host(r["status"]) == 0)
+            ex = c.extrema_batch(dev(conv_in(coeffs)), dev(conv_in(times)), der, layout=layout, want_segments=True)
+            seg_max = conv(host(ex["seg_max_value"]))
+            n_cmp = 0
+            for b in range(B):
+                for s in range(K):
+                    n = nc[b, s]
+                    assert n >= 2 and ct[b, s, 0] == 0.0 and ct[b, s, 1] == times[b, s]
+                    assert np.all(np.diff(ct[b, s, 2:n]) > 0)                       # roots ascending
+                    assert cv[b, s, :n].max() == seg_max[b, s]                      # the list IS what the maximum is taken over
+                    vals = [np.sqrt(sum(po.poly_evaluate(coeffs[b, s, d_], t, der) ** 2 for d_ in range(3)))
+                            for t in ct[b, s, :n]]
+                    assert np.allclose(cv[b, s, :n], vals, rtol=1e-12, atol=1e-12 * seg_max[b].max())
+                    if s in (0, K - 1):
+                        continue
+                    want = po.segment_candidate_times(coeffs[b, s], der, 0.0, times[b, s])
+                    if len(want) != n:
+                        continue       # an even-multiplicity / near-real complex pair on one side only: values are checked above
+                    n_cmp += 1
+                    assert np.abs(np.sort(want[2:]) - ct[b, s, 2:n]).max(initial=0.0) <= 1e-7 * times[b, s]
+            assert n_cmp > 0.9 * B * (K - 2)
+
+
+def test_candidate_interval_and_dimension_subset(po):
+    """t_start / t_end and `dimensions` of Segment::computeMinMaxMagnitudeCandidateTimes (segment.cpp:82-133):
+    a sub-interval of every segment, all dimensions and a single one (roots of p^(d+1), :124-131)."""
+    B, K = 32, 4
+    pos, times = random_problems(po, B, K, 3, seed0=9300)
+    coeffs, _ = po.solve_canonical_batch(pos, times, n_threads=8)
+    lo, hi = 0.25 * times, 0.8 * times
+    c = ctx()
+    for mask, dims in ((0, None), (0b010, [1]), (0b101, [0, 2])):
+        r = c.extrema_candidates_batch(dev(soa(coeffs)), dev(soa(times)), 1, t_start=dev(soa(lo)), t_end=dev(soa(hi)),
+                                       dim_mask=mask)
+        ct, cv, nc = aos(host(r["cand_time"])), aos(host(r["cand_value"])), aos(host(r["n_candidates"]))
+        n_cmp = 0
+        for b in range(B):
+            for s in range(K):
+                n = nc[b, s]
+                assert ct[b, s, 0] == lo[b, s] and ct[b, s, 1] == hi[b, s]
+                assert np.all((ct[b, s, :n] >= lo[b, s]) & (ct[b, s, :n] <= hi[b, s]))
+                want = po.segment_candidate_times(coeffs[b, s], 1, lo[b, s], hi[b, s], dims=dims)
+                dd = dims if dims is not None else [0, 1, 2]
+                vals = [np.sqrt(sum(po.poly_evaluate(coeffs[b, s, d_], t, 1) ** 2 for d_ in dd)) for t in ct[b, s, :n]]
+                assert np.allclose(cv[b, s, :n], vals, rtol=1e-12, atol=1e-13)
+                if len(want) == n:
+                    n_cmp += 1
+                    assert np.abs(np.sort(want[2:]) - ct[b, s, 2:n]).max(initial=0.0) <= 1e-7 * times[b, s]
+        assert n_cmp > 0.9 * B * K
+
+
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_real_roots_vs_jenkins_traub(po, layout):
+    """findRootsJenkinsTraub (rpoly_ak1.cpp:70-117) + the real / in-range selection of polynomial.cpp:46-60 on
+    random polynomials (simple roots): same count, same roots to 1e-9, for every degree up to 21."""
+    rng = np.random.RandomState(99)
+    c = ctx()
+    for n in (2, 3, 6, 11, 16, 22):
+        B = 200
+        coeffs = rng.uniform(-1, 1, size=(B, n))
+        coeffs[::9, -1] = 0.0                                     # zero leading coefficient
+        lo, hi = rng.uniform(-3, -0.5, size=B), rng.uniform(0.5, 3, size=B)
+        cc = coeffs if layout == "aos" else soa(coeffs)
+        r = c.poly_real_roots_batch(dev(cc), dev(lo), dev(hi), layout=layout)
+        roots = host(r["roots"]) if layout == "aos" else aos(host(r["roots"]))
+        nr = host(r["n_roots"])
+        assert np.all(host(r["status"]) == 0)
+        n_ok = 0
+        for b in range(B):
+            ok, z = po.find_roots_jenkins_traub(coeffs[b])
+            want = np.sort(np.array([x.real for x in z if abs(x.imag) <= np.finfo(float).eps
+                                     and lo[b] <= x.real <= hi[b]]))
+            got = roots[b, :nr[b]]
+            if len(want) != nr[b]:
+                continue                                           # a (near-)double root: counted below
+            n_ok += 1
+            assert np.abs(got - want).max(initial=0.0) <= 1e-9 * max(1.0, np.abs(want).max(initial=0.0))
+        assert n_ok >= 0.97 * B
+    # host-memory mode and an exact root on the boundary: t^2 - 1 on [-1, 1], t (t - 0.5) on [0, 1]
+    cc = np.array([[-1.0, 0.0, 1.0], [0.0, -0.5, 1.0]])
+    r = c.poly_real_roots_batch(cc, np.array([-1.0, 0.0]), np.array([1.0, 1.0]), layout="aos")
+    assert list(r["n_roots"]) == [2, 2]
+    assert np.allclose(r["roots"][0, :2], [-1.0, 1.0], atol=1e-15) and np.allclose(r["roots"][1, :2], [0.0, 0.5], atol=1e-15)
+
+
+def test_soft_constraint(po):
+    """evaluateMaximumMagnitudeAsSoftConstraint (NL_I:2735-2766): sum over (derivative, limit) of
+    min(max_cost, exp((max - limit) / limit * weight)), max from computeMaximumOfMagnitude (LIN_I:455-487)."""
+    B = 96
+    pos, times = random_problems(po, B, 10, 3, seed0=6200)
+    coeffs, _ = po.solve_canonical_batch(pos, times, n_threads=8)
+    c = ctx()
+    ders, lims, w, cap = [1, 2], [3.0, 5.0], 100.0, 1e12
+    r = c.soft_constraint_batch(dev(soa(coeffs)), dev(soa(times)), ders, lims, w, cap)
+    cost, viol = host(r["cost"]), host(r["violations"])
+    assert np.all(host(r["status"]) == 0)
+    for b in range(B):
+        want = 0.0
+        for q, (d_, lim) in enumerate(zip(ders, lims)):
+            _, v, _ = po.opt_max_magnitude(coeffs[b], times[b], d_)
+            assert abs(viol[q, b] - (v - lim)) <= 1e-9 * v
+            want += min(cap, np.exp((v - lim) / lim * w))
+        # the exponential amplifies the 1e-9 value tolerance by weight / limit
+        assert abs(cost[b] - want) <= 1e-6 * want
