@@ -105,8 +105,8 @@ __host__ __device__ inline ExtremaPlan extrema_plan(int N, int D, int derivative
   const int need = raw ? 0 : ((D * pl.nd + 1) / 2) | 1;
   if (need > S) S = need;
   pl.S = S;
-  // doubles: 4 arrays x G x S + lo/hi[G];  ints: n, na, cnt, par, st [G], off[G + 1];  uint16 ent[G * len]
-  size_t bytes = (size_t)(4 * kExG * S + 2 * kExG) * sizeof(double) + (size_t)(5 * kExG + kExG + 1) * sizeof(int) +
+  // doubles: 4 arrays x G x S + lo/hi[G];  ints: n, na, cnt, par, st [G], off[G + 1], next;  uint16 ent[G * len]
+  size_t bytes = (size_t)(4 * kExG * S + 2 * kExG) * sizeof(double) + (size_t)(5 * kExG + kExG + 2) * sizeof(int) +
                  (size_t)kExG * pl.len * sizeof(uint16_t);
   pl.warp_bytes = (bytes + 15) & ~(size_t)15;
   pl.cta_bytes = pl.warp_bytes * kExWarps + (size_t)MTG_BASE_LD * MTG_BASE_LD * sizeof(double);
@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   int* s_par = s_cnt + G;
   int* s_st = s_par + G;
   int* s_off = s_st + G;  // G + 1
-  uint16_t* s_ent = reinterpret_cast<uint16_t*>(s_off + G + 1);
+  int* s_next = s_off + G + 1;
+  uint16_t* s_ent = reinterpret_cast<uint16_t*>(s_next + 1);
 
   const size_t Bsz = (size_t)p.B;
   const size_t rec_c = p.raw ? (size_t)N : (size_t)K * D * N;
@@ -344,51 +345,91 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
       }
       __syncwarp();
     }
-    // refine: lane = bracket
-    for (int e = lane; e < nent; e += 32) {
-      const unsigned en = s_ent[e];
-      const int q = en & 15, qi = (en >> 4) & 31, slot = (en >> 9) & 31;
-      const bool fa_neg = (en >> 14) & 1;
-      const int na = s_na[q];
-      const double* rprev = (s_par[q] ? s_rb : s_ra) + q * S;
-      double* rcur = (s_par[q] ? s_ra : s_rb) + q * S;
-      double a = qi > 0 ? rprev[qi - 1] : s_lo[q];
-      double bb = qi < na ? rprev[qi] : s_hi[q];
-      // roots of the upper levels only PARTITION the interval for the level below: 1e-12 of its length is
-      // plenty; the roots of g itself (deg = n) are refined to full precision
-      const double tol = (s_n[q] > deg) ? 1e-12 * (s_hi[q] - s_lo[q]) : 0.0;
-      const double* pk = s_pk + q * S;
-      double t = rcur[slot];
-      double res = t;
-      for (int it = 0;; ++it) {
-        // value and slope from one coefficient stream: p and p' by the coupled Horner recurrence
-        double ft = pk[deg], dft = 0.0;
+    // refine: lane = bracket. ONE flat loop whose trip is one bracketed-Newton iteration of whichever bracket
+    // the lane is working on; a lane that finishes a bracket draws the next one from a shared counter, so the
+    // warp waits for the largest SUM of iterations per lane, not for the slowest bracket of every round.
+    if (lane == 0) *s_next = 32;
+    __syncwarp();
+    {
+      int e = lane;
+      bool have = false;
+      int q = 0, slot = 0, it = 0;
+      bool fa_neg = false;
+      double a = 0.0, bb = 0.0, t = 0.0, tol = 0.0;
+      const double* pk = s_pk;
+      double* rcur = s_rb;
+      for (;;) {
+        if (!have) {
+          if (e >= nent) break;
+          const unsigned en = s_ent[e];
+          q = en & 15;
+          const int qi = (en >> 4) & 31;
+          slot = (en >> 9) & 31;
+          fa_neg = (en >> 14) & 1;
+          const int na = s_na[q];
+          const double* rprev = (s_par[q] ? s_rb : s_ra) + q * S;
+          rcur = (s_par[q] ? s_ra : s_rb) + q * S;
+          a = qi > 0 ? rprev[qi - 1] : s_lo[q];
+          bb = qi < na ? rprev[qi] : s_hi[q];
+          // roots of the upper levels only PARTITION the interval for the level below: 1e-12 of its length is
+          // plenty; the roots of g itself (deg = n) go to 1e-15 of the length (a few ulp of a mid-interval time)
+          tol = ((s_n[q] > deg) ? 1e-12 : 1e-15) * (s_hi[q] - s_lo[q]);
+          pk = s_pk + q * S;
+          t = rcur[slot];
+          it = 0;
+          have = true;
+        }
+        // value, slope and the running rounding-error bound of the value from one coefficient stream:
+        // p and p' by the coupled Horner recurrence, err = sum |c_j| |t|^j
+        double ft = pk[deg], dft = 0.0, err = fabs(ft);
+        const double at = fabs(t);
         for (int j = deg - 1; j >= 0; --j) {
+          const double c = pk[j];
           dft = fma(dft, t, ft);
-          ft = fma(ft, t, pk[j]);
+          ft = fma(ft, t, c);
+          err = fma(err, at, fabs(c));
         }
-        res = t;
-        if (ft == 0.0) break;
-        if ((ft < 0.0) == fa_neg)
-          a = t;
-        else
-          bb = t;
-        const double width = bb - a;
-        if (!(width > fmax(tol, 4.5e-16 * fmax(fabs(a), fabs(bb))))) break;
-        double tn = t - ft / dft;
-        if (!(tn > a && tn < bb)) tn = 0.5 * (a + bb);
-        if (!(fabs(tn - t) > tol)) {
-          res = tn;
-          break;
+        double res = t;
+        // |value| inside its own rounding noise: the root is located as well as fp64 can tell. (This is what
+        // ends the iteration on the numerically multiple roots of rest-to-rest ends, where Newton converges
+        // only linearly and every further digit is noise anyway.)
+        bool fin = fabs(ft) <= (double)(2 * deg + 2) * 1.1102230246251565e-16 * err;
+        if (!fin) {
+          if ((ft < 0.0) == fa_neg)
+            a = t;
+          else
+            bb = t;
+          const double width = bb - a;
+          if (!(width > fmax(tol, 4.5e-16 * fmax(fabs(a), fabs(bb))))) {
+            fin = true;
+          } else {
+            // Newton step with a cheap reciprocal (rcp.approx.f64: ~20 bits over the whole fp64 exponent range,
+            // + one Newton step: ~1e-12 relative — the step only has to land inside the bracket; anything
+            // else, incl. NaN / infinity from a vanishing slope, bisects)
+            double r;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dft));
+            r = r * fma(-dft, r, 2.0);
+            double tn = fma(-ft, r, t);
+            if (!(tn > a && tn < bb)) tn = 0.5 * (a + bb);
+            if (!(fabs(tn - t) > tol)) {
+              fin = true;
+              res = tn;
+            } else {
+              t = tn;
+              if (++it >= kRootIters) {
+                atomicOr(&s_st[q], 16);  // MTG_ST_NO_CONVERGENCE (reference: rpoly returns partial roots, RPOLY_C:372-377)
+                fin = true;
+                res = t;
+              }
+            }
+          }
         }
-        t = tn;
-        res = t;
-        if (it + 1 >= kRootIters) {
-          atomicOr(&s_st[q], 16);  // MTG_ST_NO_CONVERGENCE (reference: rpoly returns partial roots, RPOLY_C:372-377)
-          break;
+        if (fin) {
+          rcur[slot] = res;
+          have = false;
+          e = atomicAdd(s_next, 1);
         }
       }
-      rcur[slot] = res;
     }
     __syncwarp();
     // the problems of this level: current roots become the partition of the next level

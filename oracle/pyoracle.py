@@ -182,6 +182,25 @@ def solve_canonical_batch(positions, times, N=10, derivative=4, solver=0, n_thre
     return coeffs, cost
 
 
+def solve_exact128_batch(times, mask, values, N=10, derivative=4, n_threads=8):
+    """Binary128 arbiter (oracle/exact128.cpp): the reference's normal equations solved in IEEE binary128 and
+    rounded once. times [B,K], mask [K+1,h] shared, values [B,K+1,h,D] -> coeffs [B,K,D,N], cost [B], d_p [B,D,n_free]."""
+    times = _f64(times)
+    values = _f64(values)
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    B, K = times.shape
+    D = values.shape[-1]
+    n_free = int((mask == 0).sum())
+    coeffs = np.zeros((B, K, D, N))
+    cost = np.zeros(B)
+    d_p = np.zeros((B, D, max(n_free, 1)))
+    bad = lib().mtgo_solve_exact128_batch(B, N, D, K, derivative, _d(times), mask.ctypes.data_as(_u8p), _d(values),
+                                          _d(coeffs), _d(cost), _d(d_p) if n_free else None, n_free, n_threads)
+    if bad:
+        raise RuntimeError(f"{bad} problems could not be solved in binary128")
+    return coeffs, cost, d_p[:, :, :n_free]
+
+
 def canonical_mask_values(positions, N=10):
     """mask/values of the createRandomVertices pattern for given positions [K+1,D]."""
     positions = _f64(positions)

@@ -88,10 +88,14 @@ def test_patterns_vs_oracle_and_exact(po, pattern, K, D, der):
         assert errs[b] < 1e-6, (b, errs[b])              # the oracle's (= the reference's) own order is this noisy
         assert abs(cost[b] - s.cost) <= 1e-6 * s.cost
         assert np.abs(free[b] - s.d_p.reshape(D, -1)).max() <= 1e-6 * max(1.0, np.abs(s.d_p).max())
-    for b in np.argsort(errs)[-2:]:                        # arbitration by the 60-digit solve
-        ce, cost_e, dpe = exact_solve(N, der, times[b], mask, values[b])
-        assert normwise(coeffs[b], ce).max() < 1e-9, (b, normwise(coeffs[b], ce).max())
-        assert abs(cost[b] - cost_e) <= 1e-9 * abs(cost_e)
+    # the 1e-9 bar on EVERY item, against the exact (binary128) solution of the same normal equations
+    ce, cost_e, dpe = po.solve_exact128_batch(times, mask, values, N=N, derivative=der, n_threads=8)
+    assert normwise(coeffs, ce).max() < 1e-9, normwise(coeffs, ce).max()
+    assert (np.abs(cost - cost_e) / np.abs(cost_e)).max() <= 1e-9
+    assert np.abs(free - dpe).max() <= 1e-9 * max(1.0, np.abs(dpe).max())
+    b = int(np.argmax(errs))                               # and the arbiter itself against the 60-digit solve
+    cm, cost_m, _ = exact_solve(N, der, times[b], mask, values[b])
+    assert normwise(ce[b], cm).max() < 1e-15 and abs(cost_e[b] - cost_m) <= 1e-15 * abs(cost_m)
 
 
 @pytest.mark.parametrize("layout", ["soa", "aos"])

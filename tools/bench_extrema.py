@@ -15,13 +15,16 @@ for layout in ("soa", "aos"):
     p, t = torch.from_numpy(p).cuda(), torch.from_numpy(t).cuda()
     sol = ctx.solve_batch(p, t, layout=layout)
     for der in (1, 2):
-        ctx.extrema_batch(sol["coeffs"], t, der, layout=layout)
+        for _ in range(3):
+            ctx.extrema_batch(sol["coeffs"], t, der, layout=layout)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = ctx.extrema_batch(sol["coeffs"], t, der, layout=layout)
-        e1.record()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record()
+        for i in range(5):
+            r = ctx.extrema_batch(sol["coeffs"], t, der, layout=layout)
+            ev[i + 1].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        print(json.dumps({"layout": layout, "derivative": der, "batch": B, "ms": ms,
+        all_ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(5))
+        ms = all_ms[2]
+        print(json.dumps({"layout": layout, "derivative": der, "batch": B, "ms": ms, "ms_best": all_ms[0],
                           "root_problems_per_s": B * 10 / ms * 1e3, "status_nonzero": int((r["status"] != 0).sum())}))
