@@ -200,7 +200,7 @@ def run_reference(args, rank, world):
     emit(line)
 
 
-def sweep_section(ctx, peak, batch=None):
+def sweep_section(ctx, peak, batch=None, time_it=True):
     """BASELINE configs[3]: evaluateRange + fused v/a/tube feasibility sweep, S ~ 1000 samples per
     trajectory, trajectory-contiguous outputs (the reference's order), device-resident."""
     import torch
@@ -221,6 +221,11 @@ def sweep_section(ctx, peak, batch=None):
     n0 = ctx.launch_count
 
     def timed(fn, reps=7, warm=3):
+        if not time_it:   # the -m gpu parity test of this section: one launch, no statistics
+            reps, warm = 1, 0
+        return _timed(fn, reps, warm)
+
+    def _timed(fn, reps, warm):
         """`warm` untimed launches (the first launch after a different kernel runs 20-30 % slow while the SM
         clock ramps: profiles/r02_sweep_clock_probe.log), then `reps` launches timed one by one with CUDA events
         on the launch stream; returns (median s, best s, SM MHz median under load)."""

@@ -223,6 +223,22 @@ def test_oracle_vs_mpmath(po, name):
         assert np.abs(s.d_p - dp_e).max() <= tol * np.abs(dp_e).max()
 
 
+@pytest.mark.parametrize("name", ["segment_10_dim_3", "segment_50_dim_1", "accel_5_dim_3", "jerk_5_dim_3"])
+def test_binary128_arbiter_vs_mpmath(po, name):
+    """oracle/exact128.cpp (the same normal equations in IEEE binary128, rounded once) against the 60-digit
+    mpmath solve: identical to the last double digit. It is what lets the GPU tests hold EVERY item of a batch
+    to 1e-9 instead of the few that mpmath can afford."""
+    from exact_solver import exact_solve
+
+    prob = make_reference_problem(name)
+    ce, cost_e, dp_e = exact_solve(N, prob["derivative"], prob["times"], prob["mask"], prob["values"])
+    c, cost, dp = po.solve_exact128_batch(prob["times"][None], prob["mask"], prob["values"][None], N=N,
+                                          derivative=prob["derivative"], n_threads=2)
+    assert normwise_error(c[0], ce) < 1e-15
+    assert abs(cost[0] - cost_e) <= 1e-15 * abs(cost_e)
+    assert np.abs(dp[0] - dp_e).max() <= 1e-15 * np.abs(dp_e).max()
+
+
 def test_golden_fixture_is_reproduced(po):
     """The committed fixtures (tests/golden/make_golden.py) replay bit-exactly."""
     g = np.load(os.path.join(GOLD, "reference_params.npz"))

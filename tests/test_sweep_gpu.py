@@ -74,3 +74,25 @@ def test_sweep_argmin_equals_oracle(po):
     assert got_i == order[0]
     assert abs(got_c - ref_cost[order[0]]) <= 1e-9 * ref_cost[order[0]]
     assert ref_cost[order[1]] - ref_cost[order[0]] > 1e-6 * ref_cost[order[0]]   # a real winner
+
+
+def test_full_size_sweep_strided_sample_vs_oracle(po):
+    """BASELINE configs[3] at FULL size — the 1,000,000-trajectory x ~1000-sample evaluateRange + v/a/tube
+    sweep that bench.py times — with every 4096th trajectory compared against the oracle: sample count,
+    sampling times and segment index bit-exact (the reference's serial recurrence, TRAJ_C:74-134), values
+    to 1e-12 of the polynomial's scale, flags identical except within 1e-9 of a limit. The same check runs
+    inside the bench line (sweep.parity_sample)."""
+    import torch
+
+    import bench
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~35 GB of free HBM")
+    c = ctx()
+    out = bench.sweep_section(c, 6454.6, batch=1_000_000, time_it=False)
+    ps = out["parity_sample"]
+    assert ps["trajectories"] == 245 and ps["ok"], ps
+    assert ps["count_mismatch"] == 0 and ps["time_mismatch"] == 0 and ps["segment_mismatch"] == 0
+    assert ps["value_err_max_rel"] <= 1e-12 and ps["flag_mismatch_away_from_limits"] == 0
+    assert ps["subset_rows_bit_identical_to_full_run"]
