@@ -246,6 +246,30 @@ int mtg_feasibility_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const doub
                           double* max_v, double* max_a, uint8_t* feasible, int32_t* n_samples,
                           uint32_t* status, void* stream);
 
+/* --------------------------------- N2: Bezier control points and the corridor constraints on them
+ * mtg_control_points_batch: the control points of every segment — setupInverseControlPointMappingMatrix
+ * + the extraction F B_inv C [d_f; d_p] of setupControlPointConstraints
+ * [impl/polynomial_optimization_qcqp_impl.h:267-355] — and the VALUES of the reference's tube, end-cap and
+ * sphere constraints on them [:357-474] (the reference only hands their coefficients to MOSEK; here a batch
+ * of given trajectories is screened). A polynomial lies in the convex hull of its control points and the
+ * tube-and-caps region is convex, so `feasible` is a sufficient (conservative) form of the sampled
+ * predicate of mtg_feasibility_batch. Entries of B_inv in (-1e-5, 1e-5) are zeroed like the reference (:300-306).
+ *  coeffs      [K][D][N]      in or NULL  (used when derivatives is NULL: endpoint derivatives are
+ *                                          re-evaluated from the coefficients)
+ *  derivatives [K+1][N/2][D]  in or NULL  C [d_f; d_p]: the full endpoint derivatives of every vertex
+ *  positions [K+1][3], radii [K][2]  in (NULL when only control points are wanted): as mtg_feasibility_batch
+ *  control_points [K][N][D]   out or NULL
+ *  tube, cap_start, cap_end [K][N-2]  out or NULL (D = 3): |A x + b|^2 - r_tube^2, (-n).(x - p_start),
+ *                              n.(x - p_end) on control points 1..N-2; feasible <=> value <= 0
+ *  sphere [K]                 out or NULL: |x - v_{i+1}|^2 - radii[i].second^2 on the last control point;
+ *                              -infinity for the last segment (not constrained by the reference, :349-351)
+ *  max_value [B], feasible [B] uint8  out or NULL: the largest value / all values <= 0 */
+int mtg_control_points_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                             const double* derivatives, const double* seg_times, const double* positions,
+                             const double* radii, double* control_points, double* tube, double* cap_start,
+                             double* cap_end, double* sphere, double* max_value, uint8_t* feasible,
+                             uint32_t* status, void* stream);
+
 /* --------------------------------- E6 / R1: analytic extrema of |p^(derivative)(t)|
  * Trajectory::computeMinMaxMagnitude(derivative, all dimensions, &minimum, &maximum)
  * [src/trajectory.cpp:184-220] for every trajectory, with

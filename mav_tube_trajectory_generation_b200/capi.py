@@ -74,6 +74,8 @@ def load() -> C.CDLL:
                                               u32p, vp]
     lib.mtg_soft_constraint_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, C.c_int, vp, dp, C.c_double,
                                               C.c_double, dp, dp, u32p, vp]
+    lib.mtg_control_points_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp,
+                                             vp, u32p, vp]
     lib.mtg_argmin_batch.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.c_int, vp, vp]
     lib.mtg_nccl_unique_id.argtypes = [vp, C.c_char_p]
     lib.mtg_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
@@ -514,6 +516,36 @@ class Context:
                                                  _ptr(status), self._stream(mode, stream))
         self._check(rc, "mtg_soft_constraint_batch")
         return dict(cost=cost, violations=viol, status=status)
+
+    def control_points_batch(self, seg_times, coeffs=None, derivatives=None, positions=None, radii=None, N=10,
+                             layout="soa", stream=None):
+        """mtg_control_points_batch. coeffs soa [K,D,N,B] / aos [B,K,D,N] or derivatives soa [K+1,h,D,B] /
+        aos [B,K+1,h,D]. Returns control_points soa [K,N,D,B] / aos [B,K,N,D] and, with positions + radii
+        (D = 3), tube / cap_start / cap_end soa [K,N-2,B] / aos [B,K,N-2], sphere [K,B] / [B,K], max_value,
+        feasible [B]."""
+        aos = layout == "aos"
+        like = derivatives if derivatives is not None else coeffs
+        B, K = seg_times.shape if aos else seg_times.shape[::-1]
+        D = like.shape[-1] if aos and derivatives is not None else (like.shape[2] if derivatives is not None
+                                                                    else (like.shape[2] if aos else like.shape[1]))
+        mode = self._mode(like)
+        desc = ProblemDesc(B, K, D, N, N // 2 - 1, mode, LAYOUT_AOS if aos else LAYOUT_SOA)
+        cps = self._empty(like, (B, K, N, D) if aos else (K, N, D, B))
+        con = positions is not None and radii is not None
+        out = dict(control_points=cps, status=self._empty(like, (B,), "u4"))
+        tube = cs = ce = sph = mx = fe = None
+        if con:
+            tube, cs, ce = (self._empty(like, (B, K, N - 2) if aos else (K, N - 2, B)) for _ in range(3))
+            sph = self._empty(like, (B, K) if aos else (K, B))
+            mx = self._empty(like, (B,))
+            fe = self._empty(like, (B,), "u1")
+        rc = self._lib.mtg_control_points_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(derivatives),
+                                                _ptr(seg_times), _ptr(positions), _ptr(radii), _ptr(cps), _ptr(tube),
+                                                _ptr(cs), _ptr(ce), _ptr(sph), _ptr(mx), _ptr(fe),
+                                                _ptr(out["status"]), self._stream(mode, stream))
+        self._check(rc, "mtg_control_points_batch")
+        out.update(tube=tube, cap_start=cs, cap_end=ce, sphere=sph, max_value=mx, feasible=fe)
+        return out
 
     def feasibility_batch(self, coeffs, seg_times, t_start, t_end, dt, v_max, a_max, positions=None,
                           radii=None, max_samples=1024, layout="soa", want_samples=False, want_flags=True,

@@ -639,6 +639,38 @@ int tube_flags(const TubeSeg& t, const double* vertex_end, const double* x) {
   return (in_cyl && in_caps ? 1 : 0) | (in_sphere ? 2 : 0);
 }
 
+
+// ------------------------------------------------------------- N2  QC_I:267-474
+// setupInverseControlPointMappingMatrix QC_I:267-319: control_point_mapping_coefficients(l, j) =
+// n!/(n-l)! (-1)^(l+j) / T^l binom(l, j) (j <= l, n = N - 1), inverted numerically, entries in
+// (-1e-5, 1e-5) zeroed (:300-306), B_lr_inv = rows reversed, column i times (-1)^i (:308-313).
+double factorial_d(int n) {
+  double r = 1.0;
+  for (int i = 2; i <= n; ++i) r *= i;
+  return r;
+}
+double binomial_d(int n, int k) { return factorial_d(n) / (factorial_d(k) * factorial_d(n - k)); }
+
+bool inverse_control_point_mapping(int N, double T, double* B_inv) {
+  const int h = N / 2, n = N - 1;
+  Vec M(static_cast<size_t>(h) * h, 0.0), Minv(static_cast<size_t>(h) * h, 0.0);
+  M[0] = 1.0;
+  for (int l = 1; l < h; ++l)
+    for (int j = 0; j < h; ++j)
+      if (j <= l)
+        M[l * h + j] = factorial_d(n) / factorial_d(n - l) * std::pow(-1.0, l + j) / std::pow(T, l) * binomial_d(l, j);
+  if (!general_inverse(h, M.data(), Minv.data())) return false;
+  for (int k = 0; k < h; ++k)
+    for (int i = 0; i < h; ++i)
+      if (Minv[k * h + i] > -0.00001 && Minv[k * h + i] < 0.00001) Minv[k * h + i] = 0.0;
+  for (int i = 0; i < N * N; ++i) B_inv[i] = 0.0;
+  for (int k = 0; k < h; ++k)
+    for (int i = 0; i < h; ++i) {
+      B_inv[k * N + i] = Minv[k * h + i];                                              // top-left
+      B_inv[(h + k) * N + (h + i)] = Minv[(h - 1 - k) * h + i] * std::pow(-1.0, i);    // bottom-right
+    }
+  return true;
+}
 }  // namespace
 
 // =========================================================== C entry points
@@ -1050,6 +1082,86 @@ int mtgo_feasibility_sweep(int N, int K, const double* coeffs, const double* tim
   if (max_v) *max_v = mv;
   if (max_a) *max_a = ma;
   return n;
+}
+
+
+/* N2 */
+int mtgo_inverse_control_point_mapping(int N, double T, double* B_inv) {
+  return inverse_control_point_mapping(N, T, B_inv) ? 0 : -1;
+}
+
+// Control points of every segment (F B_inv C [d_f; d_p], QC_I:321-355: control point j of segment i =
+// row j of B_inv_i times the segment's endpoint derivatives) and the values of the reference's
+// constraints on them (feasible <=> value <= 0): tube x^T LL x + L x + mu on control points 1..N-2
+// (QC_I:369-429), the two end-cap half spaces on the same points (:431-474), the sphere on the last
+// control point of every segment but the last (:357-365, :349-351).
+int mtgo_control_point_constraints(int N, int K, int D, const double* derivatives, const double* times,
+                                   const double* positions, const double* radii, double* control_points,
+                                   double* tube, double* cap_start, double* cap_end, double* sphere) {
+  const int h = N / 2;
+  std::vector<TubeSeg> geom;
+  const bool constraints = positions && radii && D == 3;
+  if (constraints) { geom.resize(K); tube_geometry(K, positions, radii, geom.data()); }
+  Vec B_inv(static_cast<size_t>(N) * N), cp(static_cast<size_t>(N) * D);
+  for (int i = 0; i < K; ++i) {
+    if (!inverse_control_point_mapping(N, times[i], B_inv.data())) return -1;
+    for (int dim = 0; dim < D; ++dim)
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+        for (int c = 0; c < N; ++c) {
+          const int v = i + (c >= h ? 1 : 0), k = c % h;
+          s += B_inv[j * N + c] * derivatives[(static_cast<size_t>(v) * h + k) * D + dim];
+        }
+        cp[static_cast<size_t>(j) * D + dim] = s;
+        if (control_points) control_points[(static_cast<size_t>(i) * N + j) * D + dim] = s;
+      }
+    if (!constraints) continue;
+    const TubeSeg& t = geom[i];
+    double LL[9], L[3], mu = 0.0;  // LL = A^T A, L = 2 b^T A, mu = b^T b - r^2   (QC_I:412-415)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        double s = 0.0;
+        for (int k = 0; k < 3; ++k) s += t.A[3 * k + r] * t.A[3 * k + c];
+        LL[3 * r + c] = s;
+      }
+    for (int c = 0; c < 3; ++c) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += t.b[k] * t.A[3 * k + c];
+      L[c] = 2 * s;
+    }
+    for (int k = 0; k < 3; ++k) mu += t.b[k] * t.b[k];
+    mu -= std::pow(t.r_tube, 2);
+    for (int j = 1; j < N - 1; ++j) {
+      const double* x = &cp[static_cast<size_t>(j) * 3];
+      double q = 0.0, lin = 0.0;
+      for (int r = 0; r < 3; ++r) {
+        double s = 0.0;
+        for (int c = 0; c < 3; ++c) s += LL[3 * r + c] * x[c];
+        q += x[r] * s;
+        lin += L[r] * x[r];
+      }
+      if (tube) tube[static_cast<size_t>(i) * (N - 2) + (j - 1)] = q + lin + mu;
+      double cs = 0.0, ce = 0.0;  // norm_vec_start . x - norm_vec_start . p_start ; norm_vec_end . x - norm_vec_end . p_end
+      for (int k = 0; k < 3; ++k) {
+        cs += (-t.n[k]) * x[k] - (-t.n[k]) * t.p_start[k];
+        ce += t.n[k] * x[k] - t.n[k] * t.p_end[k];
+      }
+      if (cap_start) cap_start[static_cast<size_t>(i) * (N - 2) + (j - 1)] = cs;
+      if (cap_end) cap_end[static_cast<size_t>(i) * (N - 2) + (j - 1)] = ce;
+    }
+    if (sphere) {
+      if (i < K - 1) {
+        const double* x = &cp[static_cast<size_t>(N - 1) * 3];
+        const double* pv = positions + 3 * (i + 1);
+        double xx = 0.0, px = 0.0, pp = 0.0;  // x^T x - 2 p^T x + p^T p - r^2   (QC_I:357-365)
+        for (int k = 0; k < 3; ++k) { xx += x[k] * x[k]; px += pv[k] * x[k]; pp += pv[k] * pv[k]; }
+        sphere[i] = xx - 2 * px + pp - std::pow(t.r_sphere, 2);
+      } else {
+        sphere[i] = -std::numeric_limits<double>::infinity();
+      }
+    }
+  }
+  return 0;
 }
 
 int mtgo_has_reference_rpoly(void) {

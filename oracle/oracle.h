@@ -178,6 +178,20 @@ int mtgo_feasibility_sweep(int N, int K, const double* coeffs,
                            double* pos_out, uint8_t* flags, double* max_v,
                            double* max_a);
 
+/* N2  QC_I:267-319: inverse control-point mapping matrix of one segment (N x N, row-major):
+ * Bezier control points = B_inv [d(v_i, 0..h-1); d(v_i+1, 0..h-1)], incl. the reference's 1e-5 zeroing. */
+int mtgo_inverse_control_point_mapping(int N, double T, double* B_inv);
+/* N2  QC_I:321-474: control points [K][N][D] of a trajectory given the full endpoint derivatives of every
+ * vertex [K+1][h][D] (= C [d_f; d_p]) and, for D = 3 with positions/radii, the VALUES of the reference's
+ * constraints on them (feasible <=> value <= 0): tube / cap_start / cap_end [K][N-2] on control points
+ * 1..N-2, sphere [K] on the last control point (-inf for the last segment: not constrained there).
+ * No reference test pins these (the reference hands them to MOSEK); they are pinned here by two
+ * mathematical properties (tests/test_oracle.py): the control points reproduce the polynomial in the
+ * Bernstein basis, and control points inside the convex tube-and-caps region imply every sample inside. */
+int mtgo_control_point_constraints(int N, int K, int D, const double* derivatives, const double* times,
+                                   const double* positions, const double* radii, double* control_points,
+                                   double* tube, double* cap_start, double* cap_end, double* sphere);
+
 int mtgo_has_reference_rpoly(void);
 
 #ifdef __cplusplus

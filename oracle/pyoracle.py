@@ -411,3 +411,34 @@ def feasibility_sweep(coeffs, times, positions, radii, v_max, a_max, t_start, t_
     if n < 0:
         return None
     return pos[:n].copy(), flags[:n].copy(), mv.value, ma.value
+
+
+# ------------------------------------------------------------------ N2 control points
+def inverse_control_point_mapping(N: int, T: float) -> np.ndarray:
+    out = np.zeros((N, N))
+    if lib().mtgo_inverse_control_point_mapping(N, C.c_double(T), _d(out)):
+        raise RuntimeError("singular control-point mapping")
+    return out
+
+
+def control_point_constraints(derivatives, times, positions=None, radii=None, N=10):
+    """derivatives [K+1,h,D] -> dict(control_points [K,N,D], tube/cap_start/cap_end [K,N-2], sphere [K])."""
+    derivatives = _f64(derivatives)
+    times = _f64(times)
+    K = times.shape[0]
+    D = derivatives.shape[-1]
+    cps = np.zeros((K, N, D))
+    con = positions is not None and radii is not None and D == 3
+    tube, cs, ce, sph = np.zeros((K, N - 2)), np.zeros((K, N - 2)), np.zeros((K, N - 2)), np.zeros(K)
+    pos = _f64(positions) if con else None
+    rad = _f64(radii) if con else None
+    rc = lib().mtgo_control_point_constraints(N, K, D, _d(derivatives), _d(times), _d(pos) if con else None,
+                                              _d(rad) if con else None, _d(cps), _d(tube) if con else None,
+                                              _d(cs) if con else None, _d(ce) if con else None,
+                                              _d(sph) if con else None)
+    if rc:
+        raise RuntimeError("control_point_constraints failed")
+    out = dict(control_points=cps)
+    if con:
+        out.update(tube=tube, cap_start=cs, cap_end=ce, sphere=sph)
+    return out

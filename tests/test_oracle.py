@@ -512,3 +512,64 @@ def test_feasibility_sweep_consistency(po):
     # but every sample exactly at a vertex start is inside
     assert (flags[0] & 4) != 0
     assert not np.all(flags & 4)
+
+
+# ------------------------------------------------------------------ N2 control points (QC_I:267-474)
+def _endpoint_derivatives(po, coeffs, times):
+    K, D, _ = coeffs.shape
+    der = np.zeros((K + 1, N // 2, D))
+    for v in range(K + 1):
+        seg, t = (v, 0.0) if v < K else (K - 1, times[K - 1])
+        for k in range(N // 2):
+            for dim in range(D):
+                der[v, k, dim] = po.poly_evaluate(coeffs[seg, dim], t, k)
+    return der
+
+
+def test_control_point_mapping_closed_form_and_bernstein_identity(po):
+    """setupInverseControlPointMappingMatrix (QC_I:267-319): the numerically inverted, thresholded matrix equals
+    the closed form binom(k,i) (n-i)!/n! T^i, and the control points it yields reproduce the polynomial in the
+    Bernstein basis — the mathematical pin of the N2 restatement (no reference test covers it)."""
+    import math
+
+    n, h = N - 1, N // 2
+    for T in (0.37, 1.0, 4.3, 9.6):
+        Bi = po.inverse_control_point_mapping(N, T)
+        cf = np.array([[math.comb(k, i) * math.factorial(n - i) / math.factorial(n) * T ** i if i <= k else 0.0
+                        for i in range(h)] for k in range(h)])
+        cf[np.abs(cf) < 1e-5] = 0.0                       # QC_I:300-306
+        assert np.abs(Bi[:h, :h] - cf).max() <= 1e-12 * np.abs(cf).max()
+        assert np.all(Bi[:h, h:] == 0) and np.all(Bi[h:, :h] == 0)
+        sign = (-1.0) ** np.arange(h)
+        assert np.array_equal(Bi[h:, h:], Bi[:h, :h][::-1] * sign)        # QC_I:308-313
+    prob = make_reference_problem("segment_10_dim_3")
+    s = po.solve(N, 4, prob["times"], prob["mask"], prob["values"])
+    der = _endpoint_derivatives(po, s.coeffs, prob["times"])
+    cp = po.control_point_constraints(der, prob["times"])["control_points"]
+    for i in range(prob["K"]):
+        for u in np.linspace(0, 1, 9):
+            bern = np.array([math.comb(n, j) * u ** j * (1 - u) ** (n - j) for j in range(N)])
+            want = [po.poly_evaluate(s.coeffs[i, d], u * prob["times"][i], 0) for d in range(3)]
+            assert np.abs(bern @ cp[i] - want).max() <= 1e-9 * np.abs(s.coeffs[i, :, 0]).max()
+        assert np.allclose(cp[i, 0], prob["values"][i, 0], atol=1e-9)      # first / last control point = the vertices
+        assert np.allclose(cp[i, -1], prob["values"][i + 1, 0], atol=1e-9)
+
+
+def test_control_points_inside_imply_samples_inside(po):
+    """The link between the two restatements of QC_I:357-474 — constraints ON control points (N2) and the SAMPLED
+    predicate (T1): tube + caps convex, curve inside the hull of its control points."""
+    n_feasible = 0
+    for seed in range(40):
+        mask, values = po.create_random_vertices(4, 6, [-5.0] * 3, [5.0] * 3, 300 + seed)
+        pos = values[:, 0, :]
+        times = po.estimate_segment_times_nfabian(pos, 3.0, 5.0)
+        s = po.solve(N, 4, times, mask, values)
+        radii = np.full((6, 2), 2.0 + 0.5 * seed)
+        o = po.control_point_constraints(_endpoint_derivatives(po, s.coeffs, times), times, pos, radii)
+        if max(o["tube"].max(), o["cap_start"].max(), o["cap_end"].max()) > 0.0:
+            continue
+        n_feasible += 1
+        tmax = float(np.sum(times))
+        f = po.feasibility_sweep(s.coeffs, times, pos, radii, 3.0, 5.0, 0.0, tmax, tmax / 500)
+        assert np.all(f[1] & 4), seed
+    assert n_feasible >= 5
