@@ -246,6 +246,90 @@ int mtg_feasibility_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const doub
                           double* max_v, double* max_a, uint8_t* feasible, int32_t* n_samples,
                           uint32_t* status, void* stream);
 
+/* --------------------------------- N1: the non-linear objective over the free endpoint derivatives
+ * (device pointers only: these calls sit inside optimiser loops and only enqueue work on `stream`; the
+ *  canonical constraint pattern of mtg_solve_batch; tensors as there, free_constraints = d_p [D][K-1][N/2-1])
+ *
+ * mtg_cost_derivative_batch: getCostAndGradientDerivative [NL_I:1537-1606]:
+ *   J_d  [B]                      sum_dim [d_f; d_p]^T R [d_f; d_p]  (no 1/2)
+ *   grad [D][K-1][N/2-1]          2 R_pf d_f + 2 R_pp d_p, in the layout of free_constraints
+ *   diag [K-1][N/2-1]             the diagonal of 2 R_pp (same for every dimension; a Jacobi preconditioner)
+ * Evaluated segment by segment from H(T) = T^(1-2d) S H1 S; the reference forms the dense R (getR) per call.
+ *
+ * mtg_soft_constraint_gradient_batch: getCostAndGradientSoftConstraints [NL_I:2365-2423] (central != 0) or
+ * ...Simple [:2425-2490] (forward): J_sc = evaluateMaximumMagnitudeAsSoftConstraint [:2735-2766] of the given
+ * trajectory and its finite-difference gradient with respect to every free derivative,
+ *   grad[q] = (J_sc(d_p + inc e_q) - J_sc(d_p - inc e_q)) / (2 inc)   or   (J_sc(d_p + inc e_q) - J_sc) / inc,
+ * where the reference re-runs setFreeConstraints + rpoly over ALL segments per perturbation; here only the two
+ * segments next to the perturbed vertex are re-evaluated (2 D (K-1)(N/2-1) two-segment root problems per
+ * trajectory in one launch of the extrema kernel). coeffs [K][D][N] are the coefficients OF d_p
+ * (mtg_set_free_constraints_batch). AoS layout. constraints: HOST arrays derivatives[n], limits[n], n <= 4.
+ *
+ * mtg_nl_descent_batch: a projected-gradient driver standing in for NLOPT on
+ * objectiveFunctionFreeConstraints[AndCollision] [NL_I:1024-1284] without the collision term:
+ *   f = w_d J_d + w_sc J_sc,   d_p <- clamp(d_p - step * (w_d grad_d + w_sc grad_sc) / diag, -bound, +bound)
+ * (diag only when precondition != 0; bound[k] = |limit| of the constraint on derivative k,
+ * setFreeEndpointDerivativeHardConstraints [NL_I:2858-2905]), `iterations` times; free_constraints is updated
+ * in place, coeffs [K][D][N] receives the final coefficients, cost_history [iterations + 1][2][B] (or NULL)
+ * J_d and J_sc at every iterate (the last row is the returned point). Everything is enqueued on `stream`
+ * (capturable in a CUDA graph once the tables of (N, derivative) are resident). AoS layout. */
+int mtg_cost_derivative_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* positions,
+                              const double* end_derivatives, const double* seg_times,
+                              const double* free_constraints, double* J_d, double* grad, double* diag,
+                              uint32_t* status, void* stream);
+int mtg_soft_constraint_gradient_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                                       const double* seg_times, int n_constraints, const int32_t* derivatives,
+                                       const double* limits, double weight, double maximum_cost,
+                                       double increment, int central, double* J_sc, double* grad,
+                                       uint32_t* status, void* stream);
+int mtg_nl_descent_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* positions,
+                         const double* end_derivatives, const double* seg_times, double* free_constraints,
+                         int n_constraints, const int32_t* derivatives, const double* limits, double w_d,
+                         double w_sc, double soft_weight, double maximum_cost, double increment, double step,
+                         int precondition, int iterations, double* coeffs, double* cost_history,
+                         uint32_t* status, void* stream);
+
+/* --------------------------------- N3: batched trajectory composition and I/O
+ * mtg_vertex_at_time_batch: Trajectory::getVertexAtTime(t, max_derivative_order) [src/trajectory.cpp:248-254]
+ * (getStartVertex / getGoalVertex with t = 0 / max time, :256-262): evaluate(t, k) for k = 0..max at one
+ * time per trajectory. t [B]; out [max+1][D] records; segment_idx [B] or NULL (-1 and a zero vertex when t is
+ * out of range, MTG_ST_OUT_OF_RANGE).
+ *
+ * mtg_pick_dimensions_batch: getTrajectoryWithSingleDimension / getTrajectoryWithAppendedDimension
+ * [src/trajectory.cpp:136-182, src/segment.cpp:186-222] in one gather: output dimension q of every segment is
+ * dimension pick[q] of trajectory set a (desc.D dimensions) when pick[q] < desc.D, else dimension
+ * pick[q] - desc.D of set b (D_b dimensions; coeffs_b NULL when D_b = 0). pick: HOST array, n_out <= 8.
+ * coeffs_out [K][n_out][N] records. Segment times are shared (the reference CHECKs equal K; equal times are
+ * the caller's contract there too).
+ *
+ * mtg_concat_segments_batch: Trajectory::addTrajectories [src/trajectory.cpp:230-246] for whole batches: the
+ * K_in[q] segments of trajectory b of every input set, one set after the other, into records of
+ * sum K_in segments (coefficients and segment times). Strided DMA copies, no kernel.
+ *
+ * mtg_compute_cost_batch: PolynomialOptimization::computeCost [LIN_I:113-130] of GIVEN coefficients and
+ * segment times (0.5 sum c^T Q(T) c, derivative desc.derivative_to_optimize) — what the reference returns
+ * after updateSegmentTimes without a new solve.
+ *
+ * mtg_sample_dump_batch: the sample matrix of printMatlabSampledTrajectory [NL_I:2907-3003]: per segment
+ * `for (t = 0; t < T_i; t += dt)` (the accumulation is replayed, so the row count is the reference's), rows
+ * [t + segment start, pos(D), vel(D), acc(D), jerk(D), snap(D), tm]; rows [B][max_rows][5 D + 2], trajectory-
+ * contiguous in both layouts; rows without a sample are zero and tm of ROW i holds the end time of segment i
+ * like the reference. n_rows [B] or NULL; MTG_ST_TRUNCATED when max_rows is too small. */
+int mtg_vertex_at_time_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                             const double* seg_times, const double* t, int max_derivative_order, double* out,
+                             int32_t* segment_idx, uint32_t* status, void* stream);
+int mtg_pick_dimensions_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs_a, int D_b,
+                              const double* coeffs_b, int n_out, const int32_t* pick, double* coeffs_out,
+                              void* stream);
+int mtg_concat_segments_batch(mtg_ctx* ctx, int B, int D, int N, int memory, int layout, int n_inputs,
+                              const int32_t* K_in, const double* const* coeffs_in, const double* const* times_in,
+                              double* coeffs_out, double* times_out, void* stream);
+int mtg_compute_cost_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                           const double* seg_times, double* cost, uint32_t* status, void* stream);
+int mtg_sample_dump_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                          const double* seg_times, double dt, int max_rows, double* rows, int32_t* n_rows,
+                          uint32_t* status, void* stream);
+
 /* --------------------------------- N2: Bezier control points and the corridor constraints on them
  * mtg_control_points_batch: the control points of every segment — setupInverseControlPointMappingMatrix
  * + the extraction F B_inv C [d_f; d_p] of setupControlPointConstraints

@@ -76,6 +76,18 @@ def load() -> C.CDLL:
                                               C.c_double, dp, dp, u32p, vp]
     lib.mtg_control_points_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp,
                                              vp, u32p, vp]
+    lib.mtg_vertex_at_time_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, C.c_int, dp, vp, u32p, vp]
+    lib.mtg_pick_dimensions_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, C.c_int, dp, C.c_int, vp, dp, vp]
+    lib.mtg_concat_segments_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,
+                                              dp, dp, vp]
+    lib.mtg_compute_cost_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, u32p, vp]
+    lib.mtg_sample_dump_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, C.c_double, C.c_int, dp, vp, u32p, vp]
+    lib.mtg_cost_derivative_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, dp, u32p, vp]
+    lib.mtg_soft_constraint_gradient_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, C.c_int, vp, dp, C.c_double,
+                                                       C.c_double, C.c_double, C.c_int, dp, dp, u32p, vp]
+    lib.mtg_nl_descent_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, C.c_int, vp, dp, C.c_double,
+                                         C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                         dp, dp, u32p, vp]
     lib.mtg_argmin_batch.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.c_int, vp, vp]
     lib.mtg_nccl_unique_id.argtypes = [vp, C.c_char_p]
     lib.mtg_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
@@ -546,6 +558,138 @@ class Context:
         self._check(rc, "mtg_control_points_batch")
         out.update(tube=tube, cap_start=cs, cap_end=ce, sphere=sph, max_value=mx, feasible=fe)
         return out
+
+    # ------------------------------------------------------------- non-linear objective (N1), CUDA tensors
+    def cost_derivative_batch(self, positions, seg_times, free, end_derivatives=None, N=10, derivative=4,
+                              layout="soa", want_diag=False, stream=None):
+        """mtg_cost_derivative_batch: J_d [B], grad shaped like `free`, diag soa [K-1,NF,B] / aos [B,K-1,NF]."""
+        aos = layout == "aos"
+        if aos:
+            B, Kp1, D = positions.shape
+        else:
+            Kp1, D, B = positions.shape
+        K = Kp1 - 1
+        desc = ProblemDesc(B, K, D, N, derivative, MTG_MEM_DEVICE, LAYOUT_AOS if aos else LAYOUT_SOA)
+        J = self._empty(positions, (B,))
+        grad = self._empty(positions, tuple(free.shape))
+        NF = N // 2 - 1
+        diag = self._empty(positions, (B, K - 1, NF) if aos else (K - 1, NF, B)) if want_diag else None
+        status = self._empty(positions, (B,), "u4")
+        rc = self._lib.mtg_cost_derivative_batch(self._h, C.byref(desc), _ptr(positions), _ptr(end_derivatives),
+                                                 _ptr(seg_times), _ptr(free), _ptr(J), _ptr(grad), _ptr(diag),
+                                                 _ptr(status), self._stream(MTG_MEM_DEVICE, stream))
+        self._check(rc, "mtg_cost_derivative_batch")
+        return dict(J_d=J, grad=grad, diag=diag, status=status)
+
+    def soft_constraint_gradient_batch(self, coeffs, seg_times, derivatives, limits, weight, maximum_cost, increment,
+                                       central=True, want_grad=True, stream=None):
+        """mtg_soft_constraint_gradient_batch (AoS): J_sc [B], grad [B, D, K-1, NF]."""
+        aos, B, K, D, N, mode, desc = self._desc_for(coeffs, "aos")
+        n = len(derivatives)
+        der = (C.c_int32 * n)(*[int(x) for x in derivatives])
+        lim = (C.c_double * n)(*[float(x) for x in limits])
+        J = self._empty(coeffs, (B,))
+        grad = self._empty(coeffs, (B, D, K - 1, N // 2 - 1)) if want_grad else None
+        status = self._empty(coeffs, (B,), "u4")
+        rc = self._lib.mtg_soft_constraint_gradient_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(seg_times), n, der,
+                                                          lim, float(weight), float(maximum_cost), float(increment),
+                                                          1 if central else 0, _ptr(J), _ptr(grad), _ptr(status),
+                                                          self._stream(mode, stream))
+        self._check(rc, "mtg_soft_constraint_gradient_batch")
+        return dict(J_sc=J, grad=grad, status=status)
+
+    def nl_descent_batch(self, positions, seg_times, free, derivatives=(), limits=(), w_d=1.0, w_sc=1.0,
+                         soft_weight=100.0, maximum_cost=1e12, increment=0.05, step=0.5, precondition=True,
+                         iterations=10, end_derivatives=None, N=10, derivative=4, want_history=True, stream=None):
+        """mtg_nl_descent_batch (AoS): updates `free` in place; returns coeffs [B,K,D,N], history [it+1,2,B]."""
+        B, Kp1, D = positions.shape
+        K = Kp1 - 1
+        desc = ProblemDesc(B, K, D, N, derivative, MTG_MEM_DEVICE, LAYOUT_AOS)
+        n = len(derivatives)
+        der = (C.c_int32 * max(n, 1))(*[int(x) for x in derivatives])
+        lim = (C.c_double * max(n, 1))(*[float(x) for x in limits])
+        coeffs = self._empty(positions, (B, K, D, N))
+        hist = self._empty(positions, (iterations + 1, 2, B)) if want_history else None
+        status = self._empty(positions, (B,), "u4")
+        rc = self._lib.mtg_nl_descent_batch(self._h, C.byref(desc), _ptr(positions), _ptr(end_derivatives),
+                                            _ptr(seg_times), _ptr(free), n, der, lim, float(w_d), float(w_sc),
+                                            float(soft_weight), float(maximum_cost), float(increment), float(step),
+                                            1 if precondition else 0, int(iterations), _ptr(coeffs), _ptr(hist),
+                                            _ptr(status), self._stream(MTG_MEM_DEVICE, stream))
+        self._check(rc, "mtg_nl_descent_batch")
+        return dict(coeffs=coeffs, history=hist, free=free, status=status)
+
+    # ------------------------------------------------------------- composition / I/O (N3)
+    def vertex_at_time_batch(self, coeffs, seg_times, t, max_derivative_order, layout="soa", stream=None):
+        """mtg_vertex_at_time_batch: out soa [M+1,D,B] / aos [B,M+1,D], segment_idx [B]."""
+        aos, B, K, D, N, mode, desc = self._desc_for(coeffs, layout)
+        M = int(max_derivative_order)
+        tv = self._bvec(coeffs, t, B)
+        out = self._empty(coeffs, (B, M + 1, D) if aos else (M + 1, D, B))
+        seg = self._empty(coeffs, (B,), "i4")
+        status = self._empty(coeffs, (B,), "u4")
+        rc = self._lib.mtg_vertex_at_time_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(seg_times), _ptr(tv), M,
+                                                _ptr(out), _ptr(seg), _ptr(status), self._stream(mode, stream))
+        self._check(rc, "mtg_vertex_at_time_batch")
+        return dict(out=out, segment_idx=seg, status=status)
+
+    def pick_dimensions_batch(self, coeffs_a, pick, coeffs_b=None, layout="soa", stream=None):
+        """mtg_pick_dimensions_batch: output dimension q = dimension pick[q] of a (< D_a) or pick[q] - D_a of b."""
+        aos, B, K, D, N, mode, desc = self._desc_for(coeffs_a, layout)
+        Db = 0 if coeffs_b is None else (coeffs_b.shape[2] if aos else coeffs_b.shape[1])
+        n_out = len(pick)
+        arr = (C.c_int32 * n_out)(*[int(x) for x in pick])
+        out = self._empty(coeffs_a, (B, K, n_out, N) if aos else (K, n_out, N, B))
+        rc = self._lib.mtg_pick_dimensions_batch(self._h, C.byref(desc), _ptr(coeffs_a), Db, _ptr(coeffs_b), n_out, arr,
+                                                 _ptr(out), self._stream(mode, stream))
+        self._check(rc, "mtg_pick_dimensions_batch")
+        return out
+
+    def concat_segments_batch(self, coeffs_list, times_list, layout="soa", stream=None):
+        """mtg_concat_segments_batch: addTrajectories over whole batches -> (coeffs, seg_times)."""
+        aos = layout == "aos"
+        first = coeffs_list[0]
+        if aos:
+            B, _, D, N = first.shape
+            Ks = [c.shape[1] for c in coeffs_list]
+        else:
+            _, D, N, B = first.shape
+            Ks = [c.shape[0] for c in coeffs_list]
+        mode = self._mode(first)
+        Kt = sum(Ks)
+        oc = self._empty(first, (B, Kt, D, N) if aos else (Kt, D, N, B))
+        ot = self._empty(first, (B, Kt) if aos else (Kt, B))
+        n = len(coeffs_list)
+        karr = (C.c_int32 * n)(*Ks)
+        carr = (C.c_void_p * n)(*[_ptr(c) for c in coeffs_list])
+        tarr = (C.c_void_p * n)(*[_ptr(t) for t in times_list])
+        rc = self._lib.mtg_concat_segments_batch(self._h, B, D, N, mode, LAYOUT_AOS if aos else LAYOUT_SOA, n, karr,
+                                                 carr, tarr, _ptr(oc), _ptr(ot), self._stream(mode, stream))
+        self._check(rc, "mtg_concat_segments_batch")
+        return oc, ot
+
+    def compute_cost_batch(self, coeffs, seg_times, derivative=4, layout="soa", stream=None):
+        """mtg_compute_cost_batch: computeCost (LIN_I:113-130) of given coefficients."""
+        aos, B, K, D, N, mode, _ = self._desc_for(coeffs, layout)
+        desc = ProblemDesc(B, K, D, N, derivative, mode, LAYOUT_AOS if aos else LAYOUT_SOA)
+        cost = self._empty(coeffs, (B,))
+        status = self._empty(coeffs, (B,), "u4")
+        rc = self._lib.mtg_compute_cost_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(seg_times), _ptr(cost),
+                                              _ptr(status), self._stream(mode, stream))
+        self._check(rc, "mtg_compute_cost_batch")
+        return dict(cost=cost, status=status)
+
+    def sample_dump_batch(self, coeffs, seg_times, dt, max_rows, layout="soa", stream=None):
+        """mtg_sample_dump_batch: rows [B, max_rows, 5 D + 2], n_rows [B]."""
+        aos, B, K, D, N, mode, desc = self._desc_for(coeffs, layout)
+        rows = self._empty(coeffs, (B, max_rows, 5 * D + 2))
+        n = self._empty(coeffs, (B,), "i4")
+        status = self._empty(coeffs, (B,), "u4")
+        rc = self._lib.mtg_sample_dump_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(seg_times), float(dt),
+                                             int(max_rows), _ptr(rows), _ptr(n), _ptr(status),
+                                             self._stream(mode, stream))
+        self._check(rc, "mtg_sample_dump_batch")
+        return dict(rows=rows, n_rows=n, status=status)
 
     def feasibility_batch(self, coeffs, seg_times, t_start, t_end, dt, v_max, a_max, positions=None,
                           radii=None, max_samples=1024, layout="soa", want_samples=False, want_flags=True,

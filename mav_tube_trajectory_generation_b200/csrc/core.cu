@@ -157,6 +157,7 @@ void mtg_destroy(mtg_ctx* ctx) {
   ctx->scratch.release();
   for (auto& e : ctx->stream_scratch) e.second.release();
   for (auto& e : ctx->stream_argmin) e.second.release();
+  for (auto& e : ctx->stream_nl) e.second.release();
   delete ctx;
 }
 

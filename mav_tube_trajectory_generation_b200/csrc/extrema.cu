@@ -9,6 +9,10 @@ using namespace mtg;
 namespace {
 constexpr int kExtremaChunk = 1 << 18;  // trajectories per launch pair (bounds the scratch: 36 B x K each)
 
+}  // namespace
+
+namespace mtg {
+// also used by nl_objective.cu (soft-constraint gradient)
 int launch_extrema(mtg_ctx* ctx, bool aos, const ExtremaParams& p_in, cudaStream_t s) {
   ExtremaParams p = p_in;
   const ExtremaPlan pl = extrema_plan(p.N, p.D, p.derivative, p.dim_mask, p.raw);
@@ -49,7 +53,9 @@ int launch_extrema(mtg_ctx* ctx, bool aos, const ExtremaParams& p_in, cudaStream
   }
   return MTG_OK;
 }
+}  // namespace mtg
 
+namespace {
 int validate_extrema(mtg_ctx* ctx, const mtg_problem_desc* desc, int derivative) {
   // LIN_I:400-401 CHECK(N - derivative - 1 > 0)
   if (derivative < 0 || desc->N - derivative - 1 <= 0)

@@ -113,6 +113,12 @@ __host__ __device__ inline ExtremaPlan extrema_plan(int N, int D, int derivative
   return pl;
 }
 
+}  // namespace mtg
+struct mtg_ctx;
+namespace mtg {
+// extrema.cu: chunked launch of extrema_warp_kernel (+ extrema_reduce_kernel when per-trajectory outputs are wanted)
+int launch_extrema(mtg_ctx* ctx, bool aos, const ExtremaParams& p, cudaStream_t s);
+
 __device__ __forceinline__ unsigned lanes_lt(int lane) { return (1u << lane) - 1u; }
 
 template <bool AOS>
@@ -191,24 +197,37 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   // In raw mode the record is the polynomial itself.
   auto stage_delta = [&](double* dst, int sd) {
     const int n_el = np * rec_one;
+    // element e = lane + 32 k walks memory in order; (q, r) follow it with counters (no division per element)
+    int q = AOS ? lane / rec_one : 0, r = AOS ? lane - q * rec_one : lane / np;
+    int qs = AOS ? 0 : lane - r * np;  // SoA: problem within the row of 16
     for (int e = lane; e < n_el; e += 32) {
-      int q, r;
-      if (AOS) {
-        q = e / rec_one;
-        r = e - q * rec_one;
-      } else {
-        r = e / np;
-        q = e - r * np;
-      }
-      const int b = p.b0 + prob_local(q), seg = prob_seg(q);
+      const int qq = AOS ? q : qs;
+      const int b = p.b0 + prob_local(qq), seg = prob_seg(qq);
       if (p.raw) {
-        dst[q * sd + r] = p.coeffs[at<AOS>((size_t)r, rec_c, Bsz, (size_t)b)];
+        dst[qq * sd + r] = p.coeffs[at<AOS>((size_t)r, rec_c, Bsz, (size_t)b)];
       } else {
-        const int dim = r / N, jj = r - dim * N;
-        if (jj < d) continue;
-        const double c = p.coeffs[at<AOS>((size_t)(seg * D + dim) * N + jj, rec_c, Bsz, (size_t)b)];
-        const double v = ((p.dim_mask >> dim) & 1) ? s_base[d * MTG_BASE_LD + jj] * c : 0.0;
-        dst[q * sd + dim * nd + (jj - d)] = v;
+        int dim = 0, jj = r;
+        while (jj >= N) {
+          jj -= N;
+          ++dim;
+        }
+        if (jj >= d) {
+          const double c = p.coeffs[at<AOS>((size_t)(seg * D + dim) * N + jj, rec_c, Bsz, (size_t)b)];
+          dst[qq * sd + dim * nd + (jj - d)] = ((p.dim_mask >> dim) & 1) ? s_base[d * MTG_BASE_LD + jj] * c : 0.0;
+        }
+      }
+      if (AOS) {
+        r += 32;
+        while (r >= rec_one) {
+          r -= rec_one;
+          ++q;
+        }
+      } else {
+        qs += 32;
+        while (qs >= np) {
+          qs -= np;
+          ++r;
+        }
       }
     }
   };
@@ -219,22 +238,30 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
     const int sd = p.raw ? N : D * nd;
     stage_delta(s_delta, sd);
     __syncwarp();
-    for (int e = lane; e < np * len; e += 32) {
-      const int q = e / len, m = e - q * len;
+    // lane = (problem q, coefficient m = 2 k + half): 16 problems x 2 lanes, conflict-free odd strides
+    const int q = lane & 15;
+    if (q < np) {
       const double* dl = s_delta + q * sd;
-      double acc = 0.0;
-      if (p.raw) {
-        acc = dl[m];
-      } else if (pl.ndim > 1) {
-        // sum_dim conv(delta, delta'), delta'[j] = (j+1) delta[j+1]   (segment.cpp:93-115)
-        const int i0 = max(0, m - (nd - 2)), i1 = min(m, nd - 1);
-        for (int dim = 0; dim < D; ++dim)
-          for (int i = i0; i <= i1; ++i) acc = fma(dl[dim * nd + i], (double)(m - i + 1) * dl[dim * nd + m - i + 1], acc);
-      } else {
-        // one dimension: roots of p^(d+1)   (segment.cpp:124-131); the other dimensions are staged as zeros
-        for (int dim = 0; dim < D; ++dim) acc += (double)(m + 1) * dl[dim * nd + m + 1];
+      for (int m = lane >> 4; m < len; m += 2) {
+        double acc = 0.0;
+        if (p.raw) {
+          acc = dl[m];
+        } else if (pl.ndim > 1) {
+          // sum_dim conv(delta, delta'), delta'[j] = (j+1) delta[j+1]   (segment.cpp:93-115)
+          const int i0 = max(0, m - (nd - 2)), i1 = min(m, nd - 1);
+          for (int dim = 0; dim < D; ++dim) {
+            double f = (double)(m - i0 + 1);
+            for (int i = i0; i <= i1; ++i) {
+              acc = fma(dl[dim * nd + i], f * dl[dim * nd + m - i + 1], acc);
+              f -= 1.0;
+            }
+          }
+        } else {
+          // one dimension: roots of p^(d+1)   (segment.cpp:124-131); the other dimensions are staged as zeros
+          for (int dim = 0; dim < D; ++dim) acc += (double)(m + 1) * dl[dim * nd + m + 1];
+        }
+        s_g[q * S + m] = acc;
       }
-      s_g[q * S + m] = acc;
     }
     __syncwarp();
   }
@@ -256,10 +283,15 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   // ---- the derivative chain, level by level: deg = degree of the level polynomial g^(n - deg)
   for (int deg = 1; deg <= nmax; ++deg) {
     // build: pk[q][j] = B(k, j + k) g[q][j + k], k = n_q - deg, for the problems still in the chain
-    for (int e = lane; e < np * (deg + 1); e += 32) {
-      const int q = e / (deg + 1), j = e - q * (deg + 1);
-      const int k = s_n[q] - deg;
-      if (k >= 0) s_pk[q * S + j] = s_base[k * MTG_BASE_LD + j + k] * s_g[q * S + j + k];
+    {
+      const int q = lane & 15;  // lane = (problem, coefficient parity)
+      const int k = q < np ? s_n[q] - deg : -1;
+      if (k >= 0) {
+        const double* bk = s_base + k * MTG_BASE_LD + k;
+        const double* gk = s_g + q * S + k;
+        double* pq = s_pk + q * S;
+        for (int j = lane >> 4; j <= deg; j += 2) pq[j] = bk[j] * gk[j];
+      }
     }
     // pieces of the partition per problem (exclusive prefix over the problems)
     {
@@ -355,7 +387,7 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
       bool have = false;
       int q = 0, slot = 0, it = 0;
       bool fa_neg = false;
-      double a = 0.0, bb = 0.0, t = 0.0, tol = 0.0;
+      double a = 0.0, bb = 0.0, t = 0.0, tol = 0.0, wmin = 0.0;
       const double* pk = s_pk;
       double* rcur = s_rb;
       for (;;) {
@@ -374,6 +406,8 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
           // roots of the upper levels only PARTITION the interval for the level below: 1e-12 of its length is
           // plenty; the roots of g itself (deg = n) go to 1e-15 of the length (a few ulp of a mid-interval time)
           tol = ((s_n[q] > deg) ? 1e-12 : 1e-15) * (s_hi[q] - s_lo[q]);
+          // bracket narrower than tol or than fp64 can resolve anywhere in the interval
+          wmin = fmax(tol, 4.5e-16 * fmax(fabs(s_lo[q]), fabs(s_hi[q])));
           pk = s_pk + q * S;
           t = rcur[slot];
           it = 0;
@@ -400,7 +434,7 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
           else
             bb = t;
           const double width = bb - a;
-          if (!(width > fmax(tol, 4.5e-16 * fmax(fabs(a), fabs(bb))))) {
+          if (!(width > wmin)) {
             fin = true;
           } else {
             // Newton step with a cheap reciprocal (rcp.approx.f64: ~20 bits over the whole fp64 exponent range,

@@ -66,6 +66,14 @@ struct mtg_ctx {
     stream_argmin.emplace_back(s, DeviceBuffer());
     return &stream_argmin.back().second;
   }
+  // per-stream work space of the non-linear objective (perturbed segments, nominal maxima, gradients)
+  std::vector<std::pair<std::pair<cudaStream_t, int>, DeviceBuffer>> stream_nl;
+  DeviceBuffer* nl_scratch_for(cudaStream_t s, int slot) {
+    for (auto& e : stream_nl)
+      if (e.first.first == s && e.first.second == slot) return &e.second;
+    stream_nl.emplace_back(std::make_pair(s, slot), DeviceBuffer());
+    return &stream_nl.back().second;
+  }
   void* nccl = nullptr;             // lazily created NCCL state (argmin gather)
   cudaEvent_t order_event = nullptr;  // host-memory mode: orders the staging streams behind the caller's stream
 };

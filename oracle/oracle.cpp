@@ -1164,6 +1164,109 @@ int mtgo_control_point_constraints(int N, int K, int D, const double* derivative
   return 0;
 }
 
+// N3  NL_I:2907-3003 printMatlabSampledTrajectory as a matrix: rows [t, pos(D), vel(D), acc(D), jerk(D),
+// snap(D), tm]; per segment `for (t = 0; t < T_i; t += dt)`, values as T_seg^T (derivative matrix) p with
+// T_seg[n] = pow(t, n) and the super-diagonal derivative matrices of NL_I:2820-2846; rows without a sample
+// stay zero; output(i, 1 + 5 D) = end time of segment i. Returns the number of sample rows (j).
+int mtgo_sample_dump(int N, int D, int K, const double* coeffs, const double* times, double dt, int max_rows,
+                     double* rows) {
+  const int W = 5 * D + 2;
+  for (size_t e = 0; e < static_cast<size_t>(max_rows) * W; ++e) rows[e] = 0.0;
+  int j = 0;
+  double current_segment_time = 0.0;
+  for (int i = 0; i < K; ++i) {
+    for (double t = 0.0; t < times[i]; t += dt) {
+      if (j < max_rows) {
+        double* r = rows + static_cast<size_t>(j) * W;
+        r[0] = t + current_segment_time;
+        for (int k = 0; k < D; ++k) {
+          const double* p = coeffs + (static_cast<size_t>(i) * D + k) * N;
+          for (int der = 0; der < 5; ++der) {
+            double v = 0.0;  // sum_n pow(t, n) * (n+1)...(n+der) * p[n + der]
+            for (int n = 0; n + der < N; ++n) {
+              double f = 1.0;
+              for (int q = 1; q <= der; ++q) f *= (n + q);
+              v += std::pow(t, n) * (f * p[n + der]);
+            }
+            r[1 + der * D + k] = v;
+          }
+        }
+        ++j;
+      }
+    }
+    current_segment_time += times[i];
+    if (i < max_rows) rows[static_cast<size_t>(i) * W + (W - 1)] = current_segment_time;
+  }
+  return j;
+}
+
+// N1  NL_I:1537-1606 getCostAndGradientDerivative: J_d and grad_{d_p} = 2 R_pf d_f + 2 R_pp d_p from the dense R
+int mtgo_cost_gradient_derivative(int N, int D, int K, int derivative, const double* times, const uint8_t* mask,
+                                  const double* values, const double* d_p, double* J_d, double* grad) {
+  Problem p;
+  int rc = setup_problem(p, N, D, K, derivative, times, mask, values);
+  if (rc) return rc;
+  p.d_p.assign(d_p, d_p + static_cast<size_t>(D) * p.n_free);
+  if (J_d) *J_d = cost_derivative(p);
+  Vec R;
+  construct_R(p, &R);
+  const int nf = p.n_fixed, np = p.n_free, n = nf + np;
+  for (int dim = 0; dim < D; ++dim)
+    for (int r = 0; r < np; ++r) {
+      double s1 = 0.0, s2 = 0.0;  // (2 d_f^T R_pf^T)_r + (2 d_p^T R_pp)_r
+      for (int c = 0; c < nf; ++c) s1 += p.d_f[static_cast<size_t>(dim) * nf + c] * R[static_cast<size_t>(nf + r) * n + c];
+      for (int c = 0; c < np; ++c) s2 += p.d_p[static_cast<size_t>(dim) * np + c] * R[static_cast<size_t>(nf + c) * n + nf + r];
+      grad[static_cast<size_t>(dim) * np + r] = 2 * s1 + 2 * s2;
+    }
+  return 0;
+}
+
+// N1  NL_I:2735-2766 + 2365-2490: the soft-constraint cost of the trajectory with free derivatives d_p and its
+// finite-difference gradient (central: (cost(d_p + e) - cost(d_p - e)) / (2 inc); forward: (cost(d_p + e) - J_sc) / inc),
+// each evaluation = setFreeConstraints + computeMaximumOfMagnitude (LIN_I:455-487) per constraint.
+double soft_constraint_cost(Problem& p, const double* d_p, int n_con, const int* ders, const double* limits,
+                            double weight, double max_cost, Vec& coeffs) {
+  p.d_p.assign(d_p, d_p + static_cast<size_t>(p.D) * p.n_free);
+  update_segments_from_compact(p, coeffs.data());
+  double cost = 0.0;
+  for (int c = 0; c < n_con; ++c) {
+    double t = 0.0, v = 0.0;
+    int sidx = 0;
+    mtgo_opt_max_magnitude(p.N, p.D, p.K, coeffs.data(), p.times, ders[c], &t, &v, &sidx);
+    const double rel = (v - limits[c]) / limits[c];
+    cost += std::min(max_cost, std::exp(rel * weight));
+  }
+  return cost;
+}
+
+int mtgo_soft_constraint_gradient(int N, int D, int K, int derivative, const double* times, const uint8_t* mask,
+                                  const double* values, const double* d_p, int n_con, const int* ders,
+                                  const double* limits, double weight, double max_cost, double increment,
+                                  int central, double* J_sc, double* grad) {
+  Problem p;
+  int rc = setup_problem(p, N, D, K, derivative, times, mask, values);
+  if (rc) return rc;
+  Vec coeffs(static_cast<size_t>(K) * D * N);
+  const size_t nv = static_cast<size_t>(D) * p.n_free;
+  Vec x(d_p, d_p + nv);
+  const double J = soft_constraint_cost(p, x.data(), n_con, ders, limits, weight, max_cost, coeffs);
+  if (J_sc) *J_sc = J;
+  if (!grad) return 0;
+  for (size_t q = 0; q < nv; ++q) {
+    const double keep = x[q];
+    x[q] = keep + increment;
+    const double right = soft_constraint_cost(p, x.data(), n_con, ders, limits, weight, max_cost, coeffs);
+    double left = J;
+    if (central) {
+      x[q] = keep - increment;
+      left = soft_constraint_cost(p, x.data(), n_con, ders, limits, weight, max_cost, coeffs);
+    }
+    x[q] = keep;
+    grad[q] = central ? (right - left) / (2.0 * increment) : (right - J) / increment;
+  }
+  return 0;
+}
+
 int mtgo_has_reference_rpoly(void) {
 #ifdef MTG_ORACLE_NO_RPOLY
   return 0;

@@ -192,6 +192,19 @@ int mtgo_control_point_constraints(int N, int K, int D, const double* derivative
                                    const double* positions, const double* radii, double* control_points,
                                    double* tube, double* cap_start, double* cap_end, double* sphere);
 
+/* N1  NL_I:1537-1606: J_d (no 1/2) and grad_{d_p} = 2 R_pf d_f + 2 R_pp d_p [D][n_free] from the dense R. */
+int mtgo_cost_gradient_derivative(int N, int D, int K, int derivative, const double* times, const uint8_t* mask,
+                                  const double* values, const double* d_p, double* J_d, double* grad);
+/* N1  NL_I:2735-2766, 2365-2490: soft-constraint cost and its finite-difference gradient wrt d_p [D][n_free]. */
+int mtgo_soft_constraint_gradient(int N, int D, int K, int derivative, const double* times, const uint8_t* mask,
+                                  const double* values, const double* d_p, int n_con, const int* ders,
+                                  const double* limits, double weight, double max_cost, double increment,
+                                  int central, double* J_sc, double* grad);
+
+/* N3  NL_I:2907-3003: the sampled dump [t, pos, vel, acc, jerk, snap, tm] as a max_rows x (5 D + 2) matrix. */
+int mtgo_sample_dump(int N, int D, int K, const double* coeffs, const double* times, double dt, int max_rows,
+                     double* rows);
+
 int mtgo_has_reference_rpoly(void);
 
 #ifdef __cplusplus

@@ -442,3 +442,56 @@ def control_point_constraints(derivatives, times, positions=None, radii=None, N=
     if con:
         out.update(tube=tube, cap_start=cs, cap_end=ce, sphere=sph)
     return out
+
+
+# ------------------------------------------------------------------ N3 composition / dump
+def vertex_at_time(coeffs, times, t, max_derivative_order):
+    """Trajectory::getVertexAtTime (TRAJ_C:248-254): evaluate(t, k) for k = 0..max -> [max+1, D]."""
+    return np.stack([traj_evaluate(coeffs, times, t, k)[0] for k in range(max_derivative_order + 1)])
+
+
+def sample_dump(coeffs, times, dt, max_rows):
+    coeffs = _f64(coeffs)
+    times = _f64(times)
+    K, D, N = coeffs.shape
+    rows = np.zeros((max_rows, 5 * D + 2))
+    n = lib().mtgo_sample_dump(N, D, K, _d(coeffs), _d(times), C.c_double(dt), max_rows, _d(rows))
+    return rows, n
+
+
+# ------------------------------------------------------------------ N1 non-linear objective
+def cost_gradient_derivative(N, derivative, times, mask, values, d_p):
+    """NL_I:1537-1606 -> (J_d, grad [D, n_free])."""
+    times = _f64(times)
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    values = _f64(values)
+    d_p = _f64(d_p)
+    D = values.shape[2]
+    J = C.c_double(0.0)
+    g = np.zeros(d_p.size)
+    rc = lib().mtgo_cost_gradient_derivative(N, D, times.size, derivative, _d(times), mask.ctypes.data_as(_u8p),
+                                             _d(values), _d(d_p), C.byref(J), _d(g))
+    if rc:
+        raise ValueError(rc)
+    return J.value, g.reshape(D, -1)
+
+
+def soft_constraint_gradient(N, derivative, times, mask, values, d_p, ders, limits, weight, max_cost, increment,
+                             central=True, want_grad=True):
+    """NL_I:2735-2766, 2365-2490 -> (J_sc, grad [D, n_free] or None)."""
+    times = _f64(times)
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    values = _f64(values)
+    d_p = _f64(d_p)
+    D = values.shape[2]
+    J = C.c_double(0.0)
+    g = np.zeros(d_p.size)
+    da = np.ascontiguousarray(ders, dtype=np.int32)
+    la = _f64(limits)
+    rc = lib().mtgo_soft_constraint_gradient(N, D, times.size, derivative, _d(times), mask.ctypes.data_as(_u8p),
+                                             _d(values), _d(d_p), len(da), da.ctypes.data_as(_ip), _d(la),
+                                             C.c_double(weight), C.c_double(max_cost), C.c_double(increment),
+                                             1 if central else 0, C.byref(J), _d(g) if want_grad else None)
+    if rc:
+        raise ValueError(rc)
+    return J.value, (g.reshape(D, -1) if want_grad else None)

@@ -95,8 +95,8 @@ def test_control_points_inside_imply_every_sample_inside(po):
     pos = np.repeat(pos, B // 64, axis=0) + rng.normal(0, 0.2, size=(B, K + 1, 3))
     times = np.repeat(times, B // 64, axis=0) * rng.uniform(0.9, 1.3, size=(B, K))
     radii = np.empty((B, K, 2))
-    radii[..., 0] = rng.uniform(0.5, 12.0, size=(B, 1))       # tube radius: from tight to generous
-    radii[..., 1] = rng.uniform(0.5, 12.0, size=(B, 1))       # cap / sphere radius
+    radii[..., 0] = rng.uniform(0.5, 25.0, size=(B, 1))       # tube radius: from tight to generous
+    radii[..., 1] = rng.uniform(0.5, 25.0, size=(B, 1))       # cap / sphere radius
     c = ctx()
     p, t, rd = dev(soa(pos)), dev(soa(times)), dev(soa(radii))
     sol = c.solve_batch(p, t)
@@ -106,7 +106,7 @@ def test_control_points_inside_imply_every_sample_inside(po):
     sw = c.feasibility_batch(sol["coeffs"], t, 0.0, tm, tm / 1000, 3.0, 5.0, positions=p, radii=rd, max_samples=1010)
     flags, n = aos(host(sw["flags"])), host(sw["n_samples"])
     all_in = np.array([np.all(flags[b, :n[b]] & 4) for b in range(B)])
-    assert tube_ok.sum() > B // 10 and (~tube_ok).sum() > B // 10
+    assert tube_ok.sum() > B // 20 and (~tube_ok).sum() > B // 20
     assert np.all(all_in[tube_ok]), np.flatnonzero(tube_ok & ~all_in)[:5]
     assert (~all_in).sum() > 0          # the sampled predicate does reject somewhere
     # the oracle's sampled predicate agrees on a subset (it is the checker of the flags elsewhere)
