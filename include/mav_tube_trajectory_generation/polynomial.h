@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <limits>
+#include <utility>
 #include <vector>
 
 #include "linalg_lite.h"
@@ -86,6 +87,60 @@ class Polynomial {
       (*coeffs)[j] = baseCoefficient(derivative, j) * tp;
       tp *= t;
     }
+  }
+
+  // Real roots of the derivative-th derivative inside [t_start, t_end], ascending — the part of getRoots
+  // (findRootsJenkinsTraub, src/polynomial.cpp:28-30) that the library consumes (only real, in-range,
+  // sign-changing roots; see mtg_poly_real_roots_batch).
+  bool getRealRoots(int derivative, double t_start, double t_end, std::vector<double>* roots) const {
+    MTG_SHIM_CHECK(roots != nullptr, "roots is null");
+    roots->clear();
+    const VectorXd c = getCoefficients(derivative);
+    const int n = N_ - derivative;
+    if (n < 1) return true;
+    std::vector<double> cc(c.data(), c.data() + n), r(n);
+    int32_t nr = 0;
+    uint32_t st = 0;
+    runtime::check_rc(mtg_poly_real_roots_batch(runtime::context(), 1, n, MTG_MEM_HOST, MTG_LAYOUT_AOS, cc.data(),
+                                                &t_start, &t_end, n, r.data(), &nr, &st, nullptr),
+                      "mtg_poly_real_roots_batch");
+    roots->assign(r.begin(), r.begin() + nr);
+    return true;
+  }
+  // src/polynomial.cpp:65-83: [t_start, t_end, real roots of p^(derivative + 1) in range]
+  bool computeMinMaxCandidates(double t_start, double t_end, int derivative, std::vector<double>* candidates) const {
+    MTG_SHIM_CHECK(candidates != nullptr, "candidates is null");
+    candidates->clear();
+    if (N_ - derivative - 1 < 0) return false;
+    if (t_start > t_end) return false;  // selectMinMaxCandidatesFromRoots, :37-40
+    std::vector<double> roots;
+    getRealRoots(derivative + 1, t_start, t_end, &roots);
+    candidates->push_back(t_start);
+    candidates->push_back(t_end);
+    candidates->insert(candidates->end(), roots.begin(), roots.end());
+    return true;
+  }
+  // src/polynomial.cpp:116-143: first candidate wins ties
+  bool selectMinMaxFromCandidates(const std::vector<double>& candidates, int derivative,
+                                  std::pair<double, double>* minimum, std::pair<double, double>* maximum) const {
+    MTG_SHIM_CHECK(minimum != nullptr && maximum != nullptr, "null output");
+    if (candidates.empty()) return false;
+    minimum->first = maximum->first = candidates[0];
+    minimum->second = std::numeric_limits<double>::max();
+    maximum->second = std::numeric_limits<double>::lowest();
+    for (double t : candidates) {
+      const double v = evaluate(t, derivative);
+      if (v < minimum->second) *minimum = std::make_pair(t, v);
+      if (v > maximum->second) *maximum = std::make_pair(t, v);
+    }
+    return true;
+  }
+  // src/polynomial.cpp:99-114
+  bool computeMinMax(double t_start, double t_end, int derivative, std::pair<double, double>* minimum,
+                     std::pair<double, double>* maximum) const {
+    std::vector<double> candidates;
+    if (!computeMinMaxCandidates(t_start, t_end, derivative, &candidates)) return false;
+    return selectMinMaxFromCandidates(candidates, derivative, minimum, maximum);
   }
 
   static int getConvolutionLength(int data_size, int kernel_size) { return data_size + kernel_size - 1; }

@@ -129,8 +129,21 @@ class PolynomialOptimization {
     return true;  // like the reference, always
   }
 
-  // LIN_I:113-130: 0.5 sum c^T Q c of the current segments
-  double computeCost() const { return cost_; }
+  // LIN_I:113-130: 0.5 sum c^T Q c of the CURRENT segments with the CURRENT segment times (after
+  // updateSegmentTimes without a new solve: new Q, old coefficients — like the reference)
+  double computeCost() const {
+    if (n_segments_ == 0) return 0.0;
+    Trajectory t;
+    t.setSegments(segments_);
+    std::vector<double> c, times;
+    t.pack(&c, &times);
+    double cost = 0.0;
+    mtg_problem_desc d = runtime::desc(1, (int)n_segments_, (int)dimension_, N, derivative_to_optimize_);
+    runtime::check_rc(mtg_compute_cost_batch(runtime::context(), &d, c.data(), segment_times_.data(), &cost, nullptr,
+                                             nullptr),
+                      "mtg_compute_cost_batch");
+    return cost;
+  }
 
   void getTrajectory(Trajectory* trajectory) const {
     MTG_SHIM_CHECK(trajectory != nullptr, "trajectory is null");
@@ -185,8 +198,49 @@ class PolynomialOptimization {
     unpackSegments(coeffs);
   }
 
-  // LIN_I:455-487: maximum of |p^(derivative)| over the trajectory (time relative to its segment).
-  // `candidates`, if given, receives the per-segment maxima (the reference lists every candidate).
+  // LIN_I:396-417: candidate times of one segment: [t_start, t_stop, roots of the magnitude derivative in range]
+  static bool computeSegmentMaximumMagnitudeCandidates(int derivative, const Segment& segment, double t_start,
+                                                       double t_stop, std::vector<double>* candidates) {
+    MTG_SHIM_CHECK(candidates != nullptr, "candidates is null");
+    MTG_SHIM_CHECK(N - derivative - 1 > 0, "N-Derivative-1 has to be greater 0");  // :400-401
+    std::vector<int> dimensions;
+    for (int i = 0; i < segment.D(); ++i) dimensions.push_back(i);
+    return segment.computeMinMaxMagnitudeCandidateTimes(derivative, t_start, t_stop, dimensions, candidates);
+  }
+  template <int Derivative>
+  static bool computeSegmentMaximumMagnitudeCandidates(const Segment& segment, double t_start, double t_stop,
+                                                       std::vector<double>* candidates) {
+    return computeSegmentMaximumMagnitudeCandidates(Derivative, segment, t_start, t_stop, candidates);
+  }
+  // LIN_I:419-453: candidates by sampling (direction changes of the magnitude with |p^(d+1)| < 1e-2); the
+  // samples come from one evaluateRange-free sweep: the t += dt accumulation of the reference's loop is kept
+  template <int Derivative>
+  static void computeSegmentMaximumMagnitudeCandidatesBySampling(const Segment& segment, double t_start,
+                                                                 double t_stop, double dt,
+                                                                 std::vector<double>* candidates) {
+    MTG_SHIM_CHECK(candidates != nullptr, "candidates is null");
+    auto norm = [](const VectorXd& v) {
+      double s = 0.0;
+      for (int i = 0; i < (int)v.size(); ++i) s += v[i] * v[i];
+      return std::sqrt(s);
+    };
+    const VectorXd value_start = segment.evaluate(t_start - dt, Derivative);
+    VectorXd value_old = segment.evaluate(t_start, Derivative);
+    double direction = norm(value_old) - norm(value_start);
+    for (double t = t_start + dt; t < t_stop + dt; t += dt) {
+      const VectorXd value_new = segment.evaluate(t, Derivative);
+      const double direction_new = norm(value_new) - norm(value_old);
+      if (std::signbit(direction) != std::signbit(direction_new)) {
+        if (norm(segment.evaluate(t - dt, Derivative + 1)) < 1e-2) candidates->push_back(t - dt);
+      }
+      value_old = value_new;
+      direction = direction_new;
+    }
+  }
+
+  // LIN_I:455-487: maximum of |p^(derivative)| over the trajectory (time relative to its segment). `candidates`,
+  // if given, receives every candidate like the reference: per segment t = 0, then [0, T, roots...], and the
+  // end of the last segment once more.
   Extremum computeMaximumOfMagnitude(int derivative, std::vector<Extremum>* candidates) const {
     MTG_SHIM_CHECK(N - derivative - 1 > 0, "N - derivative - 1 has to be greater 0");  // :400-401
     if (candidates) candidates->clear();
@@ -194,15 +248,25 @@ class PolynomialOptimization {
     t.setSegments(segments_);
     std::vector<double> c, times;
     t.pack(&c, &times);
-    const int K = (int)n_segments_;
-    std::vector<double> sv(K), st(K);
+    const int K = (int)n_segments_, MC = 2 * N;
+    std::vector<double> ct((size_t)K * MC), cv((size_t)K * MC);
+    std::vector<int32_t> nc(K);
     mtg_problem_desc d = runtime::desc(1, K, (int)dimension_, N, derivative_to_optimize_);
-    runtime::check_rc(mtg_extrema_batch(runtime::context(), &d, c.data(), times.data(), derivative, nullptr, nullptr,
-                                        nullptr, nullptr, nullptr, nullptr, sv.data(), st.data(), nullptr, nullptr),
-                      "mtg_extrema_batch");
+    runtime::check_rc(mtg_extrema_candidates_batch(runtime::context(), &d, c.data(), times.data(), nullptr, nullptr,
+                                                   derivative, 0, MC, ct.data(), cv.data(), nc.data(), nullptr, nullptr),
+                      "mtg_extrema_candidates_batch");
     Extremum best;
     for (int s = 0; s < K; ++s) {
-      const Extremum cand(st[s], sv[s], s);
+      // extrema_times = {0.0} + the segment's candidates (the call clears the vector first in the reference,
+      // so the list is just [0, T, roots...]; LIN_I:466-470 with segment.cpp:86)
+      for (int q = 0; q < nc[s] && q < MC; ++q) {
+        const Extremum cand(ct[(size_t)s * MC + q], cv[(size_t)s * MC + q], s);
+        if (best < cand) best = cand;
+        if (candidates) candidates->push_back(cand);
+      }
+    }
+    if (K > 0) {  // LIN_I:479-484: the last time of the last segment (candidate 1 of that segment)
+      const Extremum cand(ct[(size_t)(K - 1) * MC + 1], cv[(size_t)(K - 1) * MC + 1], K - 1);
       if (best < cand) best = cand;
       if (candidates) candidates->push_back(cand);
     }

@@ -62,6 +62,42 @@ class Segment {
     return out;
   }
 
+  // segment.cpp:82-133 / 135-158: candidate times [t_start, t_end, roots of the magnitude derivative in range]
+  // and their magnitudes over `dimensions`, through mtg_extrema_candidates_batch (one-segment trajectory)
+  bool computeMinMaxMagnitudeCandidates(int derivative, double t_start, double t_end,
+                                        const std::vector<int>& dimensions, std::vector<Extremum>* candidates) const {
+    MTG_SHIM_CHECK(candidates != nullptr, "candidates is null");
+    candidates->clear();
+    if (dimensions.empty()) return false;  // segment.cpp:89-91
+    int mask = 0;
+    for (int dim : dimensions) {
+      if (dim < 0 || dim >= D_) return false;  // segment.cpp:97-102
+      mask |= 1 << dim;
+    }
+    const int n = N_ + (N_ & 1);
+    std::vector<double> c;
+    packCoefficients(n, &c);
+    const int MC = 2 * n;
+    std::vector<double> ct(MC), cv(MC);
+    int32_t nc = 0;
+    mtg_problem_desc d = runtime::desc(1, 1, D_, n, 0);
+    runtime::check_rc(mtg_extrema_candidates_batch(runtime::context(), &d, c.data(), &time_, &t_start, &t_end,
+                                                   derivative, mask, MC, ct.data(), cv.data(), &nc, nullptr, nullptr),
+                      "mtg_extrema_candidates_batch");
+    for (int q = 0; q < nc && q < MC; ++q) candidates->push_back(Extremum(ct[q], cv[q], 0));
+    return true;
+  }
+  bool computeMinMaxMagnitudeCandidateTimes(int derivative, double t_start, double t_end,
+                                            const std::vector<int>& dimensions,
+                                            std::vector<double>* candidate_times) const {
+    MTG_SHIM_CHECK(candidate_times != nullptr, "candidate_times is null");
+    candidate_times->clear();
+    std::vector<Extremum> cand;
+    if (!computeMinMaxMagnitudeCandidates(derivative, t_start, t_end, dimensions, &cand)) return false;
+    for (const Extremum& e : cand) candidate_times->push_back(e.time);
+    return true;
+  }
+
   // segment.cpp:160-184 (pure selection, host)
   bool selectMinMaxMagnitudeFromCandidates(int /*derivative*/, double t_start, double t_end,
                                            const std::vector<int>& /*dimensions*/,

@@ -267,12 +267,15 @@ int mtg_feasibility_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const doub
  *
  * mtg_nl_descent_batch: a projected-gradient driver standing in for NLOPT on
  * objectiveFunctionFreeConstraints[AndCollision] [NL_I:1024-1284] without the collision term:
- *   f = w_d J_d + w_sc J_sc,   d_p <- clamp(d_p - step * (w_d grad_d + w_sc grad_sc) / diag, -bound, +bound)
+ *   f = w_d J_d + w_sc J_sc,   trial = clamp(x_acc - step_b * (w_d grad_d + w_sc grad_sc) / diag, -bound, +bound)
  * (diag only when precondition != 0; bound[k] = |limit| of the constraint on derivative k,
- * setFreeEndpointDerivativeHardConstraints [NL_I:2858-2905]), `iterations` times; free_constraints is updated
- * in place, coeffs [K][D][N] receives the final coefficients, cost_history [iterations + 1][2][B] (or NULL)
- * J_d and J_sc at every iterate (the last row is the returned point). Everything is enqueued on `stream`
- * (capturable in a CUDA graph once the tables of (N, derivative) are resident). AoS layout. */
+ * setFreeEndpointDerivativeHardConstraints [NL_I:2858-2905]). A trial point is accepted iff f did not
+ * increase; a rejected trial halves that trajectory's step and restarts from the last accepted point, so
+ * the returned point never has a larger f than the start. `iterations` trial steps; free_constraints is
+ * updated in place (the last accepted point), coeffs [K][D][N] receives its coefficients, cost_history
+ * [iterations + 2][3][B] (or NULL): J_d, J_sc and accepted (1 / 0) of trial point 0..iterations, then of the
+ * returned point. Everything is enqueued on `stream` (capturable in a CUDA graph once the tables of
+ * (N, derivative) are resident). AoS layout. */
 int mtg_cost_derivative_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* positions,
                               const double* end_derivatives, const double* seg_times,
                               const double* free_constraints, double* J_d, double* grad, double* diag,

@@ -601,7 +601,8 @@ class Context:
     def nl_descent_batch(self, positions, seg_times, free, derivatives=(), limits=(), w_d=1.0, w_sc=1.0,
                          soft_weight=100.0, maximum_cost=1e12, increment=0.05, step=0.5, precondition=True,
                          iterations=10, end_derivatives=None, N=10, derivative=4, want_history=True, stream=None):
-        """mtg_nl_descent_batch (AoS): updates `free` in place; returns coeffs [B,K,D,N], history [it+1,2,B]."""
+        """mtg_nl_descent_batch (AoS): updates `free` in place; returns coeffs [B,K,D,N], history [it+2,3,B]
+        (J_d, J_sc, accepted of every trial point, then of the returned point)."""
         B, Kp1, D = positions.shape
         K = Kp1 - 1
         desc = ProblemDesc(B, K, D, N, derivative, MTG_MEM_DEVICE, LAYOUT_AOS)
@@ -609,7 +610,7 @@ class Context:
         der = (C.c_int32 * max(n, 1))(*[int(x) for x in derivatives])
         lim = (C.c_double * max(n, 1))(*[float(x) for x in limits])
         coeffs = self._empty(positions, (B, K, D, N))
-        hist = self._empty(positions, (iterations + 1, 2, B)) if want_history else None
+        hist = self._empty(positions, (iterations + 2, 3, B)) if want_history else None
         status = self._empty(positions, (B,), "u4")
         rc = self._lib.mtg_nl_descent_batch(self._h, C.byref(desc), _ptr(positions), _ptr(end_derivatives),
                                             _ptr(seg_times), _ptr(free), n, der, lim, float(w_d), float(w_sc),

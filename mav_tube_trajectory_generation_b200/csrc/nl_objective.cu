@@ -256,6 +256,7 @@ struct SoftCombineParams {
   double weight, max_cost, increment;
   int central;
   int n_con, B, b0, nb, K, Q, NF;
+  int cost_only;  // 1: J_sc only (Q = 1, no perturbed maxima)
 };
 
 __device__ __forceinline__ double soft_cost(double mx, double limit, double w, double cap) {
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(128) soft_combine_kernel(const SoftCombinePara
   if (g >= (size_t)p.nb * p.Q) return;
   const int local = (int)(g / p.Q), q = (int)(g % p.Q);
   const int K = p.K;
-  const int v = (q / p.NF) % (K - 1) + 1;
+  const int v = p.cost_only ? 1 : (q / p.NF) % (K - 1) + 1;
   double c_nom = 0.0, c_lo = 0.0, c_hi = 0.0;
   for (int c = 0; c < p.n_con; ++c) {
     const double* nm = p.nominal[c] + (size_t)local * K;
@@ -278,8 +279,9 @@ __global__ void __launch_bounds__(128) soft_combine_kernel(const SoftCombinePara
       all = fmax(all, m);
       if (s != v - 1 && s != v) rest = fmax(rest, m);
     }
-    const double* pm = p.perturbed[c] + ((size_t)local * p.Q + q) * 4;
     c_nom += soft_cost(all, p.limit[c], p.weight, p.max_cost);
+    if (p.cost_only) continue;
+    const double* pm = p.perturbed[c] + ((size_t)local * p.Q + q) * 4;
     c_lo += soft_cost(fmax(rest, fmax(pm[0], pm[1])), p.limit[c], p.weight, p.max_cost);
     c_hi += soft_cost(fmax(rest, fmax(pm[2], pm[3])), p.limit[c], p.weight, p.max_cost);
   }
@@ -290,34 +292,80 @@ __global__ void __launch_bounds__(128) soft_combine_kernel(const SoftCombinePara
   if (p.J_sc && q == 0) p.J_sc[b] = c_nom;
 }
 
-// ------------------------------------------------------------------ projected gradient step
+// ------------------------------------------------------------------ projected gradient with step rejection
+// State per trajectory: the last ACCEPTED point x_prev with its search direction g_prev and objective f_prev,
+// and a step length. Every pass evaluates the objective and gradients at the current trial point; the trial is
+// accepted iff f did not increase (a NaN never is), otherwise the step is halved and the next trial starts again
+// from x_prev along g_prev. No extra objective evaluations are needed.
 struct DescentParams {
-  double* __restrict__ x;              // free constraints, elem ((dim*(K-1) + v-1)*NF + k-1), rec Q
+  double* __restrict__ x;              // trial point: free constraints, elem ((dim*(K-1) + v-1)*NF + k-1), rec Q
+  double* __restrict__ x_prev;         // last accepted point, same layout
+  double* __restrict__ g_prev;         // its (preconditioned, weighted) direction, same layout
   const double* __restrict__ grad_d;   // same layout
   const double* __restrict__ grad_sc;  // same layout or nullptr
   const double* __restrict__ diag;     // elem ((v-1)*NF + k-1), rec (K-1)*NF; or nullptr (plain gradient step)
+  const double* __restrict__ J_d;      // [B]
+  const double* __restrict__ J_sc;     // [B] or nullptr
+  double* __restrict__ f_prev;         // [B]
+  double* __restrict__ step;           // [B]
+  double* __restrict__ accepted;       // [B] or nullptr: 1.0 / 0.0 (a row of cost_history)
+  uint8_t* __restrict__ flag;          // [B]
   double bound[MTG_TAB_LD];            // |x| <= bound[k] for derivative order k (infinity: unbounded)
-  double w_d, w_sc, step;
+  double w_d, w_sc;
   int B, nb, Q, NF, per_dim;
 };
 
-template <bool AOS>
+__global__ void __launch_bounds__(256) descent_accept_kernel(const DescentParams p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.nb) return;
+  double f = p.w_d * p.J_d[b];
+  if (p.J_sc) f = fma(p.w_sc, p.J_sc[b], f);
+  const bool acc = f <= p.f_prev[b];  // false for NaN
+  if (acc)
+    p.f_prev[b] = f;
+  else
+    p.step[b] *= 0.5;
+  p.flag[b] = acc ? 1 : 0;
+  if (p.accepted) p.accepted[b] = acc ? 1.0 : 0.0;
+}
+
+// MODE 0: take the next trial step; MODE 1: finalize (a rejected last trial falls back to x_prev)
+template <bool AOS, int MODE>
 __global__ void __launch_bounds__(256) descent_step_kernel(const DescentParams p) {
   const size_t total = (size_t)p.nb * p.Q;
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
     const size_t b = AOS ? g / p.Q : g % p.nb;
     const int q = (int)(AOS ? g % p.Q : g / p.nb);
     const size_t o = at<AOS>((size_t)q, (size_t)p.Q, (size_t)p.B, b);
-    double gr = p.w_d * p.grad_d[o];
-    if (p.grad_sc) gr = fma(p.w_sc, p.grad_sc[o], gr);
-    const int within = q % p.per_dim;  // (v-1)*NF + k-1
-    const int k = within % p.NF + 1;
-    if (p.diag) gr /= p.diag[at<AOS>((size_t)within, (size_t)p.per_dim, (size_t)p.B, b)];
-    double xn = p.x[o] - p.step * gr;
+    const bool acc = p.flag[b] != 0;
+    if (MODE == 1) {
+      if (!acc) p.x[o] = p.x_prev[o];
+      continue;
+    }
+    double xa, gr;
+    if (acc) {
+      xa = p.x[o];
+      gr = p.w_d * p.grad_d[o];
+      if (p.grad_sc) gr = fma(p.w_sc, p.grad_sc[o], gr);
+      const int within = q % p.per_dim;  // (v-1)*NF + k-1
+      if (p.diag) gr /= p.diag[at<AOS>((size_t)within, (size_t)p.per_dim, (size_t)p.B, b)];
+      p.x_prev[o] = xa;
+      p.g_prev[o] = gr;
+    } else {
+      xa = p.x_prev[o];
+      gr = p.g_prev[o];
+    }
+    const int k = (q % p.per_dim) % p.NF + 1;
+    double xn = xa - p.step[b] * gr;
     const double bd = p.bound[k];
     xn = fmin(fmax(xn, -bd), bd);  // setFreeEndpointDerivativeHardConstraints, NL_I:2858-2905
     p.x[o] = xn;
   }
+}
+
+__global__ void fill_kernel(double* x, double v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
 }
 
 int check_nl_desc(mtg_ctx* ctx, const mtg_problem_desc* desc) {
@@ -404,6 +452,15 @@ int mtg_soft_constraint_gradient_batch(mtg_ctx* ctx, const mtg_problem_desc* des
       sc.nominal[c] = nom;
       sc.limit[c] = limits[c];
     }
+    if (!grad) {  // cost only: no perturbed segments
+      sc.J_sc = J_sc + off; sc.grad = nullptr; sc.weight = weight; sc.max_cost = maximum_cost; sc.increment = increment;
+      sc.central = 1; sc.n_con = n_constraints; sc.B = nb; sc.b0 = 0; sc.nb = nb; sc.K = K; sc.Q = 1; sc.NF = NF;
+      sc.cost_only = 1;
+      soft_combine_kernel<true><<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(sc);
+      ++ctx->launches;
+      MTG_CUDA_TRY(cudaGetLastError());
+      continue;
+    }
     PerturbParams pp = {};
     pp.coeffs = c_off; pp.seg_times = t_off; pp.pc = pc; pp.pt = pt; pp.increment = increment;
     pp.B = nb; pp.b0 = 0; pp.nb = nb; pp.K = K; pp.D = D; pp.N = N;
@@ -445,8 +502,8 @@ int mtg_nl_descent_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const doubl
   int rc = check_nl_desc(ctx, desc);
   if (rc) return rc;
   if (!positions || !seg_times || !free_constraints || !coeffs || iterations < 0 || n_constraints < 0 ||
-      n_constraints > kMaxSoft || (n_constraints > 0 && (!derivatives || !limits)))
-    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "positions, seg_times, free_constraints, coeffs and a valid constraint list are required");
+      n_constraints > kMaxSoft || (n_constraints > 0 && (!derivatives || !limits)) || !(step > 0.0))
+    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "positions, seg_times, free_constraints, coeffs, step > 0 and a valid constraint list are required");
   if (desc->layout != MTG_LAYOUT_AOS)
     return fail(ctx, MTG_ERR_UNSUPPORTED, "mtg_nl_descent_batch: AoS layout only");
   if (desc->B == 0) return MTG_OK;
@@ -454,40 +511,66 @@ int mtg_nl_descent_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const doubl
   cudaStream_t s = (cudaStream_t)stream_;
   const int B = desc->B, K = desc->K, D = desc->D, N = desc->N, NF = N / 2 - 1;
   const int Q = D * (K - 1) * NF, per_dim = (K - 1) * NF;
-  DeviceBuffer* gbuf = ctx->nl_scratch_for(s, 1);  // gradients + diagonal (slot 0 is the soft-gradient work space)
-  if (gbuf->ensure(((size_t)2 * Q + per_dim) * B * 8 + 256)) return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of the gradient buffers failed");
+  DeviceBuffer* gbuf = ctx->nl_scratch_for(s, 1);  // gradients, diagonal, optimiser state (slot 0: soft-gradient work space)
+  const size_t n_d = ((size_t)4 * Q + per_dim + 4) * B;
+  if (gbuf->ensure(n_d * 8 + (size_t)B + 256)) return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of the optimiser state failed");
   double* g_d = (double*)gbuf->ptr;
   double* g_sc = g_d + (size_t)Q * B;
-  double* dg = g_sc + (size_t)Q * B;
+  double* x_prev = g_sc + (size_t)Q * B;
+  double* g_prev = x_prev + (size_t)Q * B;
+  double* dg = g_prev + (size_t)Q * B;
+  double* Jd_buf = dg + (size_t)per_dim * B;
+  double* Jsc_buf = Jd_buf + B;
+  double* f_prev = Jsc_buf + B;
+  double* step_b = f_prev + B;
+  uint8_t* flag = (uint8_t*)(step_b + B);
   const bool soft = n_constraints > 0 && w_sc != 0.0;
-  for (int it = 0; it <= iterations; ++it) {
-    // coefficients (and 0.5 c^T Q c, unused here) of the current free derivatives
+  fill_kernel<<<(B + 255) / 256, 256, 0, s>>>(f_prev, INFINITY, B);
+  fill_kernel<<<(B + 255) / 256, 256, 0, s>>>(step_b, step, B);
+  ctx->launches += 2;
+  DescentParams dp = {};
+  dp.x = free_constraints; dp.x_prev = x_prev; dp.g_prev = g_prev; dp.grad_d = g_d; dp.grad_sc = soft ? g_sc : nullptr;
+  dp.diag = precondition ? dg : nullptr; dp.f_prev = f_prev; dp.step = step_b; dp.flag = flag;
+  for (int k = 0; k < MTG_TAB_LD; ++k) dp.bound[k] = INFINITY;
+  for (int c = 0; c < n_constraints; ++c)
+    if (derivatives[c] >= 1 && derivatives[c] <= NF) dp.bound[derivatives[c]] = std::fabs(limits[c]);
+  dp.w_d = w_d; dp.w_sc = w_sc; dp.B = B; dp.nb = B; dp.Q = Q; dp.NF = NF; dp.per_dim = per_dim;
+  const size_t total = (size_t)B * Q;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 32);
+  // rows of cost_history: [pass][3][B] = J_d, J_sc, accepted; passes 0..iterations are the trial points, pass
+  // iterations + 1 is the returned (last accepted) point
+  for (int it = 0; it <= iterations + 1; ++it) {
+    const bool final_pass = it == iterations + 1;
     rc = mtg_set_free_constraints_batch(ctx, desc, positions, end_derivatives, seg_times, free_constraints, coeffs,
                                         nullptr, status, stream_);
     if (rc) return rc;
-    double* Jd = cost_history ? cost_history + (size_t)it * 2 * B : nullptr;
-    double* Jsc = cost_history ? Jd + B : nullptr;
-    rc = mtg_cost_derivative_batch(ctx, desc, positions, end_derivatives, seg_times, free_constraints, Jd, g_d,
-                                   precondition ? dg : nullptr, nullptr, stream_);
+    double* Jd = cost_history ? cost_history + (size_t)it * 3 * B : Jd_buf;
+    double* Jsc = cost_history ? Jd + B : Jsc_buf;
+    rc = mtg_cost_derivative_batch(ctx, desc, positions, end_derivatives, seg_times, free_constraints, Jd,
+                                   final_pass ? nullptr : g_d, (precondition && !final_pass) ? dg : nullptr, nullptr, stream_);
     if (rc) return rc;
     if (soft) {
       rc = mtg_soft_constraint_gradient_batch(ctx, desc, coeffs, seg_times, n_constraints, derivatives, limits,
-                                              soft_weight, maximum_cost, increment, 1, Jsc, g_sc, nullptr, stream_);
+                                              soft_weight, maximum_cost, increment, 1, Jsc, final_pass ? nullptr : g_sc,
+                                              nullptr, stream_);
       if (rc) return rc;
-    } else if (Jsc) {
+    } else {
       MTG_CUDA_TRY(cudaMemsetAsync(Jsc, 0, sizeof(double) * (size_t)B, s));
     }
-    if (it == iterations) break;  // the last pass only evaluates the final point
-    DescentParams dp = {};
-    dp.x = free_constraints; dp.grad_d = g_d; dp.grad_sc = soft ? g_sc : nullptr; dp.diag = precondition ? dg : nullptr;
-    for (int k = 0; k < MTG_TAB_LD; ++k) dp.bound[k] = INFINITY;
-    for (int c = 0; c < n_constraints; ++c)
-      if (derivatives[c] >= 1 && derivatives[c] <= NF) dp.bound[derivatives[c]] = std::fabs(limits[c]);
-    dp.w_d = w_d; dp.w_sc = w_sc; dp.step = step; dp.B = B; dp.nb = B; dp.Q = Q; dp.NF = NF; dp.per_dim = per_dim;
-    const size_t total = (size_t)B * Q;
-    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 32);
-    descent_step_kernel<true><<<grid, 256, 0, s>>>(dp);
-    ++ctx->launches;
+    if (final_pass) {
+      if (cost_history) {
+        fill_kernel<<<(B + 255) / 256, 256, 0, s>>>(Jd + 2 * (size_t)B, 1.0, B);
+        ++ctx->launches;
+      }
+      break;
+    }
+    dp.J_d = Jd; dp.J_sc = soft ? Jsc : nullptr; dp.accepted = cost_history ? Jd + 2 * (size_t)B : nullptr;
+    descent_accept_kernel<<<(B + 255) / 256, 256, 0, s>>>(dp);
+    if (it == iterations)
+      descent_step_kernel<true, 1><<<grid, 256, 0, s>>>(dp);
+    else
+      descent_step_kernel<true, 0><<<grid, 256, 0, s>>>(dp);
+    ctx->launches += 2;
     MTG_CUDA_TRY(cudaGetLastError());
   }
   return MTG_OK;

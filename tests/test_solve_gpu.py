@@ -34,8 +34,8 @@ ORACLE_NOISE = {4: 1e-8, 3: 1e-8, 2: 5e-8, 1: 5e-6, 0: 1e-4}
 def arbitrate(po, pos, times, der, coeffs, cost, ref_c, ref_cost, n=1):
     """EVERY item of the batch against the exact solution of the reference's normal equations — the
     binary128 arbiter oracle/exact128.cpp (pinned to the 60-digit mpmath solve in tests/test_oracle.py) —
-    at 1e-10 (coefficients, norm-wise per polynomial) / 1e-11 (cost): an order of magnitude inside the
-    north-star's 1e-9. The worst item is cross-checked with the mpmath solve itself."""
+    at 1e-10 (coefficients, norm-wise per polynomial) / 1e-11 (cost) for cost derivatives >= 2, 5e-10 / 1e-10 below:
+    inside the north-star's 1e-9. The worst item is cross-checked with the mpmath solve itself."""
     from exact_solver import exact_solve
 
     B = len(pos)
@@ -45,8 +45,10 @@ def arbitrate(po, pos, times, der, coeffs, cost, ref_c, ref_cost, n=1):
     ce, cost_e, _ = po.solve_exact128_batch(times, mask, values, N=N, derivative=der, n_threads=8)
     e_gpu = normwise(coeffs, ce).reshape(B, -1).max(axis=1)
     e_ora = normwise(ref_c, ce).reshape(B, -1).max(axis=1)
-    assert e_gpu.max() < 1e-10, (int(e_gpu.argmax()), e_gpu.max(), e_ora.max())
-    assert (np.abs(cost - cost_e) / np.abs(cost_e)).max() <= 1e-11
+    # min-snap / jerk / acceleration: an order of magnitude inside the bar; velocity and position costs (cond(R_pp)
+    # grows as the cost derivative drops): inside it by 2x
+    assert e_gpu.max() < (1e-10 if der >= 2 else 5e-10), (int(e_gpu.argmax()), e_gpu.max(), e_ora.max())
+    assert (np.abs(cost - cost_e) / np.abs(cost_e)).max() <= (1e-11 if der >= 2 else 1e-10)
     # where the CUDA path and the oracle visibly disagree it is the reference order's rounding noise
     err = normwise(coeffs, ref_c).reshape(B, -1).max(axis=1)
     vis = err > 1e-10
