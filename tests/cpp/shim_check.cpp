@@ -212,6 +212,69 @@ int main() {
     EXPECT(std::fabs(0.5 * J - cost0) <= 1e-6 * cost0);
     std::printf("general pattern: cost %.9g, checkPath %.2e, n_fixed %zu, n_free %zu\n", cost0, worst, nf, np);
   }
+  // candidate lists (LIN_I:396-487, segment.cpp:82-158), Polynomial::computeMinMax (polynomial.cpp:99-114, in the
+  // spirit of PolynomialTest.FindMinMax TEST_POLY:81-137) and computeCost after updateSegmentTimes (LIN_I:113-130)
+  {
+    Vertex::Vector v = createRandomVertices(4, 5, VectorXd::Constant(3, -10.0), VectorXd::Constant(3, 10.0), 109);
+    std::vector<double> times = estimateSegmentTimes(v, 3.0, 5.0);
+    PolynomialOptimization<10> opt(3);
+    EXPECT(opt.setupFromVertices(v, times));
+    EXPECT(opt.solveLinear());
+    std::vector<Extremum> cand;
+    const Extremum vmax = opt.computeMaximumOfMagnitude(derivative_order::VELOCITY, &cand);
+    EXPECT(cand.size() >= 2 * 5 + 1);
+    double best = 0.0;
+    for (const Extremum& e : cand) best = std::fmax(best, e.value);
+    EXPECT(best == vmax.value);
+    Segment::Vector segs;
+    opt.getSegments(&segs);
+    std::vector<double> ct;
+    EXPECT(PolynomialOptimization<10>::computeSegmentMaximumMagnitudeCandidates(derivative_order::VELOCITY, segs[2], 0.0,
+                                                                                segs[2].getTime(), &ct));
+    EXPECT(ct.size() >= 2 && ct[0] == 0.0 && ct[1] == segs[2].getTime());
+    for (size_t q = 2; q < ct.size(); ++q) {   // every root is a stationary point of |v|^2: v . a = 0
+      const VectorXd vel = segs[2].evaluate(ct[q], 1), acc = segs[2].evaluate(ct[q], 2);
+      double dot = 0.0, nv = 0.0, na = 0.0;
+      for (int d = 0; d < 3; ++d) { dot += vel[d] * acc[d]; nv += vel[d] * vel[d]; na += acc[d] * acc[d]; }
+      EXPECT(std::fabs(dot) <= 1e-9 * std::sqrt(nv * na) + 1e-12);
+    }
+    std::vector<double> cs;
+    PolynomialOptimization<10>::computeSegmentMaximumMagnitudeCandidatesBySampling<derivative_order::VELOCITY>(
+        segs[2], 0.0, segs[2].getTime(), 0.01, &cs);
+    for (double t : cs) {   // every sampled candidate sits next to an analytic one
+      double d = 1e9;
+      for (double a : ct) d = std::fmin(d, std::fabs(a - t));
+      EXPECT(d <= 0.02);
+    }
+    // one polynomial: extrema of p'(t) on a sub-interval against dense sampling
+    std::pair<double, double> mn, mx;
+    EXPECT(segs[1][0].computeMinMax(0.2, segs[1].getTime() * 0.9, 1, &mn, &mx));
+    double smin = 1e300, smax = -1e300;
+    for (double t = 0.2; t <= segs[1].getTime() * 0.9; t += 0.001) {
+      const double val = segs[1][0].evaluate(t, 1);
+      smin = std::fmin(smin, val);
+      smax = std::fmax(smax, val);
+    }
+    EXPECT(mx.second >= smax - 1e-12 && mx.second <= smax + 1e-4 && mn.second <= smin + 1e-12 && mn.second >= smin - 1e-4);
+    // new segment times without a new solve: the cost is 0.5 sum c^T Q(T_new) c of the OLD coefficients
+    const double cost0 = opt.computeCost();
+    std::vector<double> t2 = times;
+    for (double& x : t2) x *= 1.5;
+    opt.updateSegmentTimes(t2);
+    double want = 0.0;
+    for (int i = 0; i < 5; ++i) {
+      MatrixXd Q;
+      PolynomialOptimization<10>::computeQuadraticCostJacobian(derivative_order::SNAP, t2[i], &Q);
+      for (int d = 0; d < 3; ++d) {
+        const VectorXd c = segs[i][d].getCoefficients(0);
+        for (int a = 0; a < 10; ++a)
+          for (int b = 0; b < 10; ++b) want += 0.5 * c[a] * Q(a, b) * c[b];
+      }
+    }
+    EXPECT(std::fabs(opt.computeCost() - want) <= 1e-9 * want && std::fabs(want - cost0) > 1e-3 * cost0);
+    std::printf("candidates: %zu over 5 segments, max|v| %.6g; computeCost after updateSegmentTimes %.9g (was %.9g)\n",
+                cand.size(), vmax.value, opt.computeCost(), cost0);
+  }
   if (failures) {
     std::printf("SHIM FAILED: %d check(s)\n", failures);
     return 1;
