@@ -269,7 +269,8 @@ int mtg_feasibility_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const doub
  * objectiveFunctionFreeConstraints[AndCollision] [NL_I:1024-1284] without the collision term:
  *   f = w_d J_d + w_sc J_sc,   trial = clamp(x_acc - step_b * (w_d grad_d + w_sc grad_sc) / diag, -bound, +bound)
  * (diag only when precondition != 0; bound[k] = |limit| of the constraint on derivative k,
- * setFreeEndpointDerivativeHardConstraints [NL_I:2858-2905]). A trial point is accepted iff f did not
+ * setFreeEndpointDerivativeHardConstraints [NL_I:2858-2905]; the start point is projected onto the bounds
+ * first). A trial point is accepted iff f did not
  * increase; a rejected trial halves that trajectory's step and restarts from the last accepted point, so
  * the returned point never has a larger f than the start. `iterations` trial steps; free_constraints is
  * updated in place (the last accepted point), coeffs [K][D][N] receives its coefficients, cost_history

@@ -329,7 +329,8 @@ __global__ void __launch_bounds__(256) descent_accept_kernel(const DescentParams
   if (p.accepted) p.accepted[b] = acc ? 1.0 : 0.0;
 }
 
-// MODE 0: take the next trial step; MODE 1: finalize (a rejected last trial falls back to x_prev)
+// MODE 0: take the next trial step; MODE 1: finalize (a rejected last trial falls back to x_prev);
+// MODE 2: project the start point onto the bounds (the optimiser's iterates live inside them)
 template <bool AOS, int MODE>
 __global__ void __launch_bounds__(256) descent_step_kernel(const DescentParams p) {
   const size_t total = (size_t)p.nb * p.Q;
@@ -337,6 +338,11 @@ __global__ void __launch_bounds__(256) descent_step_kernel(const DescentParams p
     const size_t b = AOS ? g / p.Q : g % p.nb;
     const int q = (int)(AOS ? g % p.Q : g / p.nb);
     const size_t o = at<AOS>((size_t)q, (size_t)p.Q, (size_t)p.B, b);
+    if (MODE == 2) {
+      const double bd0 = p.bound[(q % p.per_dim) % p.NF + 1];
+      p.x[o] = fmin(fmax(p.x[o], -bd0), bd0);
+      continue;
+    }
     const bool acc = p.flag[b] != 0;
     if (MODE == 1) {
       if (!acc) p.x[o] = p.x_prev[o];
@@ -537,6 +543,8 @@ int mtg_nl_descent_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const doubl
   dp.w_d = w_d; dp.w_sc = w_sc; dp.B = B; dp.nb = B; dp.Q = Q; dp.NF = NF; dp.per_dim = per_dim;
   const size_t total = (size_t)B * Q;
   const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 32);
+  descent_step_kernel<true, 2><<<grid, 256, 0, s>>>(dp);  // the start point, projected onto the bounds
+  ++ctx->launches;
   // rows of cost_history: [pass][3][B] = J_d, J_sc, accepted; passes 0..iterations are the trial points, pass
   // iterations + 1 is the returned (last accepted) point
   for (int it = 0; it <= iterations + 1; ++it) {

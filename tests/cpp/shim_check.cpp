@@ -90,7 +90,7 @@ static void random_problem(int D, int K, size_t seed) {
   EXPECT(traj.computeMinMaxMagnitude(derivative_order::VELOCITY, dims, &mn, &mx));
   EXPECT(vmax.value >= vmax_sampled - 1e-9 && vmax.value <= vmax_sampled + 0.01);
   EXPECT(std::fabs(vmax.value - mx.value) < 1e-12 && vmax.segment_idx == mx.segment_idx);
-  EXPECT((int)cands.size() == K);
+  EXPECT((int)cands.size() >= 2 * K + 1);  // per segment [0, T, roots...] + the end of the last segment (LIN_I:455-487)
   // ConstraintPacking: [d_f; d_p] -> p = A^-1 M d -> A p -> M^+ -> [d_f; d_p]; coefficients == segments
   std::vector<VectorXd> d_f, d_p;
   opt.getFixedConstraints(&d_f);
