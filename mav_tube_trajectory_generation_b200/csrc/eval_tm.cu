@@ -53,7 +53,7 @@ int launch_tm_planned(mtg_ctx* ctx, const EvalParams& p_in, cudaStream_t s) {
   if (scratch->ensure((size_t)chunk * c_max * sizeof(TmDesc)))
     return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of the sampling-plan scratch failed");
   TmDesc* desc = (TmDesc*)scratch->ptr;
-  const size_t smem = (size_t)tm_layout(D, NT, false, false, tm_tpw(MODE), MODE).per_warp * (kTmBlock / 32);
+  const size_t smem = (size_t)tm_layout(D, NT, false, false, tm_tpw(MODE), MODE, true).per_warp * (kTmBlock / 32);
   auto kern = eval_tm_kernel<NT, D, MODE, true>;
   if (smem > 48 * 1024) MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_block = (kTmBlock / 32) * tm_tpw(MODE);

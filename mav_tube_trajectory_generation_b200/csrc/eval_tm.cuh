@@ -62,6 +62,17 @@ __device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// bulk (TMA) store of a contiguous, 16-byte-aligned run of shared memory to global memory
+__device__ __forceinline__ void bulk_store(double* gdst, const double* smem_src, unsigned bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_src);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+// the committed bulk stores have finished READING shared memory (the tile may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+// orders this thread's shared-memory writes before later async-proxy (bulk copy) reads
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 // trajectory.cpp:88-111: first segment whose accumulated end time exceeds t_start; on
 // success acc is the START time of that segment, computed as (sum_{j<=i} T_j) - T_i like
 // the reference. false: t_start out of range (reference: LOG(ERROR) + empty result;
@@ -129,13 +140,21 @@ struct TmLayout {
 // 16 doubles the resident warps of the latency-bound position sweep; the fp64-bound feasibility
 // sweep prefers full phase-1 lanes (32).
 __host__ __device__ constexpr int tm_tpw(int mode) { return mode >= 2 ? 16 : 16; }
-__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, int kTmTPW, int mode) {
+__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, int kTmTPW, int mode,
+                                             bool bulk = false) {
   const bool kTmTauBlk = tm_taublk(mode);
   TmLayout L;
   L.slot_bytes = D * NT * 8 + (tube ? kTubeGeomLd * 8 : 0);
   L.traj_bytes = 2 * L.slot_bytes + 16;
   L.blk_ld = kTmR * D + 1;
   L.row_ld = (kTmChunk / kTmR) * L.blk_ld;
+  if (bulk) {
+    // rows lie in shared memory exactly as in global memory (+ one double so that 16-byte-aligned global
+    // addresses are 16-byte aligned here too): a row leaves as ONE bulk copy. 32 D + 2 = 2 (mod 16) doubles
+    // keeps the four trajectories of a half-warp in different banks.
+    L.blk_ld = kTmR * D;
+    L.row_ld = kTmChunk * D + 2;
+  }
   L.off_dt = kTmTPW * (kTmTauBlk ? kTmBlkLd : kTmTauLd) * 8;
   L.off_stage = L.off_dt + (kTmTauBlk ? kTmTPW * 8 : 0);
   L.off_info = L.off_stage + kTmG * L.row_ld * 8;
@@ -306,7 +325,8 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
   constexpr bool EXTRA = MODE == TM_DERIVATIVE;  // sampling_times / segment_idx outputs exist in this mode only
   const bool want_acc = EXTRA && p.sampling_times != nullptr;
   constexpr bool kTmTauBlk = tm_taublk(MODE);
-  const TmLayout L = tm_layout(D, NT, want_acc, tube, kTmTPW, MODE);
+  constexpr bool BULK = PLAN;  // the planned kernel hands its rows to the copy engine
+  const TmLayout L = tm_layout(D, NT, want_acc, tube, kTmTPW, MODE, BULK);
   unsigned char* wbase = tm_smem + (size_t)warp * L.per_warp;
   double* tau_s = reinterpret_cast<double*>(wbase);
   double* stage = reinterpret_cast<double*>(wbase + L.off_stage);
@@ -586,6 +606,13 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
       double v2m = 0.0, a2m = 0.0;
       unsigned fand = 7u;
       double* srow = stage + q8 * L.row_ld;
+      // BULK: the row is staged with the parity of its global address (even doubles are 16-byte aligned on both sides)
+      const int sh = (BULK && p.samples) ? (int)(((uintptr_t)(p.samples + off_s[r] * D) >> 3) & 1) : 0;
+      if (BULK) {
+        // the previous pass's bulk copies must have read the tile before it is overwritten
+        if (lane < G) bulk_wait_read();
+        __syncwarp();
+      }
       // JB samples advance together, one Horner step at a time: JB*D (position) or 3*JB*D
       // (feasibility) independent FMA chains cover the fp64 pipe latency from a single warp.
       constexpr int JB = FEAS ? 4 : R;
@@ -689,7 +716,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
           const int k = start + j0 + j;
           if (j0 + j < count) {
 #pragma unroll
-            for (int dim = 0; dim < D; ++dim) srow[k * D + (k >> 3) + dim] = x[j][dim];
+            for (int dim = 0; dim < D; ++dim) srow[k * D + (BULK ? sh : (k >> 3)) + dim] = x[j][dim];
           }
         }
       }
@@ -710,14 +737,34 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
           all_bits &= of;
         }
       }
+      if (BULK) fence_proxy_async_smem();
       __syncwarp();
+      if (BULK && p.samples && lane < G) {
+        // staged rows -> global memory: lane t hands row t to the copy engine as ONE bulk copy of its
+        // 16-byte-aligned body; an odd first / last double is stored directly
+        const int total = cnt_s[g * G + lane] * D;
+        if (total > 0) {
+          double* out = p.samples + off_s[g * G + lane] * D;
+          const int odd = (int)(((uintptr_t)out >> 3) & 1);
+          const double* row = stage + lane * L.row_ld + odd;  // element e of the row lies at row[e]
+          int e1 = total;
+          if ((odd + total) & 1) {
+            --e1;
+            out[e1] = row[e1];
+          }
+          if (odd) out[0] = row[0];
+          if (e1 > odd) bulk_store(out + odd, row + odd, (unsigned)(e1 - odd) * 8u);
+        }
+        bulk_commit();
+      }
       // staged rows -> global memory: whole consecutive 256-byte stores per trajectory
       // (cnt == 0 rows fall out through the predicates; everything else is branch-free)
+      if (!BULK || EXTRA)
 #pragma unroll
       for (int t = 0; t < G; ++t) {
         const int cnt_t = cnt_s[g * G + t];
         const size_t o = off_s[g * G + t];
-        if (p.samples) {
+        if (!BULK && p.samples) {
           double* out = p.samples + o * D + lane;
           const double* row = stage + t * L.row_ld;
           const int total = cnt_t * D;
@@ -747,6 +794,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
     cp_async_commit();
   }
   cp_async_wait_all();
+  if (BULK && lane < G) bulk_wait_read();  // shared memory must outlive the bulk reads
   if (valid && !PLAN) {  // PLAN: written by eval_plan_kernel
     if (p.n_samples) p.n_samples[b] = n;
     if (p.status) p.status[b] = st;
