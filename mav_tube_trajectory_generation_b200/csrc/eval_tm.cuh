@@ -442,9 +442,9 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
         const bool needB = cross < cnt;
         const int ageA = (seg0 & 1) ? age1 : age0, ageB = ((seg0 + 1) & 1) ? age1 : age0;
         if (ageA >= chunk - 1 || (needB && ageB >= chunk - 1)) cp_async_wait_all();
-        read_desc(chunk);  // chunk counts from 1 here: the descriptor of the next chunk
-        if (nd.cnt == 0) done = true;
-        i = nd.seg0;
+        // the descriptor of the NEXT chunk (chunk counts from 1 here) is requested now and first looked at after
+        // phase 2: its DRAM latency hides behind this chunk's evaluation
+        read_desc(chunk);
       }
     } else if (!done) {
       Ti = duration(i);
@@ -785,6 +785,10 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
       __syncwarp();
     }
     n += cnt;
+    if (PLAN && !done) {
+      if (nd.cnt == 0) done = true;
+      i = nd.seg0;
+    }
     // every sample emitted so far has been evaluated: both slots may be re-targeted.
     // Prefetch the current and the next segment (no-ops while they are resident).
     if (!done) {
