@@ -293,6 +293,31 @@ int mtg_nl_descent_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const doubl
                          int precondition, int iterations, double* coeffs, double* cost_history,
                          uint32_t* status, void* stream);
 
+/* --------------------------------- N4: collision potential against a dense distance grid
+ * mtg_collision_cost_batch: getCostAndGradientCollision [NL_I:1608-1780] with
+ * getCostAndGradientPotentialOctree [:1783-1917] and getCostPotential [:2659-2684] for every trajectory of the
+ * batch in one sweep. The supereight octree of the reference (findOccupiedVoxels / getDistanceOctree,
+ * :1920-2043: distance to the nearest occupied voxel inside a 20^3 window) is replaced by a DENSE grid of
+ * distances that the caller precomputes once per map:
+ *  grid [size0][size1][size2] double, DEVICE pointer shared by the batch: distance in metres at voxel
+ *       (origin0 + i0, origin1 + i1, origin2 + i2); a voxel outside the grid counts as "no obstacle in reach"
+ *       (the reference's DBL_MAX); the voxel of a position is (x / map_resolution) truncated toward zero
+ *       like Eigen's cast<int>() [:1812]
+ *  min_bound, max_bound [3]: positions within map_resolution of them are invalid = in collision [:1800-1807]
+ *  J_c [B]: sum over the consulted samples of c(x) |v| time_sum; 0 when the trajectory collides [:1774]
+ *  grad [3][K-1][N/2-1] (layout of free_constraints) or NULL: equation (14) [:1735-1748] with central
+ *       differences of the potential over the six neighbour voxels. As in the reference a collision keeps the
+ *       gradient accumulated up to the colliding sample (its zeroing loop iterates by value, :1776-1777).
+ *  in_collision [B] uint8, n_checks [B] int32 (samples at which the map was consulted) out or NULL
+ * Sampling per segment `for (t = 0; t < T_i; t += coll_check_time_increment)`, samples skipped until the
+ * travelled distance reaches map_resolution [:1705-1708]. D = 3, canonical constraint pattern, device pointers. */
+int mtg_collision_cost_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
+                             const double* seg_times, const double* grid, const int32_t grid_size[3],
+                             const int32_t grid_origin_voxel[3], double map_resolution, const double min_bound[3],
+                             const double max_bound[3], double coll_check_time_increment, double epsilon,
+                             double robot_radius, double coll_pot_multiplier, double* J_c, double* grad,
+                             uint8_t* in_collision, int32_t* n_checks, uint32_t* status, void* stream);
+
 /* --------------------------------- N3: batched trajectory composition and I/O
  * mtg_vertex_at_time_batch: Trajectory::getVertexAtTime(t, max_derivative_order) [src/trajectory.cpp:248-254]
  * (getStartVertex / getGoalVertex with t = 0 / max time, :256-262): evaluate(t, k) for k = 0..max at one

@@ -88,6 +88,8 @@ def load() -> C.CDLL:
     lib.mtg_nl_descent_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, C.c_int, vp, dp, C.c_double,
                                          C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                          dp, dp, u32p, vp]
+    lib.mtg_collision_cost_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, vp, vp, C.c_double, vp, vp, C.c_double,
+                                             C.c_double, C.c_double, C.c_double, dp, dp, vp, vp, u32p, vp]
     lib.mtg_argmin_batch.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.c_int, vp, vp]
     lib.mtg_nccl_unique_id.argtypes = [vp, C.c_char_p]
     lib.mtg_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
@@ -619,6 +621,28 @@ class Context:
                                             _ptr(status), self._stream(MTG_MEM_DEVICE, stream))
         self._check(rc, "mtg_nl_descent_batch")
         return dict(coeffs=coeffs, history=hist, free=free, status=status)
+
+    def collision_cost_batch(self, coeffs, seg_times, grid, origin, res, min_bound, max_bound, dt, epsilon=0.5,
+                             robot_radius=0.5, multiplier=1.0, layout="soa", want_grad=True, stream=None):
+        """mtg_collision_cost_batch (CUDA tensors). grid: [nx,ny,nz] float64 CUDA tensor of distances (m).
+        Returns J_c [B], grad soa [3,K-1,NF,B] / aos [B,3,K-1,NF], in_collision, n_checks [B]."""
+        aos, B, K, D, N, mode, desc = self._desc_for(coeffs, layout)
+        NF = N // 2 - 1
+        size = (C.c_int32 * 3)(*[int(x) for x in grid.shape])
+        org = (C.c_int32 * 3)(*[int(x) for x in origin])
+        lo = (C.c_double * 3)(*[float(x) for x in min_bound])
+        hi = (C.c_double * 3)(*[float(x) for x in max_bound])
+        J = self._empty(coeffs, (B,))
+        grad = self._empty(coeffs, (B, 3, K - 1, NF) if aos else (3, K - 1, NF, B)) if want_grad else None
+        col = self._empty(coeffs, (B,), "u1")
+        chk = self._empty(coeffs, (B,), "i4")
+        status = self._empty(coeffs, (B,), "u4")
+        rc = self._lib.mtg_collision_cost_batch(self._h, C.byref(desc), _ptr(coeffs), _ptr(seg_times), _ptr(grid), size,
+                                                org, float(res), lo, hi, float(dt), float(epsilon), float(robot_radius),
+                                                float(multiplier), _ptr(J), _ptr(grad), _ptr(col), _ptr(chk),
+                                                _ptr(status), self._stream(mode, stream))
+        self._check(rc, "mtg_collision_cost_batch")
+        return dict(J_c=J, grad=grad, in_collision=col, n_checks=chk, status=status)
 
     # ------------------------------------------------------------- composition / I/O (N3)
     def vertex_at_time_batch(self, coeffs, seg_times, t, max_derivative_order, layout="soa", stream=None):

@@ -34,52 +34,14 @@ int launch_tm_t(mtg_ctx* ctx, const EvalParams& p, const double* geom, cudaStrea
   if (smem > 48 * 1024) MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (p.nb + per_block - 1) / per_block;
   if (grid == 0) return MTG_OK;
-  kern<<<grid, kTmBlock, smem, s>>>(p, geom, nullptr);
+  kern<<<grid, kTmBlock, smem, s>>>(p, geom);
   ++ctx->launches;
   MTG_CUDA_TRY(cudaGetLastError());
   return MTG_OK;
 }
 
-constexpr int kPlanChunk = 1 << 18;  // trajectories per plan + evaluation launch pair (bounds the descriptor scratch)
-
-// Two-kernel form of the position / derivative sweeps: eval_plan_kernel replays the sampling recurrence once per
-// trajectory into chunk descriptors, eval_tm_kernel<..., PLAN> evaluates them.
-template <int NT, int D, int MODE>
-int launch_tm_planned(mtg_ctx* ctx, const EvalParams& p_in, cudaStream_t s) {
-  EvalParams p = p_in;
-  const int c_max = tm_max_chunks(p.max_samples, p.K);
-  const int chunk = std::min(p_in.nb, kPlanChunk);
-  DeviceBuffer* scratch = ctx->scratch_for(s);
-  if (scratch->ensure((size_t)chunk * c_max * sizeof(TmDesc)))
-    return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of the sampling-plan scratch failed");
-  TmDesc* desc = (TmDesc*)scratch->ptr;
-  const size_t smem = (size_t)tm_layout(D, NT, false, false, tm_tpw(MODE), MODE, true).per_warp * (kTmBlock / 32);
-  auto kern = eval_tm_kernel<NT, D, MODE, true>;
-  if (smem > 48 * 1024) MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int per_block = (kTmBlock / 32) * tm_tpw(MODE);
-  for (int off = 0; off < p_in.nb; off += chunk) {
-    p.b0 = p_in.b0 + off;
-    p.nb = std::min(chunk, p_in.nb - off);
-    eval_plan_kernel<<<(p.nb + 127) / 128, 128, 0, s>>>(p, desc, c_max);
-    kern<<<(p.nb + per_block - 1) / per_block, kTmBlock, smem, s>>>(p, nullptr, desc);
-    ctx->launches += 2;
-    MTG_CUDA_TRY(cudaGetLastError());
-  }
-  return MTG_OK;
-}
-
 template <int NT, int MODE>
 int launch_tm_d(mtg_ctx* ctx, int D, const EvalParams& p, const double* geom, cudaStream_t s) {
-  // MTG_EVAL_FUSED=1 keeps the single-kernel form (A/B measurements)
-  static const bool fused = std::getenv("MTG_EVAL_FUSED") != nullptr;
-  if (MODE < 2 && !p.sampling_times && !fused) {
-    switch (D) {
-      case 1: return launch_tm_planned<NT, 1, MODE < 2 ? MODE : 0>(ctx, p, s);
-      case 2: return launch_tm_planned<NT, 2, MODE < 2 ? MODE : 0>(ctx, p, s);
-      case 3: return launch_tm_planned<NT, 3, MODE < 2 ? MODE : 0>(ctx, p, s);
-      case 4: return launch_tm_planned<NT, 4, MODE < 2 ? MODE : 0>(ctx, p, s);
-    }
-  }
   switch (D) {
     case 1: return launch_tm_t<NT, 1, MODE>(ctx, p, geom, s);
     case 2: return launch_tm_t<NT, 2, MODE>(ctx, p, geom, s);

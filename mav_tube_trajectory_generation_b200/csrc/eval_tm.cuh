@@ -62,17 +62,6 @@ __device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// bulk (TMA) store of a contiguous, 16-byte-aligned run of shared memory to global memory
-__device__ __forceinline__ void bulk_store(double* gdst, const double* smem_src, unsigned bytes) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_src);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-// the committed bulk stores have finished READING shared memory (the tile may be overwritten)
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
-// orders this thread's shared-memory writes before later async-proxy (bulk copy) reads
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
 // trajectory.cpp:88-111: first segment whose accumulated end time exceeds t_start; on
 // success acc is the START time of that segment, computed as (sum_{j<=i} T_j) - T_i like
 // the reference. false: t_start out of range (reference: LOG(ERROR) + empty result;
@@ -140,21 +129,13 @@ struct TmLayout {
 // 16 doubles the resident warps of the latency-bound position sweep; the fp64-bound feasibility
 // sweep prefers full phase-1 lanes (32).
 __host__ __device__ constexpr int tm_tpw(int mode) { return mode >= 2 ? 16 : 16; }
-__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, int kTmTPW, int mode,
-                                             bool bulk = false) {
+__host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, int kTmTPW, int mode) {
   const bool kTmTauBlk = tm_taublk(mode);
   TmLayout L;
   L.slot_bytes = D * NT * 8 + (tube ? kTubeGeomLd * 8 : 0);
   L.traj_bytes = 2 * L.slot_bytes + 16;
   L.blk_ld = kTmR * D + 1;
   L.row_ld = (kTmChunk / kTmR) * L.blk_ld;
-  if (bulk) {
-    // rows lie in shared memory exactly as in global memory (+ one double so that 16-byte-aligned global
-    // addresses are 16-byte aligned here too): a row leaves as ONE bulk copy. 32 D + 2 = 2 (mod 16) doubles
-    // keeps the four trajectories of a half-warp in different banks.
-    L.blk_ld = kTmR * D;
-    L.row_ld = kTmChunk * D + 2;
-  }
   L.off_dt = kTmTPW * (kTmTauBlk ? kTmBlkLd : kTmTauLd) * 8;
   L.off_stage = L.off_dt + (kTmTauBlk ? kTmTPW * 8 : 0);
   L.off_info = L.off_stage + kTmG * L.row_ld * 8;
@@ -168,152 +149,12 @@ __host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool
   return L;
 }
 
-// ---------------------------------------------------------------- the sampling PLAN (two-kernel form)
-// The serial part of evaluateRange — the recurrence acc += dt; tau += dt; tau -= T_i on a strict '>' crossing
-// (trajectory.cpp:114-133) — does not depend on the coefficients. eval_plan_kernel replays it ONCE per
-// trajectory with one thread per trajectory (32 busy lanes, no shared memory, ~8 instructions per sample) and
-// cuts the sample sequence into the same chunks the fused kernel forms (<= 32 samples, at most one crossing,
-// no 8-sample block straddling it), leaving one 48-byte descriptor per chunk: {samples, first row, first
-// segment, crossing position, tau of the four block starts}. The evaluation kernel then has NO serial phase:
-// its lanes read descriptors and run Horner chains. The descriptors cost 2 x 1.5 B per sample of extra HBM
-// traffic (written here, read there) against 24 B per sample of output; what they remove is 41 % of the
-// fused kernel's instructions, executed at half its lanes.
-struct TmDesc {
-  int cnt;     // samples of the chunk (0: the trajectory has ended; the last descriptor of every trajectory)
-  int n;       // index of the chunk's first sample in the trajectory
-  int seg0;    // segment of its first sample
-  int cross;   // samples [cross, cnt) lie in segment seg0 + 1 (kTmChunk: no crossing)
-  double tau[kTmChunk / 8];  // tau of the first sample of every 8-sample block
-};
-static_assert(sizeof(TmDesc) == 48, "descriptor layout");
-
-// chunks a trajectory can need: every chunk that is not full consumes a crossing or is the last one
-__host__ __device__ inline int tm_max_chunks(int max_samples, int K) { return max_samples / kTmChunk + K + 3; }
-
-__global__ void __launch_bounds__(128) eval_plan_kernel(const EvalParams p, TmDesc* __restrict__ desc, int c_max) {
-  constexpr int R = 8;
-  const int local = blockIdx.x * blockDim.x + threadIdx.x;
-  if (local >= p.nb) return;
-  const int b = p.b0 + local;
-  const int K = p.K;
-  const double* my_times = p.seg_times + (size_t)b * K;
-  uint32_t st = 0;
-  int n = 0, i = 0;
-  const double t0 = p.t_start[b], t1 = p.t_end[b], dt = p.dt[b];
-  double acc = 0.0, tau = 0.0, Ti = 0.0;
-  bool done = !locate_start<true>(p, b, t0, dt, i, acc);
-  if (done)
-    st |= 4u;
-  else
-    tau = t0 - acc;
-  for (int c = 0; c < c_max; ++c) {
-    int cnt = 0, seg0 = i, cross = kTmChunk;
-    double tb[kTmChunk / R] = {0.0, 0.0, 0.0, 0.0};
-    if (!done) {
-      Ti = my_times[i];
-      const int rows_left = p.max_samples - n;
-      int limit = min(kTmChunk, rows_left);
-      int mark = 0, blk = 0;  // next block-start sample, blocks parked so far
-      auto park = [&](double v) {
-        // blk is < 4 by construction; written without dynamic register indexing
-        if (blk == 0) tb[0] = v; else if (blk == 1) tb[1] = v; else if (blk == 2) tb[2] = v; else tb[3] = v;
-        ++blk;
-        mark += R;
-      };
-      for (;;) {
-        // straight runs inside the current segment: whole 8-sample blocks, then four samples, then one. The adds
-        // are the reference's, in its order; dt > 0 and rounding is monotone, so the last sample's two tests
-        // imply the others.
-        while (cnt + R <= limit && cnt == mark) {
-          double tk = tau, ak = acc;
-#pragma unroll
-          for (int j = 1; j < R; ++j) {
-            tk += dt;
-            ak += dt;
-          }
-          if (!((ak < t1) & !(tk > Ti))) break;
-          park(tau);
-          tau = tk + dt;
-          acc = ak + dt;
-          cnt += R;
-        }
-        while (cnt + 4 <= limit) {
-          const double tau1 = tau + dt, acc1 = acc + dt;
-          const double tau2 = tau1 + dt, acc2 = acc1 + dt;
-          const double tau3 = tau2 + dt, acc3 = acc2 + dt;
-          if (!((acc3 < t1) & !(tau3 > Ti))) break;
-          const int dm = mark - cnt;  // >= 0; blocks are 8 samples apart: at most one starts in this trip
-          if (dm < 4) park(dm == 0 ? tau : dm == 1 ? tau1 : dm == 2 ? tau2 : tau3);
-          tau = tau3 + dt;
-          acc = acc3 + dt;
-          cnt += 4;
-        }
-        while (cnt < limit && acc < t1 && !(tau > Ti)) {
-          if (cnt == mark) park(tau);
-          tau += dt;
-          acc += dt;
-          ++cnt;
-        }
-        if (!(acc < t1)) {
-          done = true;
-          break;
-        }
-        if (tau > Ti) {  // crossing: no sample emitted
-          tau = tau - Ti;
-          ++i;
-          if (i >= K) {
-            done = true;
-            break;
-          }
-          if (cnt == 0) {
-            seg0 = i;
-          } else if (i > seg0 + 1) {
-            break;  // a third segment: leave it to the next chunk
-          } else {
-            cross = cnt;
-            mark = cnt;  // segment B's blocks start at the crossing
-            limit = min(limit, cross + R * (kTmChunk / R - (cross + R - 1) / R));
-          }
-          Ti = my_times[i];
-          continue;
-        }
-        // cnt == limit
-        if (cnt >= rows_left) {  // out of output rows
-          st |= 8u;
-          done = true;
-        }
-        break;
-      }
-    }
-    TmDesc d;
-    d.cnt = cnt;
-    d.n = n;
-    d.seg0 = seg0;
-    d.cross = cross;
-#pragma unroll
-    for (int q = 0; q < kTmChunk / R; ++q) d.tau[q] = tb[q];
-    // chunk-major: the 16 trajectory lanes of an evaluation warp read 16 consecutive descriptors
-    int4* o = reinterpret_cast<int4*>(desc + ((size_t)c * p.nb + local));
-    o[0] = make_int4(d.cnt, d.n, d.seg0, d.cross);
-    reinterpret_cast<double2*>(o)[1] = make_double2(d.tau[0], d.tau[1]);
-    reinterpret_cast<double2*>(o)[2] = make_double2(d.tau[2], d.tau[3]);
-    n += cnt;
-    if (cnt == 0) break;
-  }
-  if (p.n_samples) p.n_samples[b] = n;
-  if (p.status) p.status[b] = st;
-}
-
 enum TmMode { TM_POSITION = 0, TM_DERIVATIVE = 1, TM_FEAS = 2, TM_FEAS_TUBE = 3 };
 
 // Requirements (checked by the launcher, which otherwise falls back to the one-thread-per-
 // trajectory kernels of eval.cuh): AoS layout, N == NT, coeffs 16-byte aligned.
-// PLAN: phase 1 is replaced by reading the descriptors of eval_plan_kernel (position / derivative sweeps
-// without sampling_times; n_samples and status are written by the plan kernel).
-template <int NT, int D, int MODE, bool PLAN = false>
-__global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom,
-                                                                                          const TmDesc* __restrict__ desc = nullptr) {
-  static_assert(!PLAN || MODE < 2, "the planned form exists for the position / derivative sweeps");
+template <int NT, int D, int MODE>
+__global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr bool FEAS = MODE >= TM_FEAS;
   constexpr bool tube = MODE == TM_FEAS_TUBE;
@@ -325,8 +166,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
   constexpr bool EXTRA = MODE == TM_DERIVATIVE;  // sampling_times / segment_idx outputs exist in this mode only
   const bool want_acc = EXTRA && p.sampling_times != nullptr;
   constexpr bool kTmTauBlk = tm_taublk(MODE);
-  constexpr bool BULK = PLAN;  // the planned kernel hands its rows to the copy engine
-  const TmLayout L = tm_layout(D, NT, want_acc, tube, kTmTPW, MODE, BULK);
+  const TmLayout L = tm_layout(D, NT, want_acc, tube, kTmTPW, MODE);
   unsigned char* wbase = tm_smem + (size_t)warp * L.per_warp;
   double* tau_s = reinterpret_cast<double*>(wbase);
   double* stage = reinterpret_cast<double*>(wbase + L.off_stage);
@@ -358,29 +198,12 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
   int n = 0, i = 0;
   const double t0 = p.t_start[b], t1 = p.t_end[b], dt = p.dt[b];
   double acc = 0.0, tau = 0.0, Ti = 0.0;
-  bool done = false;
-  TmDesc nd;  // PLAN: the descriptor of the NEXT chunk (read one chunk ahead: it names the segments to prefetch)
-  nd.cnt = 0; nd.n = 0; nd.seg0 = 0; nd.cross = kTmChunk;
-  auto read_desc = [&](int c) {
-    const int4* src = reinterpret_cast<const int4*>(desc + ((size_t)c * p.nb + local));
-    const int4 a = __ldg(src);
-    const double2 t01 = __ldg(reinterpret_cast<const double2*>(src) + 1);
-    const double2 t23 = __ldg(reinterpret_cast<const double2*>(src) + 2);
-    nd.cnt = a.x; nd.n = a.y; nd.seg0 = a.z; nd.cross = a.w;
-    nd.tau[0] = t01.x; nd.tau[1] = t01.y; nd.tau[2] = t23.x; nd.tau[3] = t23.y;
-  };
-  if (PLAN) {
-    if (valid) read_desc(0);
-    done = !valid || nd.cnt == 0;
-    i = nd.seg0;
-  } else {
-    done = !locate_start<true>(p, b, t0, dt, i, acc);
-    if (done)
-      st |= 4u;
-    else
-      tau = t0 - acc;
-    if (!valid) done = true;
-  }
+  bool done = !locate_start<true>(p, b, t0, dt, i, acc);
+  if (done)
+    st |= 4u;
+  else
+    tau = t0 - acc;
+  if (!valid) done = true;
   if (kTmTauBlk && lane < kTmTPW) dt_s[lane] = dt;
   double mv2 = 0.0, ma2 = 0.0;  // FEAS: running maxima of |v|^2, |a|^2 (lane = trajectory)
   unsigned all_bits = 7u;
@@ -431,22 +254,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
     // ------------------------------------------------ phase 1: trajectory.cpp:114-133
     cp_async_wait_group1();
     int cnt = 0, seg0 = i, cross = kTmChunk;  // samples [cross, cnt) lie in segment seg0 + 1
-    if (PLAN) {
-      if (!done) {
-        // this chunk = the descriptor read one chunk ago; its segments were prefetched then. Records carried by
-        // the newest commit group are not retired by wait_group 1: wait for them when they are needed now.
-        cnt = nd.cnt; n = nd.n; seg0 = nd.seg0; cross = nd.cross;
-        double* trow = tau_s + lane * TAU_LD;
-#pragma unroll
-        for (int q = 0; q < kTmChunk / R; ++q) trow[q] = nd.tau[q];
-        const bool needB = cross < cnt;
-        const int ageA = (seg0 & 1) ? age1 : age0, ageB = ((seg0 + 1) & 1) ? age1 : age0;
-        if (ageA >= chunk - 1 || (needB && ageB >= chunk - 1)) cp_async_wait_all();
-        // the descriptor of the NEXT chunk (chunk counts from 1 here) is requested now and first looked at after
-        // phase 2: its DRAM latency hides behind this chunk's evaluation
-        read_desc(chunk);
-      }
-    } else if (!done) {
+    if (!done) {
       Ti = duration(i);
       const int rows_left = p.max_samples - n;
       int limit = min(kTmChunk, rows_left);
@@ -606,13 +414,6 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
       double v2m = 0.0, a2m = 0.0;
       unsigned fand = 7u;
       double* srow = stage + q8 * L.row_ld;
-      // BULK: the row is staged with the parity of its global address (even doubles are 16-byte aligned on both sides)
-      const int sh = (BULK && p.samples) ? (int)(((uintptr_t)(p.samples + off_s[r] * D) >> 3) & 1) : 0;
-      if (BULK) {
-        // the previous pass's bulk copies must have read the tile before it is overwritten
-        if (lane < G) bulk_wait_read();
-        __syncwarp();
-      }
       // JB samples advance together, one Horner step at a time: JB*D (position) or 3*JB*D
       // (feasibility) independent FMA chains cover the fp64 pipe latency from a single warp.
       constexpr int JB = FEAS ? 4 : R;
@@ -716,7 +517,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
           const int k = start + j0 + j;
           if (j0 + j < count) {
 #pragma unroll
-            for (int dim = 0; dim < D; ++dim) srow[k * D + (BULK ? sh : (k >> 3)) + dim] = x[j][dim];
+            for (int dim = 0; dim < D; ++dim) srow[k * D + (k >> 3) + dim] = x[j][dim];
           }
         }
       }
@@ -737,34 +538,14 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
           all_bits &= of;
         }
       }
-      if (BULK) fence_proxy_async_smem();
       __syncwarp();
-      if (BULK && p.samples && lane < G) {
-        // staged rows -> global memory: lane t hands row t to the copy engine as ONE bulk copy of its
-        // 16-byte-aligned body; an odd first / last double is stored directly
-        const int total = cnt_s[g * G + lane] * D;
-        if (total > 0) {
-          double* out = p.samples + off_s[g * G + lane] * D;
-          const int odd = (int)(((uintptr_t)out >> 3) & 1);
-          const double* row = stage + lane * L.row_ld + odd;  // element e of the row lies at row[e]
-          int e1 = total;
-          if ((odd + total) & 1) {
-            --e1;
-            out[e1] = row[e1];
-          }
-          if (odd) out[0] = row[0];
-          if (e1 > odd) bulk_store(out + odd, row + odd, (unsigned)(e1 - odd) * 8u);
-        }
-        bulk_commit();
-      }
       // staged rows -> global memory: whole consecutive 256-byte stores per trajectory
       // (cnt == 0 rows fall out through the predicates; everything else is branch-free)
-      if (!BULK || EXTRA)
 #pragma unroll
       for (int t = 0; t < G; ++t) {
         const int cnt_t = cnt_s[g * G + t];
         const size_t o = off_s[g * G + t];
-        if (!BULK && p.samples) {
+        if (p.samples) {
           double* out = p.samples + o * D + lane;
           const double* row = stage + t * L.row_ld;
           const int total = cnt_t * D;
@@ -785,10 +566,6 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
       __syncwarp();
     }
     n += cnt;
-    if (PLAN && !done) {
-      if (nd.cnt == 0) done = true;
-      i = nd.seg0;
-    }
     // every sample emitted so far has been evaluated: both slots may be re-targeted.
     // Prefetch the current and the next segment (no-ops while they are resident).
     if (!done) {
@@ -798,8 +575,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
     cp_async_commit();
   }
   cp_async_wait_all();
-  if (BULK && lane < G) bulk_wait_read();  // shared memory must outlive the bulk reads
-  if (valid && !PLAN) {  // PLAN: written by eval_plan_kernel
+  if (valid) {
     if (p.n_samples) p.n_samples[b] = n;
     if (p.status) p.status[b] = st;
     if (FEAS) {

@@ -218,10 +218,7 @@ __device__ __forceinline__ void chol_solve(const double (&L)[NF][NF], const doub
   }
 }
 
-// EMIT = false: the chain solve alone — d_p goes to p.free_constraints (required) and the coefficient / cost
-// epilogue runs as a second, embarrassingly parallel kernel (coeffs_from_free_kernel, cost_fd.cuh) at several
-// times this kernel's occupancy; K >= 2 only.
-template <int HN, int D, bool AOS, int DT = -1, bool EMIT = true>
+template <int HN, int D, bool AOS, int DT = -1>
 __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCanonicalParams p) {
   constexpr int N = 2 * HN;
   constexpr int NF = HN - 1;               // free derivatives per interior vertex
@@ -474,11 +471,11 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
 
   // ---------------------------------------------------------------- backward
   double xs[D][HN];
-  double T_back = EMIT ? p.seg_times[at<AOS>((size_t)SG(n_own), rec_t, B, b)] : 1.0;  // requested one step ahead, as above
+  double T_back = p.seg_times[at<AOS>((size_t)SG(n_own), rec_t, B, b)];  // requested one step ahead, as above
 #pragma unroll 1
-  for (int c = n_own; c >= (EMIT ? 0 : 1); --c) {
-    const double T = EMIT ? checked_time(T_back) : 1.0;
-    if (EMIT && c > 0) T_back = p.seg_times[at<AOS>((size_t)SG(c - 1), rec_t, B, b)];
+  for (int c = n_own; c >= 0; --c) {
+    const double T = checked_time(T_back);
+    if (c > 0) T_back = p.seg_times[at<AOS>((size_t)SG(c - 1), rec_t, B, b)];
     if (c == 0) {
 #pragma unroll
       for (int dim = 0; dim < D; ++dim)
@@ -528,7 +525,7 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
         ds[dim][mm] = side ? e : a;
         de[dim][mm] = side ? a : e;
       }
-    if (EMIT) cost_acc += emit_segment<HN, D, AOS, DT>(p, SG(c), b, active, T, ds, de);
+    cost_acc += emit_segment<HN, D, AOS, DT>(p, SG(c), b, active, T, ds, de);
 #pragma unroll
     for (int dim = 0; dim < D; ++dim)
 #pragma unroll
@@ -537,7 +534,7 @@ __global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCano
   cost_acc += __shfl_xor_sync(FULL, cost_acc, 1);
   st |= __shfl_xor_sync(FULL, st, 1);
   if (active && side == 0) {
-    if (EMIT && p.cost) p.cost[b] = 0.5 * cost_acc;
+    if (p.cost) p.cost[b] = 0.5 * cost_acc;
     if (p.status) p.status[b] = st;
   }
 }

@@ -4,7 +4,6 @@
 
 #include "host_common.h"
 #include "solve_canonical.cuh"
-#include "cost_fd.cuh"  // coeffs_from_free_kernel: the coefficient / cost epilogue of the split solve
 
 namespace mtg {
 namespace solve_launch {
@@ -35,39 +34,12 @@ int launch_solve_canonical_dt(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, 
     return fail(ctx, MTG_ERR_UNSUPPORTED,
                 "solve_canonical: K too large for the shared-memory sweep state; use mtg_solve_generic_batch");
   const size_t smem = per_thread * block;
-  const long long threads = 2LL * p.nb;
-  const int grid = (int)((threads + block - 1) / block);
-  if (grid == 0) return MTG_OK;
-  // Split form (default for K >= 2): the chain solve writes d_p only, the coefficients and the cost come from the
-  // epilogue kernel. MTG_SOLVE_FUSED=1 keeps everything in the chain kernel (A/B measurements).
-  static const bool fused = std::getenv("MTG_SOLVE_FUSED") != nullptr;
-  if (K >= 2 && !fused) {
-    mtg::SolveCanonicalParams q = p;
-    if (!q.free_constraints) {  // d_p is not wanted by the caller: park it in the stream's work space
-      DeviceBuffer* ws = ctx->nl_scratch_for(stream, 2);
-      if (ws->ensure((size_t)p.B * D * (K - 1) * NF * sizeof(double)))
-        return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of the d_p work space failed");
-      q.free_constraints = (double*)ws->ptr;
-    }
-    auto chain = mtg::solve_canonical_kernel<HN, D, AOS, DT, false>;
-    if (smem > 48 * 1024) MTG_CUDA_TRY(cudaFuncSetAttribute(chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
-    chain<<<grid, block, smem, stream>>>(q);
-    ++ctx->launches;
-    MTG_CUDA_TRY(cudaGetLastError());
-    if (p.coeffs || p.cost) {
-      mtg::CostFdParams f = {};
-      f.positions = p.positions; f.end_derivatives = p.end_derivatives; f.seg_times = p.seg_times;
-      f.free_constraints = q.free_constraints; f.status = nullptr;  // the chain kernel owns the status word
-      f.B = p.B; f.b0 = p.b0; f.nb = p.nb; f.K = K; f.derivative = p.derivative;
-      mtg::coeffs_from_free_kernel<HN, D, AOS><<<(p.nb + 127) / 128, 128, 0, stream>>>(f, p);
-      ++ctx->launches;
-      MTG_CUDA_TRY(cudaGetLastError());
-    }
-    return MTG_OK;
-  }
   auto kern = mtg::solve_canonical_kernel<HN, D, AOS, DT>;
   if (smem > 48 * 1024)  // per device and per instantiation; a cheap host-side call
     MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
+  const long long threads = 2LL * p.nb;
+  const int grid = (int)((threads + block - 1) / block);
+  if (grid == 0) return MTG_OK;
   kern<<<grid, block, smem, stream>>>(p);
   ++ctx->launches;
   MTG_CUDA_TRY(cudaGetLastError());

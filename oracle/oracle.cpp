@@ -1267,6 +1267,119 @@ int mtgo_soft_constraint_gradient(int N, int D, int K, int derivative, const dou
   return 0;
 }
 
+// N4  NL_I:1608-1780 getCostAndGradientCollision with getCostAndGradientPotentialOctree (:1783-1917) and
+// getCostPotential (:2659-2684); the octree distance (:1920-2043) is replaced by a lookup in a dense grid of
+// distances [nx][ny][nz] (metres) whose element [0][0][0] is voxel `origin`. Canonical constraint pattern: the free
+// derivative (v, k), v = 1..K-1, k = 1..h-1, is row h + k of segment v-1 and row k of segment v of C.
+// grad [3][(K-1)(h-1)] (free_constraints order) or NULL. Like the reference, a collision returns J_c = 0 and keeps
+// the gradient accumulated so far (its zeroing loop iterates by value, NL_I:1774-1778).
+static double potential_cost(double distance, double epsilon, double robot_radius, double multiplier, bool* collision) {
+  *collision = false;
+  double cost = 0.0;
+  distance -= robot_radius;
+  if (distance <= 0.0) {
+    cost = multiplier * (-distance) + 0.5 * epsilon;
+    *collision = true;
+  } else if (distance <= epsilon) {
+    const double e = distance - epsilon;
+    cost = 0.5 * 1.0 / epsilon * e * e;
+  }
+  return cost;
+}
+
+int mtgo_collision_cost(int N, int K, const double* coeffs, const double* times, const double* grid,
+                        const int* size, const int* origin, double res, const double* min_bound,
+                        const double* max_bound, double dt, double epsilon, double robot_radius, double multiplier,
+                        double* J_c, double* grad, int* in_collision, int* n_checks) {
+  const int D = 3, h = N / 2, NF = h - 1;
+  auto dist_at = [&](int vx, int vy, int vz) {
+    const int ix = vx - origin[0], iy = vy - origin[1], iz = vz - origin[2];
+    if (ix < 0 || iy < 0 || iz < 0 || ix >= size[0] || iy >= size[1] || iz >= size[2])
+      return std::numeric_limits<double>::max();  // no occupied voxel in reach (getDistanceOctree: DBL_MAX * res)
+    return grid[(static_cast<size_t>(ix) * size[1] + iy) * size[2] + iz];
+  };
+  const int n_free = (K - 1) * NF;
+  if (grad) for (int e = 0; e < D * n_free; ++e) grad[e] = 0.0;
+  double J = 0.0;
+  bool collided = false;
+  int checks = 0;
+  double prev[3] = {0, 0, 0};
+  double time_sum = -1, dist_sum = 0.0, t = 0.0;
+  Vec A(static_cast<size_t>(N) * N), Ainv(static_cast<size_t>(N) * N), T(N);
+  for (int i = 0; i < K; ++i) {
+    setup_mapping_matrix(N, times[i], A.data());
+    invert_mapping_matrix(N, A.data(), Ainv.data());
+    for (t = 0.0; t < times[i]; t += dt) {
+      for (int n = 0; n < N; ++n) T[n] = std::pow(t, n);
+      double pos[3], vel[3];
+      for (int k = 0; k < D; ++k) {
+        const double* pk = coeffs + (static_cast<size_t>(i) * D + k) * N;
+        pos[k] = 0.0;
+        vel[k] = 0.0;
+        for (int n = 0; n < N; ++n) pos[k] += T[n] * pk[n];
+        for (int n = 0; n + 1 < N; ++n) vel[k] += T[n] * ((n + 1) * pk[n + 1]);
+      }
+      if (time_sum < 0) {
+        time_sum = 0.0;
+        for (int k = 0; k < 3; ++k) prev[k] = pos[k];
+        continue;
+      }
+      time_sum += dt;
+      dist_sum += std::sqrt((pos[0] - prev[0]) * (pos[0] - prev[0]) + (pos[1] - prev[1]) * (pos[1] - prev[1]) +
+                            (pos[2] - prev[2]) * (pos[2] - prev[2]));
+      for (int k = 0; k < 3; ++k) prev[k] = pos[k];
+      if (dist_sum < res) continue;
+      ++checks;
+      bool valid = true;
+      for (int k = 0; k < 3; ++k)
+        if (pos[k] < min_bound[k] + res || pos[k] > max_bound[k] - res) valid = false;
+      const int v[3] = {static_cast<int>(pos[0] / res), static_cast<int>(pos[1] / res), static_cast<int>(pos[2] / res)};
+      bool hit = false;
+      const double c = potential_cost(valid ? dist_at(v[0], v[1], v[2]) : 0.0, epsilon, robot_radius, multiplier, &hit);
+      if (hit) {
+        collided = true;
+        break;
+      }
+      const double nv = std::sqrt(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
+      J += c * nv * time_sum;
+      if (grad && nv > 1e-6) {
+        double gc[3];
+        for (int k = 0; k < 3; ++k) {
+          bool d1, d2;
+          const double left = potential_cost(dist_at(v[0] - (k == 0), v[1] - (k == 1), v[2] - (k == 2)), epsilon,
+                                             robot_radius, multiplier, &d1);
+          const double right = potential_cost(dist_at(v[0] + (k == 0), v[1] + (k == 1), v[2] + (k == 2)), epsilon,
+                                              robot_radius, multiplier, &d2);
+          gc[k] = (right - left) / (2.0 * res);
+        }
+        // T_all_seg^T L_pp and T_all_seg^T V_all L_pp: only the free derivatives of vertices i and i + 1
+        for (int side = 0; side < 2; ++side) {
+          const int vtx = i + side;
+          if (vtx < 1 || vtx > K - 1) continue;
+          for (int kk = 1; kk < h; ++kk) {
+            const int row = side == 0 ? kk : h + kk;  // local row of this segment
+            double TL = 0.0, TVL = 0.0;
+            for (int n = 0; n < N; ++n) TL += T[n] * Ainv[n * N + row];
+            for (int n = 0; n + 1 < N; ++n) TVL += T[n] * ((n + 1) * Ainv[(n + 1) * N + row]);
+            for (int k = 0; k < D; ++k)
+              grad[static_cast<size_t>(k) * n_free + (vtx - 1) * NF + (kk - 1)] +=
+                  nv * time_sum * gc[k] * TL + time_sum * c * vel[k] / nv * TVL;
+          }
+        }
+      }
+      dist_sum = 0.0;
+      time_sum = 0.0;
+      for (int k = 0; k < 3; ++k) prev[k] = pos[k];
+    }
+    if (collided) break;
+    time_sum += -dt + (times[i] - t);
+  }
+  *J_c = collided ? 0.0 : J;
+  if (in_collision) *in_collision = collided ? 1 : 0;
+  if (n_checks) *n_checks = checks;
+  return 0;
+}
+
 int mtgo_has_reference_rpoly(void) {
 #ifdef MTG_ORACLE_NO_RPOLY
   return 0;

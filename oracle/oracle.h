@@ -201,6 +201,14 @@ int mtgo_soft_constraint_gradient(int N, int D, int K, int derivative, const dou
                                   const double* limits, double weight, double max_cost, double increment,
                                   int central, double* J_sc, double* grad);
 
+/* N4  NL_I:1608-1780, 1783-1917, 2659-2684: collision potential along the trajectory against a dense grid of
+ * distances [size0][size1][size2] (metres; element [0][0][0] is voxel `origin`), canonical constraint pattern.
+ * grad [3][(K-1)(N/2-1)] or NULL. */
+int mtgo_collision_cost(int N, int K, const double* coeffs, const double* times, const double* grid,
+                        const int* size, const int* origin, double res, const double* min_bound,
+                        const double* max_bound, double dt, double epsilon, double robot_radius, double multiplier,
+                        double* J_c, double* grad, int* in_collision, int* n_checks);
+
 /* N3  NL_I:2907-3003: the sampled dump [t, pos, vel, acc, jerk, snap, tm] as a max_rows x (5 D + 2) matrix. */
 int mtgo_sample_dump(int N, int D, int K, const double* coeffs, const double* times, double dt, int max_rows,
                      double* rows);

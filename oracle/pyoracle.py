@@ -495,3 +495,24 @@ def soft_constraint_gradient(N, derivative, times, mask, values, d_p, ders, limi
     if rc:
         raise ValueError(rc)
     return J.value, (g.reshape(D, -1) if want_grad else None)
+
+
+# ------------------------------------------------------------------ N4 collision potential
+def collision_cost(coeffs, times, grid, origin, res, min_bound, max_bound, dt, epsilon=0.5, robot_radius=0.5,
+                   multiplier=1.0, want_grad=True):
+    """NL_I:1608-1780 on a dense distance grid -> (J_c, grad [3, (K-1)*NF] or None, in_collision, n_checks)."""
+    coeffs = _f64(coeffs)
+    times = _f64(times)
+    grid = _f64(grid)
+    K, D, N = coeffs.shape
+    assert D == 3
+    size = np.ascontiguousarray(grid.shape, dtype=np.int32)
+    org = np.ascontiguousarray(origin, dtype=np.int32)
+    J = C.c_double(0.0)
+    g = np.zeros(3 * (K - 1) * (N // 2 - 1))
+    col, chk = C.c_int(0), C.c_int(0)
+    lib().mtgo_collision_cost(N, K, _d(coeffs), _d(times), _d(grid), size.ctypes.data_as(_ip), org.ctypes.data_as(_ip),
+                              C.c_double(res), _d(_f64(min_bound)), _d(_f64(max_bound)), C.c_double(dt),
+                              C.c_double(epsilon), C.c_double(robot_radius), C.c_double(multiplier), C.byref(J),
+                              _d(g) if want_grad else None, C.byref(col), C.byref(chk))
+    return J.value, (g.reshape(3, -1) if want_grad else None), bool(col.value), chk.value
