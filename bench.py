@@ -414,6 +414,75 @@ def time_alloc_section(ctx):
     return out
 
 
+def extras_section(ctx, peak):
+    """The other entry points of the path, each timed on its own (CUDA events, 3 warm-ups, median of 5): the generic
+    constraint-pattern solve, the non-linear objective (N1), control points + corridor constraints (N2) and the
+    collision potential (N4). Sizes: 65,536 / 4,096 trajectories of the configs[1] shape."""
+    import torch
+
+    def med(fn, reps=5, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        return sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))[reps // 2] * 1e-3
+
+    out = {}
+    B = BATCH_PER_GPU
+    pos, times = make_workload(B, seed=21)
+    p, t = torch.from_numpy(pos).cuda(), torch.from_numpy(times).cuda()
+    # generic pattern solve on the canonical mask (what the class API's solveLinear() uses for other patterns)
+    h = NCOEF // 2
+    mask = np.zeros((K_SEG + 1, h), dtype=np.uint8)
+    mask[:, 0] = 1
+    mask[0, :] = 1
+    mask[-1, :] = 1
+    values = torch.zeros((K_SEG + 1, h, DIM, B), dtype=torch.float64, device="cuda")
+    values[:, 0] = p
+    secs = med(lambda: ctx.solve_generic_batch(mask, values, t))
+    out["solve_generic"] = {"value": B / secs, "unit": "trajectories/s", "ms": secs * 1e3,
+                            "frac_of_hbm": BYTES_PER_TRAJ * B / secs / 1e9 / peak,
+                            "note": "solve_generic_kernel, canonical mask, 65,536 problems"}
+    # N1 on 4,096 trajectories (AoS): one objective evaluation = coefficients of d_p + J_d with its analytic
+    # gradient + J_sc with its central finite-difference gradient (2 x 108 perturbed 2-segment root problems x 2)
+    Bn = 4096
+    pa = torch.from_numpy(np.ascontiguousarray(np.moveaxis(pos[..., :Bn], -1, 0))).cuda()
+    ta = torch.from_numpy(np.ascontiguousarray(np.moveaxis(times[..., :Bn], -1, 0))).cuda() * 0.7
+    sol = ctx.solve_batch(pa, ta, want_free=True, layout="aos")
+    ders, lims = [1, 2], [3.0, 5.0]
+
+    def objective():
+        c = ctx.set_free_constraints_batch(pa, ta, sol["free"], layout="aos")
+        ctx.cost_derivative_batch(pa, ta, sol["free"], layout="aos")
+        ctx.soft_constraint_gradient_batch(c["coeffs"], ta, ders, lims, 5.0, 1e12, 0.05)
+
+    secs = med(objective)
+    out["nl_objective"] = {"value": Bn / secs, "unit": "objective + gradient evaluations/s", "ms": secs * 1e3,
+                           "root_problems_per_evaluation": 2 * (K_SEG + 2 * 2 * DIM * (K_SEG - 1) * (h - 1) * 2),
+                           "note": "4,096 trajectories: J_d + analytic gradient, J_sc + central FD gradient (NL_I:1537-1606, 2365-2423)"}
+    x = sol["free"].clone()
+    iters = 10
+    secs = med(lambda: ctx.nl_descent_batch(pa, ta, x, ders, lims, soft_weight=5.0, increment=0.05, step=0.5,
+                                            iterations=iters, want_history=False), reps=3, warm=1)
+    out["nl_descent"] = {"value": Bn * iters / secs, "unit": "trajectory-iterations/s", "ms_per_iteration": secs * 1e3 / iters}
+    # N2 / N4 on the 65,536 batch
+    solb = ctx.solve_batch(p, t)
+    radii = torch.full((K_SEG, 2, B), 1.0, dtype=torch.float64, device="cuda")
+    secs = med(lambda: ctx.control_points_batch(t, coeffs=solb["coeffs"], positions=p, radii=radii))
+    out["control_points"] = {"value": B / secs, "unit": "trajectories/s", "ms": secs * 1e3}
+    g = torch.full((120, 120, 120), 3.0, dtype=torch.float64, device="cuda")
+    secs = med(lambda: ctx.collision_cost_batch(solb["coeffs"], t, g, [-60, -60, -60], 0.2, [-11.0] * 3, [11.0] * 3, 0.1,
+                                                epsilon=4.0, robot_radius=0.3))
+    out["collision_cost"] = {"value": B / secs, "unit": "trajectories/s", "ms": secs * 1e3,
+                             "note": "dt 0.1 s, map resolution 0.2 m, potential active everywhere (epsilon 4 m), with gradient"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -617,6 +686,7 @@ def main():
         if world == 1 and not args.no_sweep:
             line["sweep"] = sweep_section(ctx, peak, args.sweep_batch)
             line["time_alloc"] = time_alloc_section(ctx)
+            line["extras"] = extras_section(ctx, peak)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = 32768

@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
       if (valid) {
         const double* pk = s_pk + q * S;
         fu = fv = pk[deg];
+#pragma unroll 4
         for (int j = deg - 1; j >= 0; --j) {
           const double c = pk[j];
           fu = fma(fu, u, c);
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
         // p and p' by the coupled Horner recurrence, err = sum |c_j| |t|^j
         double ft = pk[deg], dft = 0.0, err = fabs(ft);
         const double at = fabs(t);
+#pragma unroll 4
         for (int j = deg - 1; j >= 0; --j) {
           const double c = pk[j];
           dft = fma(dft, t, ft);
