@@ -404,9 +404,11 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
           rcur = (s_par[q] ? s_ra : s_rb) + q * S;
           a = qi > 0 ? rprev[qi - 1] : s_lo[q];
           bb = qi < na ? rprev[qi] : s_hi[q];
-          // roots of the upper levels only PARTITION the interval for the level below: 1e-12 of its length is
-          // plenty; the roots of g itself (deg = n) go to 1e-15 of the length (a few ulp of a mid-interval time)
-          tol = ((s_n[q] > deg) ? 1e-12 : 1e-15) * (s_hi[q] - s_lo[q]);
+          // roots of the upper levels only PARTITION the interval for the level below: 1e-9 of its length is
+          // plenty (a partition point off by delta can only hide a root pair closer than delta, i.e. a bump of
+          // the magnitude of relative height ~delta^2); the roots of g itself (deg = n) go to 1e-15 of the
+          // length (a few ulp of a mid-interval time)
+          tol = ((s_n[q] > deg) ? 1e-9 : 1e-15) * (s_hi[q] - s_lo[q]);
           // bracket narrower than tol or than fp64 can resolve anywhere in the interval
           wmin = fmax(tol, 4.5e-16 * fmax(fabs(s_lo[q]), fabs(s_hi[q])));
           pk = s_pk + q * S;
