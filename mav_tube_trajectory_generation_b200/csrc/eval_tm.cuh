@@ -189,20 +189,9 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
 
   const size_t traj_off = (size_t)(p.b0 + local) * S;  // first output row of this lane's trajectory
   const int q8 = lane >> 2, sb = lane & 3;  // phase-2 role: trajectory within the pass, block within the trajectory
-  // Row copy in PHYSICAL order: lane reads word lane + 32 q of a staged row (consecutive words: conflict free —
-  // reading in logical order skips the pad after every 8-sample block and made two lanes of a half-warp share a
-  // bank in two reads out of three) and stores it at its logical position; the pad words are skipped.
-#ifndef MTG_TM_PHYSCOPY
-#define MTG_TM_PHYSCOPY 1  // 0: logical-order row copy (A/B builds only)
-#endif
-  constexpr int NQ = MTG_TM_PHYSCOPY ? ((kTmChunk / R) * (R * D + 1) + 31) / 32 : D;  // 32-word pieces of a staged row
-  int elem[NQ];  // logical element of physical word lane + 32 q, or -1 for a pad / beyond the row
+  int skew[D];  // staging-tile position of element lane + 32 q of a trajectory row
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const int w = lane + 32 * q, blk = w / (R * D + 1), in = w - blk * (R * D + 1);
-    elem[q] = (in < R * D && blk < kTmChunk / R) ? blk * (R * D) + in : -1;
-    if (!MTG_TM_PHYSCOPY) elem[q] = w + w / (R * D);  // logical order: the staged position of element w
-  }
+  for (int q = 0; q < D; ++q) skew[q] = (lane + 32 * q) + (lane + 32 * q) / (R * D);
 
   // ---- phase-1 state (lane = trajectory)
   uint32_t st = 0;
@@ -557,17 +546,12 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
         const int cnt_t = cnt_s[g * G + t];
         const size_t o = off_s[g * G + t];
         if (p.samples) {
-          double* out = p.samples + o * D;
-          const double* row = stage + t * L.row_ld + lane;
+          double* out = p.samples + o * D + lane;
+          const double* row = stage + t * L.row_ld;
           const int total = cnt_t * D;
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) {
-            if (MTG_TM_PHYSCOPY) {
-              if (elem[q] >= 0 && elem[q] < total) out[elem[q]] = row[32 * q];
-            } else {
-              if (lane + 32 * q < total) out[lane + 32 * q] = row[elem[q] - lane];
-            }
-          }
+          for (int q = 0; q < D; ++q)
+            if (lane + 32 * q < total) out[32 * q] = row[skew[q]];
         }
         if (FEAS) {
           if (p.flags && lane < cnt_t) p.flags[o + lane] = flag_s[t * 40 + lane];
