@@ -207,10 +207,8 @@ def sweep_section(ctx, peak, batch=None, time_it=True):
 
     B = batch or SWEEP_BATCH
     S = SWEEP_SAMPLES
-    pos, times = make_workload(B, seed=4)
-    pos = np.ascontiguousarray(np.moveaxis(pos, -1, 0))
-    times = np.ascontiguousarray(np.moveaxis(times, -1, 0))
-    p, t = torch.from_numpy(pos).cuda(), torch.from_numpy(times).cuda()
+    # candidates generated on the device (Philox keyed by the candidate index): no 344 MB host copy
+    p, t = ctx.generate_candidates_batch(B, K_SEG, DIM, seed=0xB200, layout="aos")
     sol = ctx.solve_batch(p, t, layout="aos")
     tmax = ctx.max_time_batch(t, layout="aos")
     dt = tmax / S

@@ -448,6 +448,19 @@ int mtg_soft_constraint_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const 
                               const double* limits, double weight, double maximum_cost, double* cost,
                               double* violations, uint32_t* status, void* stream);
 
+/* ------------------------------------------- candidate generator of a sweep (G1 on the device)
+ * mtg_generate_candidates_batch: createRandomVertices [src/vertex.cpp:27-82] (uniform positions in
+ * [pos_min, pos_max] per dimension, resampled until |pos - last| > 0.2, :65-72) + estimateSegmentTimesNfabian
+ * [:252-269] for B candidates, written straight into device tensors positions [K+1][D] / seg_times [K].
+ * The reference's std::mt19937 is serial; a sharded sweep needs a counter-based generator: Philox4x32-10, key =
+ * seed, counter = (candidate index first_index + b, draw number, block) — candidate b is identical on every
+ * rank and for every batch split; draw n yields the D uniforms of one attempt (53-bit, u0 = words 0,1 of block 0,
+ * u1 = words 2,3, u2 / u3 from block 1), position = pos_min + u * (pos_max - pos_min) (multiply, then add).
+ * pos_min / pos_max: HOST arrays [D]. magic_fabian_constant: 6.5 in the reference (vertex.h:128). */
+int mtg_generate_candidates_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, uint64_t seed, int64_t first_index,
+                                  const double* pos_min, const double* pos_max, double v_max, double a_max,
+                                  double magic_fabian_constant, double* positions, double* seg_times, void* stream);
+
 /* ------------------------------------------- candidate sweep: argmin of computeCost()
  * The reference picks the best of many candidate trajectories on the host, one
  * computeCost() [LIN_I:113-130] at a time (e.g. the random restarts of

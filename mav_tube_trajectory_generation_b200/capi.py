@@ -90,6 +90,8 @@ def load() -> C.CDLL:
                                          dp, dp, u32p, vp]
     lib.mtg_collision_cost_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, vp, vp, C.c_double, vp, vp, C.c_double,
                                              C.c_double, C.c_double, C.c_double, dp, dp, vp, vp, u32p, vp]
+    lib.mtg_generate_candidates_batch.argtypes = [vp, C.POINTER(ProblemDesc), C.c_uint64, C.c_int64, vp, vp, C.c_double,
+                                                  C.c_double, C.c_double, dp, dp, vp]
     lib.mtg_argmin_batch.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.c_int, vp, vp]
     lib.mtg_nccl_unique_id.argtypes = [vp, C.c_char_p]
     lib.mtg_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
@@ -327,6 +329,24 @@ class Context:
                                               _ptr(status), self._stream(mode, stream))
         self._check(rc, "mtg_cost_time_fd_batch")
         return dict(J=J, J_plus=Jp, J_minus=Jm, grad=grad, status=status)
+
+    def generate_candidates_batch(self, B, K, D, seed, first_index=0, pos_min=-10.0, pos_max=10.0, v_max=3.0, a_max=5.0,
+                                  magic=6.5, layout="soa", device=None, stream=None):
+        """mtg_generate_candidates_batch: (positions, seg_times) CUDA tensors, soa [K+1,D,B] / [K,B] or aos."""
+        import torch
+
+        aos = layout == "aos"
+        dev = torch.device("cuda", self.device if device is None else device)
+        pos = torch.empty((B, K + 1, D) if aos else (K + 1, D, B), dtype=torch.float64, device=dev)
+        times = torch.empty((B, K) if aos else (K, B), dtype=torch.float64, device=dev)
+        lo = (C.c_double * D)(*np.broadcast_to(np.asarray(pos_min, dtype=np.float64), (D,)))
+        hi = (C.c_double * D)(*np.broadcast_to(np.asarray(pos_max, dtype=np.float64), (D,)))
+        desc = ProblemDesc(B, K, D, 10, 4, MTG_MEM_DEVICE, LAYOUT_AOS if aos else LAYOUT_SOA)
+        rc = self._lib.mtg_generate_candidates_batch(self._h, C.byref(desc), int(seed), int(first_index), lo, hi,
+                                                     float(v_max), float(a_max), float(magic), _ptr(pos), _ptr(times),
+                                                     self._stream(MTG_MEM_DEVICE, stream))
+        self._check(rc, "mtg_generate_candidates_batch")
+        return pos, times
 
     # ------------------------------------------------------------ sweep argmin
     def argmin_batch(self, cost, status=None, global_offset: int = 0, best=None, accumulate=False, stream=None):

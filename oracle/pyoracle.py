@@ -516,3 +516,68 @@ def collision_cost(coeffs, times, grid, origin, res, min_bound, max_bound, dt, e
                               C.c_double(epsilon), C.c_double(robot_radius), C.c_double(multiplier), C.byref(J),
                               _d(g) if want_grad else None, C.byref(col), C.byref(chk))
     return J.value, (g.reshape(3, -1) if want_grad else None), bool(col.value), chk.value
+
+
+# ------------------------------------------------------------------ G1 device generator: host twin (numpy)
+def _philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 on uint64-held 32-bit lanes (vectorised over candidates)."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    k0 = np.uint64(k0)
+    k1 = np.uint64(k1)
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return c0, c1, c2, c3
+
+
+def generate_candidates(B, K, D, seed, first_index=0, pos_min=-10.0, pos_max=10.0, v_max=3.0, a_max=5.0, magic=6.5):
+    """Host twin of mtg_generate_candidates_batch: createRandomVertices' rejection rule (VTX_C:65-72) and Nfabian
+    times (VTX_C:252-269) on Philox4x32-10 keyed by (seed; candidate index, draw, block).
+    Returns positions [B, K+1, D], times [B, K]."""
+    lo = np.broadcast_to(np.asarray(pos_min, dtype=np.float64), (D,))
+    hi = np.broadcast_to(np.asarray(pos_max, dtype=np.float64), (D,))
+    idx = (np.arange(B, dtype=np.uint64) + np.uint64(first_index))
+    g0, g1 = idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    draw = np.zeros(B, dtype=np.uint64)
+    pos = np.zeros((B, K + 1, D))
+    times = np.zeros((B, K))
+    last = np.zeros((B, D))
+
+    def u53(a, b):
+        return (((a >> np.uint64(5)) << np.uint64(26)) | (b >> np.uint64(6))).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+    for v in range(K + 1):
+        todo = np.ones(B, dtype=bool)
+        cur = np.zeros((B, D))
+        dist = np.zeros(B)
+        while todo.any():
+            sel = np.flatnonzero(todo)
+            z = np.zeros(sel.size, dtype=np.uint64)
+            c = _philox4x32_10(g0[sel], g1[sel], draw[sel], z, k0, k1)
+            u = [u53(c[0], c[1]), u53(c[2], c[3])]
+            if D > 2:
+                e = _philox4x32_10(g0[sel], g1[sel], draw[sel], z + np.uint64(1), k0, k1)
+                u += [u53(e[0], e[1]), u53(e[2], e[3])]
+            draw[sel] += np.uint64(1)
+            s = np.zeros(sel.size)
+            for dim in range(D):
+                x = lo[dim] + u[dim] * (hi[dim] - lo[dim])
+                cur[sel, dim] = x
+                dd = x - last[sel, dim]
+                s = s + dd * dd
+            d_ = np.sqrt(s)
+            dist[sel] = d_
+            ok = np.ones(sel.size, dtype=bool) if v == 0 else d_ > 0.2
+            todo[sel[ok]] = False
+        pos[:, v] = cur
+        last = cur.copy()
+        if v >= 1:
+            times[:, v - 1] = dist / v_max * 2 * (1.0 + magic * v_max / a_max * np.exp(-dist / v_max * 2))
+    return pos, times

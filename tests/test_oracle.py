@@ -573,3 +573,23 @@ def test_control_points_inside_imply_samples_inside(po):
         f = po.feasibility_sweep(s.coeffs, times, pos, radii, 3.0, 5.0, 0.0, tmax, tmax / 500)
         assert np.all(f[1] & 4), seed
     assert n_feasible >= 5
+
+
+def test_philox_known_answer_and_generator_rules(po):
+    """The host twin of the device candidate generator: Philox4x32-10 against the Random123 known-answer vectors,
+    and the reference's generator rules (positions inside the box, consecutive vertices > 0.2 m apart VTX_C:65-72,
+    Nfabian times VTX_C:252-269)."""
+    z = np.zeros(1, dtype=np.uint64)
+    got = [int(x[0]) for x in po._philox4x32_10(z, z, z, z, 0, 0)]
+    assert got == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    f = np.full(1, 0xFFFFFFFF, dtype=np.uint64)
+    got = [int(x[0]) for x in po._philox4x32_10(f, f, f, f, 0xFFFFFFFF, 0xFFFFFFFF)]
+    assert got == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    pos, times = po.generate_candidates(2000, 10, 3, 0xB200)
+    assert pos.min() >= -10 and pos.max() < 10
+    d = np.linalg.norm(np.diff(pos, axis=1), axis=2)
+    assert d.min() > 0.2
+    want = np.stack([po.estimate_segment_times_nfabian(pos[b], 3.0, 5.0) for b in range(50)])
+    assert np.allclose(times[:50], want, rtol=1e-15, atol=0)
+    a, _ = po.generate_candidates(10, 10, 3, 0xB200, first_index=1990)
+    assert np.array_equal(a, pos[1990:])

@@ -96,3 +96,34 @@ def test_full_size_sweep_strided_sample_vs_oracle(po):
     assert ps["count_mismatch"] == 0 and ps["time_mismatch"] == 0 and ps["segment_mismatch"] == 0
     assert ps["value_err_max_rel"] <= 1e-12 and ps["flag_mismatch_away_from_limits"] == 0
     assert ps["subset_rows_bit_identical_to_full_run"]
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_device_candidate_generator_matches_host_twin(po, layout):
+    """mtg_generate_candidates_batch (Philox4x32-10 keyed by the candidate index; createRandomVertices' 0.2 m rejection
+    rule VTX_C:65-72; Nfabian times VTX_C:252-269) against the numpy twin: positions bit for bit, times to 2 ulp
+    (device exp vs libm exp); independent of the batch split (first_index) and of the layout."""
+    from gpu_util import aos
+
+    c = ctx()
+    B, K, D, seed = 5000, 10, 3, 0xB200
+    p, t = c.generate_candidates_batch(B, K, D, seed, layout=layout)
+    conv = aos if layout == "soa" else (lambda x: x)
+    pos, times = conv(host(p)), conv(host(t))
+    want_p, want_t = po.generate_candidates(B, K, D, seed)
+    assert np.array_equal(pos, want_p)
+    assert np.abs(times - want_t).max() <= 4e-16 * np.abs(want_t).max()
+    assert np.all(np.linalg.norm(np.diff(pos, axis=1), axis=2) > 0.2) and pos.min() >= -10 and pos.max() < 10
+    # a shard that starts at candidate 3000 reproduces the tail of the full batch
+    p2, t2 = c.generate_candidates_batch(2000, K, D, seed, first_index=3000, layout=layout)
+    assert np.array_equal(conv(host(p2)), pos[3000:]) and np.array_equal(conv(host(t2)), times[3000:])
+    # a tight box makes the rejection rule fire (|pos - last| <= 0.2 has probability ~3 % per draw in a 1 m box)
+    p3, _ = c.generate_candidates_batch(4000, 4, 3, 7, pos_min=0.0, pos_max=1.0, layout=layout)
+    w3, _ = po.generate_candidates(4000, 4, 3, 7, pos_min=0.0, pos_max=1.0)
+    assert np.array_equal(conv(host(p3)), w3)
+    assert np.all(np.linalg.norm(np.diff(w3, axis=1), axis=2) > 0.2)
+    # 2-D and 1-D candidates use one Philox block per draw
+    for d_ in (1, 2):
+        p4, _ = c.generate_candidates_batch(300, 3, d_, 11, layout=layout)
+        w4, _ = po.generate_candidates(300, 3, d_, 11)
+        assert np.array_equal(conv(host(p4)), w4)
