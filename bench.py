@@ -45,8 +45,8 @@ N_ROTATE = 4                                        # rotating buffer sets: 4 x 
 METRIC = "min-snap trajectories solved/sec (N=10, 10 seg, 3D)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one 65,536-solve launch: a CONSTANT from the named ncu capture
 # (ncu cannot run inside the bench), not measured in this run
-TRAFFIC_PER_LAUNCH = 122.82e6
-TRAFFIC_SOURCE = "constant from profiles/r01_solve_full.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+TRAFFIC_PER_LAUNCH = 123.15e6
+TRAFFIC_SOURCE = "constant from profiles/r02_solve_full.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
 SOLVE_KERNEL_NAME = "solve_canonical_kernel<5,3,false>"
 SWEEP_BATCH = 1_000_000                             # BASELINE configs[3]: 1M trajectories x 1000 samples
 SWEEP_SAMPLES = 1000

@@ -7,31 +7,27 @@
 // findRootsJenkinsTraub + rpoly_ak1 rpoly_ak1.cpp:57-937, the candidate evaluation
 // segment.cpp:135-184 and Trajectory::computeMinMaxMagnitude trajectory.cpp:184-220.
 //
-// Root finding. The reference runs Jenkins-Traub for ALL complex roots and keeps the real ones
-// inside [t_start, t_end] (polynomial.cpp:46-60). Only those are ever consumed, so this kernel
-// isolates exactly them with the derivative chain: the roots of P^(k+1) split the interval into
-// pieces on which P^(k) is monotone; every piece whose end values differ in sign holds exactly one
-// root of P^(k), refined by a bracketed Newton iteration (bisection when a Newton step leaves the
-// bracket). Going from the linear P^(n-1) down to P^(0) = g yields every real root of g in the
-// interval that is a sign change — i.e. every extremum of the magnitude; roots of even
-// multiplicity are inflections of the magnitude and cannot be its minimum or maximum. All loops
-// are bounded and there is no data-dependent recursion.
+// Root finding. The reference runs Jenkins-Traub for ALL complex roots and keeps the real ones inside
+// [t_start, t_end] (polynomial.cpp:46-60). Only those are ever consumed, so this kernel isolates exactly them,
+// in the BERNSTEIN basis of the interval: the number of sign changes V of the Bernstein coefficients bounds the
+// number of roots in the open interval (variation diminishing) — V = 0: none, V = 1: exactly one — and halving
+// the interval (de Casteljau) makes the control polygon converge to the curve, so an interval with V >= 2 is
+// split until every piece has V <= 1. The single root of a V = 1 piece is then polished by a bracketed Newton
+// iteration on the power form, started at the zero crossing of the control polygon (quadratically close to the
+// root) and stopped when |g(t)| falls inside its own rounding-error bound. On min-snap segments one split per
+// problem is typical (0.8-1.0 on average) against 15 levels x 2-5 brackets for a derivative-chain isolator:
+// ~1e3 instead of ~4.5e3 multiply-adds per problem and no level loop. Coefficients below 1e-13 of the largest
+// Bernstein coefficient count as zero: that removes the numerically 7-fold root a rest-to-rest segment has AT its
+// end point (the end points are candidates anyway) and can only hide a root PAIR whose dip of g is below 1e-13
+// of its scale — not an extremum of the magnitude at any tolerance used here. All loops are bounded.
 //
-// Mapping (warp-cooperative). One warp owns kExG = 16 root problems ((trajectory, segment) pairs,
-// contiguous in memory in both layouts). Everything a problem needs between levels — g, the
-// current level polynomial, the roots of the previous and of the current level — lives in
-// shared memory (odd strides: the 16 problems of a warp sit in 16 different bank pairs), nothing
-// in local memory. Per level the warp runs three flat, lane-parallel passes over ALL of its
-// problems at once:
-//   build   lane = (problem, coefficient): the level polynomial from g and the base table;
-//   scan    lane = (problem, piece of the partition): both end values of the piece in one Horner
-//           sweep (one shared-memory load feeds two FMA chains), sign test, ordered compaction of
-//           the brackets with ballots (roots stay sorted per problem);
-//   refine  lane = bracket: bracketed Newton with the value and the slope from ONE coefficient
-//           stream (p and p' by the coupled Horner recurrence).
-// So the lanes of a warp share the work of 16 problems instead of each waiting for the slowest
-// of 32 (root counts and iteration counts differ from problem to problem, their sums over 16
-// problems hardly do). The candidates [t_start, t_end, roots...] are then evaluated one per lane.
+// Mapping (warp-cooperative). One warp owns kExG = 16 root problems ((trajectory, segment) pairs, contiguous in
+// memory in both layouts); g, the roots and the candidate values of a problem live in shared memory (odd
+// strides), nothing in local memory. Intervals wait on a per-warp stack in shared memory; a group of 16 lanes
+// (32 for more than 16 coefficients) takes one interval: lane i holds Bernstein coefficient i, V and the
+// control-polygon crossing come from ballots, a split is n rounds of shuffles (the left child is the first lane's
+// value after every round, the right child is what the lanes hold at the end). V = 1 pieces queue as brackets and
+// are polished one per lane. The candidates [t_start, t_end, roots...] are then evaluated one per lane.
 //
 // Candidate order and tie rules follow the reference: per segment [t_start, t_end, roots...]
 // with std::max / std::min (first wins), across segments strict '>' / '<' (earliest wins).
@@ -46,10 +42,12 @@
 namespace mtg {
 
 constexpr int kMaxG = MTG_BASE_LD;  // 22 coefficients: Polynomial::kMaxConvolutionSize (polynomial.h:48)
-constexpr int kRootIters = 96;
-constexpr int kExG = 16;     // root problems per warp (the item -> problem search below is written for 16)
-static_assert(kExG == 16, "the prefix search of extrema_warp_kernel assumes 16 problems per warp");
-constexpr int kExWarps = 8;  // warps per CTA
+constexpr int kRootIters = 64;      // Newton iterations per root (bisection fallback inside)
+constexpr int kBernDepth = 30;      // halvings of one interval before it is taken as it is
+constexpr int kExG = 16;            // root problems per warp
+constexpr int kExWarps = 8;         // warps per CTA
+constexpr int kExBr = 64;           // bracket queue of a warp
+static_assert(kExG == 16, "extrema_warp_kernel maps problem = lane & 15");
 
 struct ExtremaParams {
   const double* __restrict__ coeffs;     // elem ((i*D + dim)*N + j), rec K*D*N; raw mode: elem j, rec N
@@ -84,9 +82,11 @@ struct ExtremaParams {
 // shared-memory plan of one launch (host and device agree through these numbers)
 struct ExtremaPlan {
   int len;     // coefficients of g
-  int S;       // stride (doubles) of the per-problem arrays g, pk, rA, rB
+  int S;       // stride (doubles) of the per-problem arrays g, roots, values
   int nd;      // coefficients of p^(d)
   int ndim;    // dimensions taking part
+  int lpi;     // lanes per interval (16 or 32)
+  int qc;      // interval stack capacity
   size_t warp_bytes, cta_bytes;
 };
 
@@ -99,15 +99,21 @@ __host__ __device__ inline ExtremaPlan extrema_plan(int N, int D, int derivative
   pl.len = raw ? N : (ndim > 1 ? 2 * pl.nd - 2 : pl.nd - 1);
   if (pl.len < 1) pl.len = 1;
   // every per-problem array holds <= len + 1 doubles (len coefficients; len - 1 roots + 2 end points);
-  // [g | pk] together must also hold the staged derivative coefficients (D * nd) for the candidates
-  // (and [pk | rA | rB] the same for building g)
+  // [roots | values] together must also hold the staged derivative coefficients (D * nd) while g is built
   int S = (pl.len + 1) | 1;
   const int need = raw ? 0 : ((D * pl.nd + 1) / 2) | 1;
   if (need > S) S = need;
   pl.S = S;
-  // doubles: 4 arrays x G x S + lo/hi[G];  ints: n, na, cnt, par, st [G], off[G + 1], next;  uint16 ent[G * len]
-  size_t bytes = (size_t)(4 * kExG * S + 2 * kExG) * sizeof(double) + (size_t)(5 * kExG + kExG + 2) * sizeof(int) +
-                 (size_t)kExG * pl.len * sizeof(uint16_t);
+  pl.lpi = pl.len <= 16 ? 16 : 32;
+  // the interval stack also stages the derivative coefficients for the candidate evaluation at the end
+  int qc = 32;
+  const int stage = raw ? 0 : (kExG * D * pl.nd + pl.lpi - 1) / pl.lpi;
+  if (stage > qc) qc = stage;
+  pl.qc = qc;
+  // doubles: g, roots, values [G][S]; lo, hi, eps [G]; stack coefficients [qc][lpi], a, b [qc]; brackets a, b, t [kExBr]
+  // ints: n, nroot, st [G]; stack meta [qc]; bracket meta [kExBr]; top, nbr
+  size_t bytes = (size_t)(3 * kExG * S + 3 * kExG + qc * pl.lpi + 2 * qc + 3 * kExBr) * sizeof(double) +
+                 (size_t)(3 * kExG + qc + kExBr + 2) * sizeof(int);
   pl.warp_bytes = (bytes + 15) & ~(size_t)15;
   pl.cta_bytes = pl.warp_bytes * kExWarps + (size_t)MTG_BASE_LD * MTG_BASE_LD * sizeof(double);
   return pl;
@@ -119,13 +125,11 @@ namespace mtg {
 // extrema.cu: chunked launch of extrema_warp_kernel (+ extrema_reduce_kernel when per-trajectory outputs are wanted)
 int launch_extrema(mtg_ctx* ctx, bool aos, const ExtremaParams& p, cudaStream_t s);
 
-__device__ __forceinline__ unsigned lanes_lt(int lane) { return (1u << lane) - 1u; }
-
 template <bool AOS>
 __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const ExtremaParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ExtremaPlan pl = extrema_plan(p.N, p.D, p.derivative, p.dim_mask, p.raw);
-  const int len = pl.len, S = pl.S, nd = pl.nd, G = kExG;
+  const int len = pl.len, S = pl.S, nd = pl.nd, G = kExG, LPI = pl.lpi, QC = pl.qc;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr unsigned FULL = 0xffffffffu;
 
@@ -157,20 +161,25 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   auto prob_seg = [&](int q) -> int { return AOS ? (int)((flat0 + q) % K) : seg0; };
 
   unsigned char* base_ptr = smem_raw + pl.warp_bytes * warp;
-  double* s_g = reinterpret_cast<double*>(base_ptr);
-  double* s_pk = s_g + G * S;
-  double* s_ra = s_pk + G * S;
-  double* s_rb = s_ra + G * S;
-  double* s_lo = s_rb + G * S;
+  double* s_g = reinterpret_cast<double*>(base_ptr);  // power coefficients of g in s = t - lo
+  double* s_root = s_g + G * S;                       // roots found (in s), unsorted until the end
+  double* s_val = s_root + G * S;                     // scratch: scaled coefficients, later candidate values
+  double* s_lo = s_val + G * S;
   double* s_hi = s_lo + G;
-  int* s_n = reinterpret_cast<int*>(s_hi + G);
-  int* s_na = s_n + G;
-  int* s_cnt = s_na + G;
-  int* s_par = s_cnt + G;
-  int* s_st = s_par + G;
-  int* s_off = s_st + G;  // G + 1
-  int* s_next = s_off + G + 1;
-  uint16_t* s_ent = reinterpret_cast<uint16_t*>(s_next + 1);
+  double* s_eps = s_hi + G;                           // coefficients below this count as zero
+  double* s_qc = s_eps + G;                           // interval stack: Bernstein coefficients [QC][LPI]
+  double* s_qa = s_qc + QC * LPI;                     //   interval ends (in s)
+  double* s_qb = s_qa + QC;
+  double* s_ba = s_qb + QC;                           // bracket queue: ends and first iterate
+  double* s_bb = s_ba + kExBr;
+  double* s_bt = s_bb + kExBr;
+  int* s_n = reinterpret_cast<int*>(s_bt + kExBr);    // degree of g
+  int* s_nroot = s_n + G;
+  int* s_st = s_nroot + G;
+  int* s_qm = s_st + G;                               // stack meta: problem | depth << 8
+  int* s_bm = s_qm + QC;                              // bracket meta: problem | (g < 0 left of the root) << 8
+  int* s_top = s_bm + kExBr;
+  int* s_nbr = s_top + 1;
 
   const size_t Bsz = (size_t)p.B;
   const size_t rec_c = p.raw ? (size_t)N : (size_t)K * D * N;
@@ -188,8 +197,11 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
     s_lo[lane] = lo;
     s_hi[lane] = hi;
     s_st[lane] = 0;
-    s_par[lane] = 0;
-    s_na[lane] = 0;
+    s_nroot[lane] = 0;
+  }
+  if (lane == 0) {
+    *s_top = 0;
+    *s_nbr = 0;
   }
 
   // Stages the derivative coefficients delta[dim][j] = B(d, j+d) c[j+d] (polynomial.h:99-113) of all
@@ -234,7 +246,7 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
 
   // ---- g: the polynomial whose real roots in [lo, hi] are the candidate times
   {
-    double* s_delta = s_pk;  // [pk | rA | rB] holds D * nd doubles per problem at this point
+    double* s_delta = s_root;  // [roots | values] holds D * nd doubles per problem at this point
     const int sd = p.raw ? N : D * nd;
     stage_delta(s_delta, sd);
     __syncwarp();
@@ -265,227 +277,262 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
     }
     __syncwarp();
   }
-  // strip zero leading coefficients (findLastNonZeroCoeff, rpoly_ak1.cpp:57-68)
-  int nmax = 0;
+  // strip zero leading coefficients (findLastNonZeroCoeff, rpoly_ak1.cpp:57-68); an interval that is empty or not
+  // finite has no roots either
+  bool any_shift = false;
   {
     int n = -1;
+    bool shift = false;
     if (lane < np) {
       n = len - 1;
       while (n >= 0 && !(fabs(s_g[lane * S + n]) >= 2.2250738585072014e-308)) --n;
+      const double L = s_hi[lane] - s_lo[lane];
+      if (!(L > 0.0) || !(L < 1.7e308)) n = min(n, 0);
+      shift = n >= 1 && s_lo[lane] != 0.0;
     }
     if (lane < G) s_n[lane] = n;
-    nmax = n;
+    any_shift = __any_sync(FULL, shift);
+    __syncwarp();
+  }
+  // ---- Taylor shift to s = t - lo where an interval does not start at 0 (only explicit t_start / raw roots)
+  if (any_shift && lane < np && s_n[lane] >= 1 && s_lo[lane] != 0.0) {
+    double* gq = s_g + lane * S;
+    const int n = s_n[lane];
+    const double lo = s_lo[lane];
+    for (int i = 0; i < n; ++i)
+      for (int j = n - 1; j >= i; --j) gq[j] = fma(lo, gq[j + 1], gq[j]);
+  }
+  __syncwarp();
+  // ---- Bernstein coefficients on [0, L]: b_i = sum_{j <= i} [C(i,j) / C(n,j)] g_j L^j, C(i,j)/C(n,j) = B(j,i)/B(j,n)
+  {
+    const int q = lane & 15;
+    const int n = q < np ? s_n[q] : -1;
+    if (n >= 1) {
+      const double L = s_hi[q] - s_lo[q];
+      double lp = (lane >> 4) ? L : 1.0;
+      const double L2 = L * L;
+      for (int j = lane >> 4; j <= n; j += 2) {
+        s_val[q * S + j] = s_g[q * S + j] * lp / s_base[j * MTG_BASE_LD + n];
+        lp *= L2;
+      }
+    }
+  }
+  __syncwarp();
+  const int GP = 32 / LPI;            // intervals per warp step
+  const int gi = lane / LPI, li = lane - gi * LPI;
+  const unsigned gmask = LPI == 32 ? FULL : (0xffffu << (16 * gi));
+  for (int q0 = 0; q0 < np; q0 += GP) {
+    const int q = q0 + gi;
+    const int n = q < np ? s_n[q] : -1;
+    double c = 0.0;
+    if (n >= 1 && li <= n) {
+      const double* aq = s_val + q * S;
+      for (int j = 0; j <= li; ++j) c = fma(s_base[j * MTG_BASE_LD + li], aq[j], c);
+    }
+    // scale of the problem: the largest coefficient
+    double mx = fabs(c);
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, m));
+    for (int m = 8; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, m));
+    if (LPI == 32) mx = fmax(mx, __shfl_xor_sync(FULL, mx, 16));
+    int slot = 0;
+    if (n >= 1 && li == 0) slot = atomicAdd(s_top, 1);  // one slot per interval, drawn by the group's first lane
+    const int sl = __shfl_sync(FULL, slot, gi * LPI);
+    if (n >= 1) {
+      s_qc[sl * LPI + li] = c;
+      if (li == 0) {
+        s_qa[sl] = 0.0;
+        s_qb[sl] = s_hi[q] - s_lo[q];
+        s_qm[sl] = q;
+        s_eps[q] = 1e-13 * mx;
+        if (c == 0.0) s_root[q * S + atomicAdd(&s_nroot[q], 1)] = 0.0;  // a root exactly on the left end
+      }
+      if (li == n && c == 0.0) s_root[q * S + atomicAdd(&s_nroot[q], 1)] = s_hi[q] - s_lo[q];  // ... on the right end
+    }
     __syncwarp();
   }
 
-  // ---- the derivative chain, level by level: deg = degree of the level polynomial g^(n - deg)
-  for (int deg = 1; deg <= nmax; ++deg) {
-    // build: pk[q][j] = B(k, j + k) g[q][j + k], k = n_q - deg, for the problems still in the chain
-    {
-      const int q = lane & 15;  // lane = (problem, coefficient parity)
-      const int k = q < np ? s_n[q] - deg : -1;
-      if (k >= 0) {
-        const double* bk = s_base + k * MTG_BASE_LD + k;
-        const double* gk = s_g + q * S + k;
-        double* pq = s_pk + q * S;
-        for (int j = lane >> 4; j <= deg; j += 2) pq[j] = bk[j] * gk[j];
-      }
-    }
-    // pieces of the partition per problem (exclusive prefix over the problems)
-    {
-      int cnt = 0;
-      if (lane < np && s_n[lane] >= deg) cnt = s_na[lane] + 1;
-      int incl = cnt;
-#pragma unroll
-      for (int m = 1; m < 32; m <<= 1) {
-        const int o = __shfl_up_sync(FULL, incl, m);
-        if (lane >= m) incl += o;
-      }
-      if (lane < G) {
-        s_off[lane] = incl - cnt;
-        s_cnt[lane] = 0;
-      }
-      if (lane == G - 1) s_off[G] = incl;
-    }
-    __syncwarp();
-    const int total = s_off[G];
-    int nent = 0;
-    // scan: lane = piece [u, v] of one problem's partition
-    for (int it0 = 0; it0 < total; it0 += 32) {
-      const int item = it0 + lane;
-      const bool live = item < total;
-      int q = 0;
-      if (live) {
-        if (item >= s_off[8]) q = 8;
-        if (item >= s_off[q + 4]) q += 4;
-        if (item >= s_off[q + 2]) q += 2;
-        if (item >= s_off[q + 1]) q += 1;
-      }
-      const int qi = item - s_off[q];
-      const int na = s_na[q];
-      const double* rprev = (s_par[q] ? s_rb : s_ra) + q * S;
-      double* rcur = (s_par[q] ? s_ra : s_rb) + q * S;
-      const double lo = s_lo[q], hi = s_hi[q];
-      double u = lo, v = hi;
-      if (live) {
-        if (qi > 0) u = rprev[qi - 1];
-        if (qi < na) v = rprev[qi];
-      }
-      const bool valid = live && (v > u);
-      double fu = 0.0, fv = 0.0;
-      if (valid) {
-        const double* pk = s_pk + q * S;
-        fu = fv = pk[deg];
-#pragma unroll 4
-        for (int j = deg - 1; j >= 0; --j) {
-          const double c = pk[j];
-          fu = fma(fu, u, c);
-          fv = fma(fv, v, c);
-        }
-      }
-      // what this piece contributes (in root order): a root exactly on its left end, or a bracket;
-      // and, for the piece that ends at hi, a root exactly on hi
-      const bool exact_u = valid && fu == 0.0;
-      const bool bracket = valid && fu != 0.0 && fv != 0.0 && ((fu < 0.0) != (fv < 0.0));
-      const bool exact_v = valid && fv == 0.0 && v == hi;
-      const bool e1 = exact_u || bracket;
-      // lanes of the same problem are contiguous: [first, last] within this round
-      const int first = max(0, s_off[q] - it0), last = min(31, s_off[q + 1] - 1 - it0);
-      const unsigned same = live ? ((last >= 31 ? FULL : ((1u << (last + 1)) - 1u)) & ~lanes_lt(first)) : 0u;
-      const unsigned m1 = __ballot_sync(FULL, e1);
-      const unsigned mb = __ballot_sync(FULL, bracket);
-      const int before = live ? s_cnt[q] : 0;
-      __syncwarp();
-      const int slot = before + __popc(m1 & same & lanes_lt(lane));
-      if (e1 && (m1 & same & lanes_lt(lane)) == 0u) s_cnt[q] = before + __popc(m1 & same);  // first emitter of q
-      if (exact_u) rcur[slot] = u;
-      if (bracket) {
-        // first iterate: the secant point (the midpoint if it degenerates), parked where the root will go
-        double t = u - fu * ((v - u) / (fv - fu));
-        if (!(t > u && t < v)) t = 0.5 * (u + v);
-        rcur[slot] = t;
-        s_ent[nent + __popc(mb & lanes_lt(lane))] =
-            (uint16_t)(q | (qi << 4) | (slot << 9) | ((fu < 0.0) ? (1 << 14) : 0));
-      }
-      nent += __popc(mb);
-      __syncwarp();
-      if (exact_v) {  // at most one piece per problem ends at hi
-        const int s2 = s_cnt[q];
-        rcur[s2] = v;
-        s_cnt[q] = s2 + 1;
-      }
-      __syncwarp();
-    }
-    // refine: lane = bracket. ONE flat loop whose trip is one bracketed-Newton iteration of whichever bracket
-    // the lane is working on; a lane that finishes a bracket draws the next one from a shared counter, so the
-    // warp waits for the largest SUM of iterations per lane, not for the slowest bracket of every round.
-    if (lane == 0) *s_next = 32;
-    __syncwarp();
-    {
-      int e = lane;
-      bool have = false;
-      int q = 0, slot = 0, it = 0;
-      bool fa_neg = false;
-      double a = 0.0, bb = 0.0, t = 0.0, tol = 0.0, wmin = 0.0;
-      const double* pk = s_pk;
-      double* rcur = s_rb;
-      for (;;) {
-        if (!have) {
-          if (e >= nent) break;
-          const unsigned en = s_ent[e];
-          q = en & 15;
-          const int qi = (en >> 4) & 31;
-          slot = (en >> 9) & 31;
-          fa_neg = (en >> 14) & 1;
-          const int na = s_na[q];
-          const double* rprev = (s_par[q] ? s_rb : s_ra) + q * S;
-          rcur = (s_par[q] ? s_ra : s_rb) + q * S;
-          a = qi > 0 ? rprev[qi - 1] : s_lo[q];
-          bb = qi < na ? rprev[qi] : s_hi[q];
-          // roots of the upper levels only PARTITION the interval for the level below: 1e-9 of its length is
-          // plenty (a partition point off by delta can only hide a root pair closer than delta, i.e. a bump of
-          // the magnitude of relative height ~delta^2); the roots of g itself (deg = n) go to 1e-15 of the
-          // length (a few ulp of a mid-interval time)
-          tol = ((s_n[q] > deg) ? 1e-9 : 1e-15) * (s_hi[q] - s_lo[q]);
-          // bracket narrower than tol or than fp64 can resolve anywhere in the interval
-          wmin = fmax(tol, 4.5e-16 * fmax(fabs(s_lo[q]), fabs(s_hi[q])));
-          pk = s_pk + q * S;
-          t = rcur[slot];
-          it = 0;
-          have = true;
-        }
-        // value, slope and the running rounding-error bound of the value from one coefficient stream:
-        // p and p' by the coupled Horner recurrence, err = sum |c_j| |t|^j
-        double ft = pk[deg], dft = 0.0, err = fabs(ft);
+  // Newton polish of the queued brackets, one per lane: value, slope and the running rounding-error bound of the
+  // value from one coefficient stream (p and p' by the coupled Horner recurrence, err = sum |c_j| |t|^j)
+  auto drain = [&]() {
+    const int nbr = *s_nbr;
+    for (int e = lane; e < nbr; e += 32) {
+      const int meta = s_bm[e];
+      const int q = meta & 255;
+      const bool fa_neg = (meta >> 8) & 1;
+      const int n = s_n[q];
+      const double* gq = s_g + q * S;
+      double a = s_ba[e], bb = s_bb[e], t = s_bt[e];
+      const double tol = 1e-15 * (s_hi[q] - s_lo[q]);
+      const double wmin = fmax(tol, 4.5e-16 * fmax(fabs(s_lo[q]), fabs(s_hi[q])));
+      double res = t;
+      for (int it = 0;; ++it) {
+        double ft = gq[n], dft = 0.0, err = fabs(ft);
         const double at = fabs(t);
 #pragma unroll 4
-        for (int j = deg - 1; j >= 0; --j) {
-          const double c = pk[j];
+        for (int j = n - 1; j >= 0; --j) {
+          const double c = gq[j];
           dft = fma(dft, t, ft);
           ft = fma(ft, t, c);
           err = fma(err, at, fabs(c));
         }
-        double res = t;
-        // |value| inside its own rounding noise: the root is located as well as fp64 can tell. (This is what
-        // ends the iteration on the numerically multiple roots of rest-to-rest ends, where Newton converges
-        // only linearly and every further digit is noise anyway.)
-        bool fin = fabs(ft) <= (double)(2 * deg + 2) * 1.1102230246251565e-16 * err;
-        if (!fin) {
-          if ((ft < 0.0) == fa_neg)
-            a = t;
-          else
-            bb = t;
-          const double width = bb - a;
-          if (!(width > wmin)) {
-            fin = true;
-          } else {
-            // Newton step with a cheap reciprocal (rcp.approx.f64: ~20 bits over the whole fp64 exponent range,
-            // + one Newton step: ~1e-12 relative — the step only has to land inside the bracket; anything
-            // else, incl. NaN / infinity from a vanishing slope, bisects)
-            double r;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dft));
-            r = r * fma(-dft, r, 2.0);
-            double tn = fma(-ft, r, t);
-            if (!(tn > a && tn < bb)) tn = 0.5 * (a + bb);
-            if (!(fabs(tn - t) > tol)) {
-              fin = true;
-              res = tn;
-            } else {
-              t = tn;
-              if (++it >= kRootIters) {
-                atomicOr(&s_st[q], 16);  // MTG_ST_NO_CONVERGENCE (reference: rpoly returns partial roots, RPOLY_C:372-377)
-                fin = true;
-                res = t;
-              }
-            }
-          }
+        res = t;
+        // |value| inside its own rounding noise: the root is located as well as fp64 can tell
+        if (fabs(ft) <= (double)(2 * n + 2) * 1.1102230246251565e-16 * err) break;
+        if ((ft < 0.0) == fa_neg)
+          a = t;
+        else
+          bb = t;
+        if (!(bb - a > wmin)) break;
+        // Newton step with a cheap reciprocal (rcp.approx.f64 + one Newton step: ~1e-12 relative — the step only
+        // has to land inside the bracket; anything else, incl. NaN / infinity from a vanishing slope, bisects)
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dft));
+        r = r * fma(-dft, r, 2.0);
+        double tn = fma(-ft, r, t);
+        if (!(tn > a && tn < bb)) tn = 0.5 * (a + bb);
+        if (!(fabs(tn - t) > tol)) {
+          res = tn;
+          break;
         }
-        if (fin) {
-          rcur[slot] = res;
-          have = false;
-          e = atomicAdd(s_next, 1);
+        t = tn;
+        res = t;
+        if (it + 1 >= kRootIters) {
+          atomicOr(&s_st[q], 16);  // MTG_ST_NO_CONVERGENCE (reference: rpoly returns partial roots, RPOLY_C:372-377)
+          break;
+        }
+      }
+      const int slot = atomicAdd(&s_nroot[q], 1);
+      if (slot < S) s_root[q * S + slot] = res;
+    }
+    __syncwarp();
+    if (lane == 0) *s_nbr = 0;
+    __syncwarp();
+  };
+
+  // ---- isolate: pop intervals, count sign variations, split or queue
+  for (;;) {
+    __syncwarp();
+    const int top = *s_top;
+    if (top == 0) break;
+    const int take = min(GP, top);
+    __syncwarp();
+    if (lane == 0) *s_top = top - take;
+    const bool have = gi < take;
+    const int sl = top - 1 - gi;
+    double c = 0.0, a = 0.0, b = 0.0, eps = 0.0;
+    int q = 0, depth = 0, n = 0;
+    if (have) {
+      const int meta = s_qm[sl];
+      q = meta & 255;
+      depth = meta >> 8;
+      n = s_n[q];
+      a = s_qa[sl];
+      b = s_qb[sl];
+      eps = s_eps[q];
+      if (li <= n) c = s_qc[sl * LPI + li];
+    }
+    __syncwarp();  // the popped slots may be overwritten by the pushes below
+    const unsigned shiftg = LPI == 32 ? 0u : 16u * gi;
+    const unsigned lmask = LPI == 32 ? FULL : 0xffffu;
+    const unsigned P = (__ballot_sync(FULL, have && li <= n && c > eps) >> shiftg) & lmask;
+    const unsigned M = (__ballot_sync(FULL, have && li <= n && c < -eps) >> shiftg) & lmask;
+    const unsigned nz = P | M;
+    // a sign change starts at i: i is non-zero and the next non-zero coefficient above it has the other sign
+    int nxt = -1;
+    bool var = false;
+    if ((nz >> li) & 1u) {
+      const unsigned above = li >= 31 ? 0u : (nz & ~((2u << li) - 1u));
+      if (above) {
+        nxt = __ffs(above) - 1;
+        var = ((P >> li) & 1u) != ((P >> nxt) & 1u);
+      }
+    }
+    const unsigned Vm = (__ballot_sync(FULL, var) >> shiftg) & lmask;
+    const int V = __popc(Vm);
+    const bool room = *s_top + 2 * GP <= QC;   // read before anybody pushes (uniform)
+    const bool leaf = have && V >= 1 && (V == 1 || depth >= kBernDepth || !room);
+    const bool split = have && V >= 2 && !leaf;
+    if (have && V >= 2 && leaf && li == 0 && !room) atomicOr(&s_st[q], 16);
+    // the first crossing of the control polygon: between coefficients i0 and j0
+    const int i0 = Vm ? __ffs(Vm) - 1 : 0;
+    const int j0 = __shfl_sync(FULL, nxt, gi * LPI + i0);
+    const double ci = __shfl_sync(FULL, c, gi * LPI + i0);
+    const double cj = __shfl_sync(FULL, c, gi * LPI + max(j0, 0));
+    if (leaf && li == 0) {
+      double u = ((double)i0 + ci / (ci - cj) * (double)(j0 - i0)) / (double)n;
+      double t = a + u * (b - a);
+      if (!(t > a && t < b)) t = 0.5 * (a + b);
+      const int e = atomicAdd(s_nbr, 1);
+      s_ba[e] = a;
+      s_bb[e] = b;
+      s_bt[e] = t;
+      s_bm[e] = q | (((M >> (__ffs(nz) - 1)) & 1u) << 8);  // sign of g just right of a
+    }
+    if (__any_sync(FULL, split)) {
+      // de Casteljau at the midpoint: after round r lane i <= n - r holds b_i^(r); the left child is lane 0's value
+      // after every round, the right child is what the lanes hold at the end
+      double cur = c, left = c;
+      int nmax = split ? n : 0;
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, m));
+      for (int r = 1; r <= nmax; ++r) {
+        const double up = __shfl_down_sync(FULL, cur, 1, LPI);
+        if (split && li <= n - r) cur = 0.5 * (cur + up);
+        const double l0 = __shfl_sync(FULL, cur, gi * LPI);
+        if (li == r) left = l0;
+      }
+      int basei = 0;
+      if (split && li == 0) basei = atomicAdd(s_top, 2);
+      basei = __shfl_sync(FULL, basei, gi * LPI);
+      if (split) {
+        const double mid = 0.5 * (a + b);
+        s_qc[basei * LPI + li] = li <= n ? cur : 0.0;         // right child first: the left one is popped first
+        s_qc[(basei + 1) * LPI + li] = li <= n ? left : 0.0;
+        if (li == 0) {
+          s_qa[basei] = mid;
+          s_qb[basei] = b;
+          s_qm[basei] = q | ((depth + 1) << 8);
+          s_qa[basei + 1] = a;
+          s_qb[basei + 1] = mid;
+          s_qm[basei + 1] = q | ((depth + 1) << 8);
+          if (cur == 0.0) {  // g vanishes exactly at the midpoint: neither child would see it
+            const int slot = atomicAdd(&s_nroot[q], 1);
+            if (slot < S) s_root[q * S + slot] = mid;
+          }
         }
       }
     }
     __syncwarp();
-    // the problems of this level: current roots become the partition of the next level
-    if (lane < np && s_n[lane] >= deg) {
-      s_na[lane] = s_cnt[lane];
-      s_par[lane] ^= 1;
-    }
-    __syncwarp();
+    if (*s_nbr > kExBr - GP) drain();
   }
-  // roots of g of problem q: (par ? rB : rA)[0 .. na) ascending; constant polynomial: none (rpoly_ak1.cpp:76-80)
+  drain();
+  // roots ascending, back in t = lo + s; constant polynomial: none (rpoly_ak1.cpp:76-80)
+  if (lane < np) {
+    double* rq = s_root + lane * S;
+    const int nr = min(s_nroot[lane], S - 2);
+    for (int i = 1; i < nr; ++i) {
+      const double x = rq[i];
+      int j = i - 1;
+      while (j >= 0 && rq[j] > x) {
+        rq[j + 1] = rq[j];
+        --j;
+      }
+      rq[j + 1] = x;
+    }
+    const double lo = s_lo[lane];
+    if (lo != 0.0)
+      for (int i = 0; i < nr; ++i) rq[i] += lo;
+    s_nroot[lane] = nr;
+  }
+  __syncwarp();
 
   // ---- raw mode: the roots are the result
   if (p.raw) {
     if (lane < np) {
       const int q = lane;
       const int b = p.b0 + prob_local(q), seg = prob_seg(q);
-      const double* roots = (s_par[q] ? s_rb : s_ra) + q * S;
-      const int na = s_n[q] >= 1 ? s_na[q] : 0;
+      const double* roots = s_root + q * S;
+      const int na = s_nroot[q];
       const size_t rec_k = (size_t)K * p.max_cand;
       int w = 0;
       for (int c = 0; c < na && w < p.max_cand; ++c, ++w)
@@ -499,55 +546,38 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   }
 
   // ---- candidates [t_start, t_end, roots...]: |p^(d)(t)| = sqrt(sum_dim evaluate(t, d)^2)  (segment.cpp:135-158)
-  double* s_delta = s_g;  // [g | pk] are free now
+  double* s_delta = s_qc;  // the interval stack is empty now
   const int sd = D * nd;
   stage_delta(s_delta, sd);
-  {
-    int cnt = 0;
-    if (lane < np) {
-      if (s_n[lane] < 1) s_na[lane] = 0;
-      cnt = s_na[lane] + 2;
-    }
-    int incl = cnt;
-#pragma unroll
-    for (int m = 1; m < 32; m <<= 1) {
-      const int o = __shfl_up_sync(FULL, incl, m);
-      if (lane >= m) incl += o;
-    }
-    if (lane < G) s_off[lane] = incl - cnt;
-    if (lane == G - 1) s_off[G] = incl;
-  }
   __syncwarp();
   {
-    const int total = s_off[G];
-    for (int item = lane; item < total; item += 32) {
-      int q = 0;
-      if (item >= s_off[8]) q = 8;
-      if (item >= s_off[q + 4]) q += 4;
-      if (item >= s_off[q + 2]) q += 2;
-      if (item >= s_off[q + 1]) q += 1;
-      const int c = item - s_off[q];
-      const double* roots = (s_par[q] ? s_rb : s_ra) + q * S;
-      double* vals = (s_par[q] ? s_ra : s_rb) + q * S;  // the other root buffer is free
-      const double t = (c == 0) ? s_lo[q] : (c == 1) ? s_hi[q] : roots[c - 2];
+    // lane = (problem, candidate parity): 16 problems x 2 lanes
+    const int q = lane & 15;
+    if (q < np) {
+      const double* roots = s_root + q * S;
+      double* vals = s_val + q * S;
       const double* dl = s_delta + q * sd;
-      double m2 = 0.0;
-      for (int dim = 0; dim < D; ++dim) {
-        double r = 0.0;
-        for (int j = nd - 1; j >= 0; --j) r = fma(r, t, dl[dim * nd + j]);
-        m2 = fma(r, r, m2);
+      const int nc = s_nroot[q] + 2;
+      for (int c = lane >> 4; c < nc; c += 2) {
+        const double t = (c == 0) ? s_lo[q] : (c == 1) ? s_hi[q] : roots[c - 2];
+        double m2 = 0.0;
+        for (int dim = 0; dim < D; ++dim) {
+          double r = 0.0;
+          for (int j = nd - 1; j >= 0; --j) r = fma(r, t, dl[dim * nd + j]);
+          m2 = fma(r, r, m2);
+        }
+        vals[c] = sqrt(m2);
       }
-      vals[c] = sqrt(m2);
     }
   }
   __syncwarp();
   if (lane < np) {
     const int q = lane;
     const int local = prob_local(q), seg = prob_seg(q), b = p.b0 + local;
-    const double* roots = (s_par[q] ? s_rb : s_ra) + q * S;
-    const double* vals = (s_par[q] ? s_ra : s_rb) + q * S;
+    const double* roots = s_root + q * S;
+    const double* vals = s_val + q * S;
     const double lo = s_lo[q], hi = s_hi[q];
-    const int na = s_na[q];
+    const int na = s_nroot[q];
     double mn_v = 1.7976931348623157e308, mx_v = -1.7976931348623157e308, mn_t = 0.0, mx_t = 0.0;
     const size_t rec_k = (size_t)K * p.max_cand;
     int w = 0;
