@@ -16,9 +16,9 @@
 // iteration on the power form, started at the zero crossing of the control polygon (quadratically close to the
 // root) and stopped when |g(t)| falls inside its own rounding-error bound. On min-snap segments one split per
 // problem is typical (0.8-1.0 on average) against 15 levels x 2-5 brackets for a derivative-chain isolator:
-// ~1e3 instead of ~4.5e3 multiply-adds per problem and no level loop. Coefficients below 1e-13 of the largest
+// ~1e3 instead of ~4.5e3 multiply-adds per problem and no level loop. Coefficients below 1e-12 of the largest
 // Bernstein coefficient count as zero: that removes the numerically 7-fold root a rest-to-rest segment has AT its
-// end point (the end points are candidates anyway) and can only hide a root PAIR whose dip of g is below 1e-13
+// end point (the end points are candidates anyway) and can only hide a root PAIR whose dip of g is below 1e-12
 // of its scale — not an extremum of the magnitude at any tolerance used here. All loops are bounded.
 //
 // Mapping (warp-cooperative). One warp owns kExG = 16 root problems ((trajectory, segment) pairs, contiguous in
@@ -343,7 +343,9 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
         s_qa[sl] = 0.0;
         s_qb[sl] = s_hi[q] - s_lo[q];
         s_qm[sl] = q;
-        s_eps[q] = 1e-13 * mx;
+        // "zero" for the sign-variation count: solved trajectories carry ~1e-13 of coefficient noise (the
+        // multiple root at a rest-to-rest end is not exact in the data), exact input polynomials only rounding
+        s_eps[q] = (p.raw ? 1e-14 : 1e-12) * mx;
         if (c == 0.0) s_root[q * S + atomicAdd(&s_nroot[q], 1)] = 0.0;  // a root exactly on the left end
       }
       if (li == n && c == 0.0) s_root[q * S + atomicAdd(&s_nroot[q], 1)] = s_hi[q] - s_lo[q];  // ... on the right end

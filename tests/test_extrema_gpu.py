@@ -44,7 +44,14 @@ def check_against_oracle(po, coeffs, times, der, r, idx):
         assert abs(r["max_time"][b] - Mt) <= 1e-6 * times[b][Ms], (b, r["max_time"][b], Mt)
         assert abs(r["min_value"][b] - mv) <= 1e-9 * Mv
         if mv > 1e-6 * Mv:   # a genuine interior minimum, not the ~0 of a rest-to-rest end
-            assert r["min_seg"][b] == ms and abs(r["min_time"][b] - mt) <= 1e-6 * times[b][ms]
+            same_place = r["min_seg"][b] == ms and abs(r["min_time"][b] - mt) <= 1e-6 * times[b][ms]
+            if not same_place:
+                # ... or an equally good one: next to a rest vertex the magnitude is flat to rounding over ~1e-3 T
+                # (five vanishing derivatives), and which point of the plateau a root finder reports is its own
+                # business — the oracle's magnitude at the reported time must equal its minimum
+                t_abs = float(np.sum(times[b][:r["min_seg"][b]]) + r["min_time"][b])
+                val = np.sqrt(np.sum(po.traj_evaluate(coeffs[b], times[b], t_abs, der)[0] ** 2))
+                assert abs(val - mv) <= 1e-12 * Mv, (b, r["min_time"][b], mt, val, mv)
         # per-segment maxima = what computeMaximumOfMagnitude (LIN_I:455-487) consumes
         t, v, s = po.opt_max_magnitude(coeffs[b], times[b], der)
         assert abs(r["seg_max_value"][b].max() - v) <= 1e-9 * v and int(np.argmax(r["seg_max_value"][b])) == s
