@@ -161,14 +161,14 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   auto prob_seg = [&](int q) -> int { return AOS ? (int)((flat0 + q) % K) : seg0; };
 
   unsigned char* base_ptr = smem_raw + pl.warp_bytes * warp;
-  double* s_g = reinterpret_cast<double*>(base_ptr);  // power coefficients of g in s = t - lo
-  double* s_root = s_g + G * S;                       // roots found (in s), unsorted until the end
+  double* s_g = reinterpret_cast<double*>(base_ptr);  // power coefficients of g
+  double* s_root = s_g + G * S;                       // roots found, unsorted until the end
   double* s_val = s_root + G * S;                     // scratch: scaled coefficients, later candidate values
   double* s_lo = s_val + G * S;
   double* s_hi = s_lo + G;
   double* s_eps = s_hi + G;                           // coefficients below this count as zero
   double* s_qc = s_eps + G;                           // interval stack: Bernstein coefficients [QC][LPI]
-  double* s_qa = s_qc + QC * LPI;                     //   interval ends (in s)
+  double* s_qa = s_qc + QC * LPI;                     //   interval ends
   double* s_qb = s_qa + QC;
   double* s_ba = s_qb + QC;                           // bracket queue: ends and first iterate
   double* s_bb = s_ba + kExBr;
@@ -279,79 +279,19 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   }
   // strip zero leading coefficients (findLastNonZeroCoeff, rpoly_ak1.cpp:57-68); an interval that is empty or not
   // finite has no roots either
-  bool any_shift = false;
   {
     int n = -1;
-    bool shift = false;
     if (lane < np) {
       n = len - 1;
       while (n >= 0 && !(fabs(s_g[lane * S + n]) >= 2.2250738585072014e-308)) --n;
       const double L = s_hi[lane] - s_lo[lane];
       if (!(L > 0.0) || !(L < 1.7e308)) n = min(n, 0);
-      shift = n >= 1 && s_lo[lane] != 0.0;
     }
     if (lane < G) s_n[lane] = n;
-    any_shift = __any_sync(FULL, shift);
     __syncwarp();
   }
-  // ---- Taylor shift to s = t - lo where an interval does not start at 0 (only explicit t_start / raw roots)
-  if (any_shift && lane < np && s_n[lane] >= 1 && s_lo[lane] != 0.0) {
-    double* gq = s_g + lane * S;
-    const int n = s_n[lane];
-    const double lo = s_lo[lane];
-    for (int i = 0; i < n; ++i)
-      for (int j = n - 1; j >= i; --j) gq[j] = fma(lo, gq[j + 1], gq[j]);
-  }
-  __syncwarp();
-  // ---- Bernstein coefficients on [0, L]: b_i = sum_{j <= i} [C(i,j) / C(n,j)] g_j L^j, C(i,j)/C(n,j) = B(j,i)/B(j,n)
-  {
-    const int q = lane & 15;
-    const int n = q < np ? s_n[q] : -1;
-    if (n >= 1) {
-      const double L = s_hi[q] - s_lo[q];
-      double lp = (lane >> 4) ? L : 1.0;
-      const double L2 = L * L;
-      for (int j = lane >> 4; j <= n; j += 2) {
-        s_val[q * S + j] = s_g[q * S + j] * lp / s_base[j * MTG_BASE_LD + n];
-        lp *= L2;
-      }
-    }
-  }
-  __syncwarp();
   const int GP = 32 / LPI;            // intervals per warp step
   const int gi = lane / LPI, li = lane - gi * LPI;
-  const unsigned gmask = LPI == 32 ? FULL : (0xffffu << (16 * gi));
-  for (int q0 = 0; q0 < np; q0 += GP) {
-    const int q = q0 + gi;
-    const int n = q < np ? s_n[q] : -1;
-    double c = 0.0;
-    if (n >= 1 && li <= n) {
-      const double* aq = s_val + q * S;
-      for (int j = 0; j <= li; ++j) c = fma(s_base[j * MTG_BASE_LD + li], aq[j], c);
-    }
-    // scale of the problem: the largest coefficient
-    double mx = fabs(c);
-#pragma unroll
-    for (int m = 8; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, m));
-    if (LPI == 32) mx = fmax(mx, __shfl_xor_sync(FULL, mx, 16));
-    int slot = 0;
-    if (n >= 1 && li == 0) slot = atomicAdd(s_top, 1);  // one slot per interval, drawn by the group's first lane
-    const int sl = __shfl_sync(FULL, slot, gi * LPI);
-    if (n >= 1) {
-      s_qc[sl * LPI + li] = c;
-      if (li == 0) {
-        s_qa[sl] = 0.0;
-        s_qb[sl] = s_hi[q] - s_lo[q];
-        s_qm[sl] = q;
-        // "zero" for the sign-variation count: solved trajectories carry ~1e-13 of coefficient noise (the
-        // multiple root at a rest-to-rest end is not exact in the data), exact input polynomials only rounding
-        s_eps[q] = (p.raw ? 1e-14 : 1e-12) * mx;
-        if (c == 0.0) s_root[q * S + atomicAdd(&s_nroot[q], 1)] = 0.0;  // a root exactly on the left end
-      }
-      if (li == n && c == 0.0) s_root[q * S + atomicAdd(&s_nroot[q], 1)] = s_hi[q] - s_lo[q];  // ... on the right end
-    }
-    __syncwarp();
-  }
 
   // Newton polish of the queued brackets, one per lane: value, slope and the running rounding-error bound of the
   // value from one coefficient stream (p and p' by the coupled Horner recurrence, err = sum |c_j| |t|^j)
@@ -411,119 +351,196 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
     __syncwarp();
   };
 
-  // ---- isolate: pop intervals, count sign variations, split or queue
-  for (;;) {
-    __syncwarp();
-    const int top = *s_top;
-    if (top == 0) break;
-    const int take = min(GP, top);
-    __syncwarp();
-    if (lane == 0) *s_top = top - take;
-    const bool have = gi < take;
-    const int sl = top - 1 - gi;
-    double c = 0.0, a = 0.0, b = 0.0, eps = 0.0;
-    int q = 0, depth = 0, n = 0;
-    if (have) {
-      const int meta = s_qm[sl];
-      q = meta & 255;
-      depth = meta >> 8;
-      n = s_n[q];
-      a = s_qa[sl];
-      b = s_qb[sl];
-      eps = s_eps[q];
-      if (li <= n) c = s_qc[sl * LPI + li];
-    }
-    __syncwarp();  // the popped slots may be overwritten by the pushes below
-    const unsigned shiftg = LPI == 32 ? 0u : 16u * gi;
-    const unsigned lmask = LPI == 32 ? FULL : 0xffffu;
-    const unsigned P = (__ballot_sync(FULL, have && li <= n && c > eps) >> shiftg) & lmask;
-    const unsigned M = (__ballot_sync(FULL, have && li <= n && c < -eps) >> shiftg) & lmask;
-    const unsigned nz = P | M;
-    // a sign change starts at i: i is non-zero and the next non-zero coefficient above it has the other sign
-    int nxt = -1;
-    bool var = false;
-    if ((nz >> li) & 1u) {
-      const unsigned above = li >= 31 ? 0u : (nz & ~((2u << li) - 1u));
-      if (above) {
-        nxt = __ffs(above) - 1;
-        var = ((P >> li) & 1u) != ((P >> nxt) & 1u);
-      }
-    }
-    const unsigned Vm = (__ballot_sync(FULL, var) >> shiftg) & lmask;
-    const int V = __popc(Vm);
-    const bool room = *s_top + 2 * GP <= QC;   // read before anybody pushes (uniform)
-    const bool leaf = have && V >= 1 && (V == 1 || depth >= kBernDepth || !room);
-    const bool split = have && V >= 2 && !leaf;
-    if (have && V >= 2 && leaf && li == 0 && !room) atomicOr(&s_st[q], 16);
-    // the first crossing of the control polygon: between coefficients i0 and j0
-    const int i0 = Vm ? __ffs(Vm) - 1 : 0;
-    const int j0 = __shfl_sync(FULL, nxt, gi * LPI + i0);
-    const double ci = __shfl_sync(FULL, c, gi * LPI + i0);
-    const double cj = __shfl_sync(FULL, c, gi * LPI + max(j0, 0));
-    if (leaf && li == 0) {
-      double u = ((double)i0 + ci / (ci - cj) * (double)(j0 - i0)) / (double)n;
-      double t = a + u * (b - a);
-      if (!(t > a && t < b)) t = 0.5 * (a + b);
-      const int e = atomicAdd(s_nbr, 1);
-      s_ba[e] = a;
-      s_bb[e] = b;
-      s_bt[e] = t;
-      s_bm[e] = q | (((M >> (__ffs(nz) - 1)) & 1u) << 8);  // sign of g just right of a
-    }
-    if (__any_sync(FULL, split)) {
-      // de Casteljau at the midpoint: after round r lane i <= n - r holds b_i^(r); the left child is lane 0's value
-      // after every round, the right child is what the lanes hold at the end
-      double cur = c, left = c;
-      int nmax = split ? n : 0;
-#pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, m));
-      for (int r = 1; r <= nmax; ++r) {
-        const double up = __shfl_down_sync(FULL, cur, 1, LPI);
-        if (split && li <= n - r) cur = 0.5 * (cur + up);
-        const double l0 = __shfl_sync(FULL, cur, gi * LPI);
-        if (li == r) left = l0;
-      }
-      int basei = 0;
-      if (split && li == 0) basei = atomicAdd(s_top, 2);
-      basei = __shfl_sync(FULL, basei, gi * LPI);
-      if (split) {
-        const double mid = 0.5 * (a + b);
-        s_qc[basei * LPI + li] = li <= n ? cur : 0.0;         // right child first: the left one is popped first
-        s_qc[(basei + 1) * LPI + li] = li <= n ? left : 0.0;
-        if (li == 0) {
-          s_qa[basei] = mid;
-          s_qb[basei] = b;
-          s_qm[basei] = q | ((depth + 1) << 8);
-          s_qa[basei + 1] = a;
-          s_qb[basei + 1] = mid;
-          s_qm[basei + 1] = q | ((depth + 1) << 8);
-          if (cur == 0.0) {  // g vanishes exactly at the midpoint: neither child would see it
-            const int slot = atomicAdd(&s_nroot[q], 1);
-            if (slot < S) s_root[q * S + slot] = mid;
-          }
+  // ---- isolate. The Bernstein coefficients of g on an interval that starts at t = 0 come straight from the power
+  // coefficients: b_i = sum_{j <= i} [C(i,j) / C(n,j)] g_j E^j (C(i,j)/C(n,j) = B(j,i)/B(j,n)), E the far end — as
+  // well conditioned as evaluating g. A Taylor shift to t_start is NOT (it loses ~(1 + |t_start|)^n), so an
+  // interval [lo, hi] is covered from the origin instead: side 0 isolates on [0, hi], side 1 on [lo, 0] (E = lo,
+  // coefficients stored in reverse so that the interval still runs left to right); pieces outside [lo, hi] are
+  // dropped when they are popped and roots outside it at the end. Segment extrema (lo = 0) only have side 0.
+  const int nsides = (p.t_lo != nullptr) ? 2 : 1;
+  for (int side = 0; side < nsides; ++side) {
+    {
+      const int q = lane & 15;
+      const int n = q < np ? s_n[q] : -1;
+      const double E = side == 0 ? s_hi[q] : s_lo[q];
+      if (n >= 1 && (side == 0 ? E > 0.0 : E < 0.0)) {
+        double lp = (lane >> 4) ? E : 1.0;
+        const double E2 = E * E;
+        for (int j = lane >> 4; j <= n; j += 2) {
+          s_val[q * S + j] = s_g[q * S + j] * lp / s_base[j * MTG_BASE_LD + n];
+          lp *= E2;
         }
       }
     }
     __syncwarp();
-    if (*s_nbr > kExBr - GP) drain();
+    for (int q0 = 0; q0 < np; q0 += GP) {
+      const int q = q0 + gi;
+      int n = q < np ? s_n[q] : -1;
+      if (n >= 1 && !(side == 0 ? s_hi[q] > 0.0 : s_lo[q] < 0.0)) n = -1;
+      double c = 0.0;
+      if (n >= 1 && li <= n) {
+        const double* aq = s_val + q * S;
+        for (int j = 0; j <= li; ++j) c = fma(s_base[j * MTG_BASE_LD + li], aq[j], c);
+      }
+      // scale of the problem: the largest coefficient
+      double mx = fabs(c);
+#pragma unroll
+      for (int m = 8; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, m));
+      if (LPI == 32) mx = fmax(mx, __shfl_xor_sync(FULL, mx, 16));
+      int slot = 0;
+      if (n >= 1 && li == 0) slot = atomicAdd(s_top, 1);  // one slot per interval, drawn by the group's first lane
+      const int sl = __shfl_sync(FULL, slot, gi * LPI);
+      if (n >= 1) {
+        if (li <= n) s_qc[sl * LPI + (side == 0 ? li : n - li)] = c;
+        if (li == 0) {
+          s_qa[sl] = side == 0 ? 0.0 : s_lo[q];
+          s_qb[sl] = side == 0 ? s_hi[q] : 0.0;
+          s_qm[sl] = q;
+          // "zero" for the sign-variation count: solved trajectories carry ~1e-13 of coefficient noise (the
+          // multiple root at a rest-to-rest end is not exact in the data), exact input polynomials only rounding
+          s_eps[q] = (p.raw ? 1e-14 : 1e-12) * mx;
+          // a root exactly at t = 0 (once: side 1 leaves it to side 0 when both run)
+          if (c == 0.0 && (side == 0 || !(s_hi[q] > 0.0))) s_root[q * S + atomicAdd(&s_nroot[q], 1)] = 0.0;
+        }
+        if (li == n && c == 0.0)  // ... exactly on the far end
+          s_root[q * S + atomicAdd(&s_nroot[q], 1)] = side == 0 ? s_hi[q] : s_lo[q];
+      }
+      __syncwarp();
+    }
+
+    // pop intervals, count sign variations, split or queue
+    for (;;) {
+      __syncwarp();
+      const int top = *s_top;
+      if (top == 0) break;
+      const int take = min(GP, top);
+      __syncwarp();
+      if (lane == 0) *s_top = top - take;
+      const bool have = gi < take;
+      const int sl = top - 1 - gi;
+      double c = 0.0, a = 0.0, b = 0.0, eps = 0.0;
+      int q = 0, depth = 0, n = 0;
+      if (have) {
+        const int meta = s_qm[sl];
+        q = meta & 255;
+        depth = meta >> 8;
+        n = s_n[q];
+        a = s_qa[sl];
+        b = s_qb[sl];
+        eps = s_eps[q];
+        if (li <= n) c = s_qc[sl * LPI + li];
+      }
+      const bool live = have && !(b < s_lo[q] || a > s_hi[q]);  // a piece outside [lo, hi] is dropped
+      __syncwarp();  // the popped slots may be overwritten by the pushes below
+      const unsigned shiftg = LPI == 32 ? 0u : 16u * gi;
+      const unsigned lmask = LPI == 32 ? FULL : 0xffffu;
+      const unsigned P = (__ballot_sync(FULL, live && li <= n && c > eps) >> shiftg) & lmask;
+      const unsigned M = (__ballot_sync(FULL, live && li <= n && c < -eps) >> shiftg) & lmask;
+      const unsigned nz = P | M;
+      // a sign change starts at i: i is non-zero and the next non-zero coefficient above it has the other sign
+      int nxt = -1;
+      bool var = false;
+      if ((nz >> li) & 1u) {
+        const unsigned above = li >= 31 ? 0u : (nz & ~((2u << li) - 1u));
+        if (above) {
+          nxt = __ffs(above) - 1;
+          var = ((P >> li) & 1u) != ((P >> nxt) & 1u);
+        }
+      }
+      const unsigned Vm = (__ballot_sync(FULL, var) >> shiftg) & lmask;
+      const int V = __popc(Vm);
+      const bool room = *s_top + 2 * GP <= QC;   // read before anybody pushes (uniform)
+      const bool leaf = have && V >= 1 && (V == 1 || depth >= kBernDepth || !room);
+      const bool split = have && V >= 2 && !leaf;
+      if (have && V >= 2 && leaf && li == 0 && !room) atomicOr(&s_st[q], 16);
+      // the first crossing of the control polygon: between coefficients i0 and j0
+      const int i0 = Vm ? __ffs(Vm) - 1 : 0;
+      const int j0 = __shfl_sync(FULL, nxt, gi * LPI + i0);
+      const double ci = __shfl_sync(FULL, c, gi * LPI + i0);
+      const double cj = __shfl_sync(FULL, c, gi * LPI + max(j0, 0));
+      if (leaf && li == 0) {
+        double u = ((double)i0 + ci / (ci - cj) * (double)(j0 - i0)) / (double)n;
+        double t = a + u * (b - a);
+        if (!(t > a && t < b)) t = 0.5 * (a + b);
+        const int e = atomicAdd(s_nbr, 1);
+        s_ba[e] = a;
+        s_bb[e] = b;
+        s_bt[e] = t;
+        s_bm[e] = q | (((M >> (__ffs(nz) - 1)) & 1u) << 8);  // sign of g just right of a
+      }
+      if (__any_sync(FULL, split)) {
+        // de Casteljau at the midpoint: after round r lane i <= n - r holds b_i^(r); the left child is lane 0's value
+        // after every round, the right child is what the lanes hold at the end
+        double cur = c, left = c;
+        int nmax = split ? n : 0;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, m));
+        for (int r = 1; r <= nmax; ++r) {
+          const double up = __shfl_down_sync(FULL, cur, 1, LPI);
+          if (split && li <= n - r) cur = 0.5 * (cur + up);
+          const double l0 = __shfl_sync(FULL, cur, gi * LPI);
+          if (li == r) left = l0;
+        }
+        // A root ON the split point: the shared coefficient g(mid) is then negligible for both children and neither
+        // would see the sign change that runs through it. If the nearest non-negligible coefficients on its two sides
+        // differ in sign, the root is queued directly, bracketed by one control-point spacing on either side.
+        const unsigned PL = (__ballot_sync(FULL, split && li <= n && left > eps) >> shiftg) & lmask;
+        const unsigned ML = (__ballot_sync(FULL, split && li <= n && left < -eps) >> shiftg) & lmask;
+        const unsigned PR = (__ballot_sync(FULL, split && li <= n && cur > eps) >> shiftg) & lmask;
+        const unsigned MR = (__ballot_sync(FULL, split && li <= n && cur < -eps) >> shiftg) & lmask;
+        int basei = 0;
+        if (split && li == 0) basei = atomicAdd(s_top, 2);
+        basei = __shfl_sync(FULL, basei, gi * LPI);
+        if (split) {
+          const double mid = 0.5 * (a + b);
+          s_qc[basei * LPI + li] = li <= n ? cur : 0.0;         // right child first: the left one is popped first
+          s_qc[(basei + 1) * LPI + li] = li <= n ? left : 0.0;
+          if (li == 0) {
+            s_qa[basei] = mid;
+            s_qb[basei] = b;
+            s_qm[basei] = q | ((depth + 1) << 8);
+            s_qa[basei + 1] = a;
+            s_qb[basei + 1] = mid;
+            s_qm[basei + 1] = q | ((depth + 1) << 8);
+            const unsigned nzl = (PL | ML) & ((1u << n) - 1u);   // left child without the shared coefficient (index n)
+            const unsigned nzr = (PR | MR) & ~1u;                // right child without it (index 0)
+            if (!(((PL | ML) >> n) & 1u) && nzl && nzr) {
+              const int il = 31 - __clz(nzl), ir = __ffs(nzr) - 1;
+              const bool negl = (ML >> il) & 1u, negr = (MR >> ir) & 1u;
+              if (negl != negr) {
+                const double h = (b - a) / (double)(2 * n);
+                const int e = atomicAdd(s_nbr, 1);
+                s_ba[e] = mid - h;
+                s_bb[e] = mid + h;
+                s_bt[e] = mid;
+                s_bm[e] = q | ((negl ? 1 : 0) << 8);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (*s_nbr > kExBr - 2 * GP) drain();
+    }
   }
   drain();
-  // roots ascending, back in t = lo + s; constant polynomial: none (rpoly_ak1.cpp:76-80)
+  // roots inside [lo, hi], ascending; constant polynomial: none (rpoly_ak1.cpp:76-80)
   if (lane < np) {
     double* rq = s_root + lane * S;
-    const int nr = min(s_nroot[lane], S - 2);
-    for (int i = 1; i < nr; ++i) {
+    const int nall = min(s_nroot[lane], S - 2);
+    const double lo = s_lo[lane], hi = s_hi[lane];
+    int nr = 0;
+    for (int i = 0; i < nall; ++i) {
       const double x = rq[i];
-      int j = i - 1;
+      if (!(x >= lo && x <= hi)) continue;
+      int j = nr - 1;
       while (j >= 0 && rq[j] > x) {
         rq[j + 1] = rq[j];
         --j;
       }
       rq[j + 1] = x;
+      ++nr;
     }
-    const double lo = s_lo[lane];
-    if (lo != 0.0)
-      for (int i = 0; i < nr; ++i) rq[i] += lo;
     s_nroot[lane] = nr;
   }
   __syncwarp();
