@@ -47,6 +47,9 @@ constexpr int kBernDepth = 30;      // halvings of one interval before it is tak
 constexpr int kExG = 16;            // root problems per warp
 constexpr int kExWarps = 8;         // warps per CTA
 constexpr int kExBr = 64;           // bracket queue of a warp
+#ifndef MTG_EX_MINB
+#define MTG_EX_MINB 2                // resident CTAs the register allocation aims for (shared memory allows 2)
+#endif
 static_assert(kExG == 16, "extrema_warp_kernel maps problem = lane & 15");
 
 struct ExtremaParams {
@@ -111,9 +114,9 @@ __host__ __device__ inline ExtremaPlan extrema_plan(int N, int D, int derivative
   if (stage > qc) qc = stage;
   pl.qc = qc;
   // doubles: g, roots, values [G][S]; lo, hi, eps [G]; stack coefficients [qc][lpi], a, b [qc]; brackets a, b, t [kExBr]
-  // ints: n, nroot, st [G]; stack meta [qc]; bracket meta [kExBr]; top, nbr
+  // ints: n, nroot, st, trajectory, segment [G]; stack meta [qc]; bracket meta [kExBr]; top, nbr
   size_t bytes = (size_t)(3 * kExG * S + 3 * kExG + qc * pl.lpi + 2 * qc + 3 * kExBr) * sizeof(double) +
-                 (size_t)(3 * kExG + qc + kExBr + 2) * sizeof(int);
+                 (size_t)(5 * kExG + qc + kExBr + 2) * sizeof(int);
   pl.warp_bytes = (bytes + 15) & ~(size_t)15;
   pl.cta_bytes = pl.warp_bytes * kExWarps + (size_t)MTG_BASE_LD * MTG_BASE_LD * sizeof(double);
   return pl;
@@ -126,7 +129,7 @@ namespace mtg {
 int launch_extrema(mtg_ctx* ctx, bool aos, const ExtremaParams& p, cudaStream_t s);
 
 template <bool AOS>
-__global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const ExtremaParams p) {
+__global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kernel(const ExtremaParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ExtremaPlan pl = extrema_plan(p.N, p.D, p.derivative, p.dim_mask, p.raw);
   const int len = pl.len, S = pl.S, nd = pl.nd, G = kExG, LPI = pl.lpi, QC = pl.qc;
@@ -176,7 +179,9 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   int* s_n = reinterpret_cast<int*>(s_bt + kExBr);    // degree of g
   int* s_nroot = s_n + G;
   int* s_st = s_nroot + G;
-  int* s_qm = s_st + G;                               // stack meta: problem | depth << 8
+  int* s_pb = s_st + G;                               // trajectory (batch index) and segment of every problem
+  int* s_ps = s_pb + G;
+  int* s_qm = s_ps + G;                               // stack meta: problem | depth << 8
   int* s_bm = s_qm + QC;                              // bracket meta: problem | (g < 0 left of the root) << 8
   int* s_top = s_bm + kExBr;
   int* s_nbr = s_top + 1;
@@ -188,12 +193,16 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   // ---- interval of every problem
   if (lane < G) {
     double lo = 0.0, hi = 1.0;
+    int b = 0, seg = 0;
     if (lane < np) {
-      const int b = p.b0 + prob_local(lane), seg = prob_seg(lane);
+      b = p.b0 + prob_local(lane);
+      seg = prob_seg(lane);
       const size_t o = at<AOS>((size_t)seg, (size_t)K, Bsz, (size_t)b);
       lo = p.t_lo ? p.t_lo[o] : 0.0;
       hi = p.t_hi ? p.t_hi[o] : p.seg_times[o];
     }
+    s_pb[lane] = b;
+    s_ps[lane] = seg;
     s_lo[lane] = lo;
     s_hi[lane] = hi;
     s_st[lane] = 0;
@@ -204,41 +213,60 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
     *s_nbr = 0;
   }
 
-  // Stages the derivative coefficients delta[dim][j] = B(d, j+d) c[j+d] (polynomial.h:99-113) of all
-  // problems at `dst` (stride sd per problem, dims not in dim_mask zeroed), coalesced in both layouts.
+  // Stages the derivative coefficients delta[dim][j] = B(d, j+d) c[j+d] (polynomial.h:99-113) of all problems at
+  // `dst` (stride sd per problem, dims not in dim_mask zeroed) and, if wanted, delta'[dim][j] = (j+1) delta[dim][j+1]
+  // at `dpr` (stride sdp, nd - 1 per dimension). Element e = lane + 32 k walks memory in order in both layouts;
+  // the loads of kStageU elements are issued before the first is used (one memory round trip per batch).
   // In raw mode the record is the polynomial itself.
-  auto stage_delta = [&](double* dst, int sd) {
+  constexpr int kStageU = 8;
+  auto stage_delta = [&](double* dst, int sd, double* dpr, int sdp) {
     const int n_el = np * rec_one;
-    // element e = lane + 32 k walks memory in order; (q, r) follow it with counters (no division per element)
-    int q = AOS ? lane / rec_one : 0, r = AOS ? lane - q * rec_one : lane / np;
-    int qs = AOS ? 0 : lane - r * np;  // SoA: problem within the row of 16
-    for (int e = lane; e < n_el; e += 32) {
-      const int qq = AOS ? q : qs;
-      const int b = p.b0 + prob_local(qq), seg = prob_seg(qq);
-      if (p.raw) {
-        dst[qq * sd + r] = p.coeffs[at<AOS>((size_t)r, rec_c, Bsz, (size_t)b)];
-      } else {
-        int dim = 0, jj = r;
-        while (jj >= N) {
-          jj -= N;
-          ++dim;
-        }
-        if (jj >= d) {
-          const double c = p.coeffs[at<AOS>((size_t)(seg * D + dim) * N + jj, rec_c, Bsz, (size_t)b)];
-          dst[qq * sd + dim * nd + (jj - d)] = ((p.dim_mask >> dim) & 1) ? s_base[d * MTG_BASE_LD + jj] * c : 0.0;
+    const float inv_a = 1.0f / (float)(AOS ? rec_one : np), inv_N = 1.0f / (float)N;
+    for (int e0 = lane; e0 < n_el; e0 += 32 * kStageU) {
+      double v[kStageU];
+      int qv[kStageU], rv[kStageU];
+#pragma unroll
+      for (int u = 0; u < kStageU; ++u) {
+        const int e = e0 + 32 * u;
+        v[u] = 0.0;
+        qv[u] = -1;
+        rv[u] = 0;
+        if (e < n_el) {
+          int q, r;
+          if (AOS) {
+            q = (int)(((float)e + 0.5f) * inv_a);
+            r = e - q * rec_one;
+          } else {
+            r = (int)(((float)e + 0.5f) * inv_a);
+            q = e - r * np;
+          }
+          const int b = s_pb[q], seg = s_ps[q];
+          if (p.raw) {
+            v[u] = p.coeffs[at<AOS>((size_t)r, rec_c, Bsz, (size_t)b)];
+            qv[u] = q;
+            rv[u] = r;
+          } else {
+            const int dim = (int)(((float)r + 0.5f) * inv_N);
+            const int jj = r - dim * N;
+            if (jj >= d) {
+              v[u] = p.coeffs[at<AOS>((size_t)(seg * D + dim) * N + jj, rec_c, Bsz, (size_t)b)];
+              qv[u] = q;
+              rv[u] = dim | (jj << 8);
+            }
+          }
         }
       }
-      if (AOS) {
-        r += 32;
-        while (r >= rec_one) {
-          r -= rec_one;
-          ++q;
-        }
-      } else {
-        qs += 32;
-        while (qs >= np) {
-          qs -= np;
-          ++r;
+#pragma unroll
+      for (int u = 0; u < kStageU; ++u) {
+        const int q = qv[u];
+        if (q < 0) continue;
+        if (p.raw) {
+          dst[q * sd + rv[u]] = v[u];
+        } else {
+          const int dim = rv[u] & 255, jj = rv[u] >> 8, j = jj - d;
+          const double dv = ((p.dim_mask >> dim) & 1) ? s_base[d * MTG_BASE_LD + jj] * v[u] : 0.0;
+          dst[q * sd + dim * nd + j] = dv;
+          if (dpr && j >= 1) dpr[q * sdp + dim * (nd - 1) + j - 1] = (double)j * dv;
         }
       }
     }
@@ -247,13 +275,15 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   // ---- g: the polynomial whose real roots in [lo, hi] are the candidate times
   {
     double* s_delta = s_root;  // [roots | values] holds D * nd doubles per problem at this point
-    const int sd = p.raw ? N : D * nd;
-    stage_delta(s_delta, sd);
+    double* s_dpr = s_qc;      // delta' in the (still empty) interval stack
+    const int sd = p.raw ? N : D * nd, sdp = D * (nd - 1);
+    stage_delta(s_delta, sd, pl.ndim > 1 ? s_dpr : nullptr, sdp);
     __syncwarp();
     // lane = (problem q, coefficient m = 2 k + half): 16 problems x 2 lanes, conflict-free odd strides
     const int q = lane & 15;
     if (q < np) {
       const double* dl = s_delta + q * sd;
+      const double* dp = s_dpr + q * sdp;
       for (int m = lane >> 4; m < len; m += 2) {
         double acc = 0.0;
         if (p.raw) {
@@ -262,11 +292,9 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
           // sum_dim conv(delta, delta'), delta'[j] = (j+1) delta[j+1]   (segment.cpp:93-115)
           const int i0 = max(0, m - (nd - 2)), i1 = min(m, nd - 1);
           for (int dim = 0; dim < D; ++dim) {
-            double f = (double)(m - i0 + 1);
-            for (int i = i0; i <= i1; ++i) {
-              acc = fma(dl[dim * nd + i], f * dl[dim * nd + m - i + 1], acc);
-              f -= 1.0;
-            }
+            const double* x = dl + dim * nd;
+            const double* y = dp + dim * (nd - 1) + m;
+            for (int i = i0; i <= i1; ++i) acc = fma(x[i], y[-i], acc);
           }
         } else {
           // one dimension: roots of p^(d+1)   (segment.cpp:124-131); the other dimensions are staged as zeros
@@ -459,7 +487,11 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
       const double ci = __shfl_sync(FULL, c, gi * LPI + i0);
       const double cj = __shfl_sync(FULL, c, gi * LPI + max(j0, 0));
       if (leaf && li == 0) {
-        double u = ((double)i0 + ci / (ci - cj) * (double)(j0 - i0)) / (double)n;
+        // a starting point needs no more than a few digits: approximate reciprocals instead of two divisions
+        double rc;
+        const double dc = ci - cj;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(dc));
+        const double u = ((double)i0 + ci * rc * (double)(j0 - i0)) * (double)__frcp_rn((float)n);
         double t = a + u * (b - a);
         if (!(t > a && t < b)) t = 0.5 * (a + b);
         const int e = atomicAdd(s_nbr, 1);
@@ -549,7 +581,7 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   if (p.raw) {
     if (lane < np) {
       const int q = lane;
-      const int b = p.b0 + prob_local(q), seg = prob_seg(q);
+      const int b = s_pb[q], seg = s_ps[q];
       const double* roots = s_root + q * S;
       const int na = s_nroot[q];
       const size_t rec_k = (size_t)K * p.max_cand;
@@ -567,7 +599,7 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   // ---- candidates [t_start, t_end, roots...]: |p^(d)(t)| = sqrt(sum_dim evaluate(t, d)^2)  (segment.cpp:135-158)
   double* s_delta = s_qc;  // the interval stack is empty now
   const int sd = D * nd;
-  stage_delta(s_delta, sd);
+  stage_delta(s_delta, sd, nullptr, 0);
   __syncwarp();
   {
     // lane = (problem, candidate parity): 16 problems x 2 lanes
@@ -592,7 +624,7 @@ __global__ void __launch_bounds__(kExWarps * 32) extrema_warp_kernel(const Extre
   __syncwarp();
   if (lane < np) {
     const int q = lane;
-    const int local = prob_local(q), seg = prob_seg(q), b = p.b0 + local;
+    const int b = s_pb[q], seg = s_ps[q], local = b - p.b0;
     const double* roots = s_root + q * S;
     const double* vals = s_val + q * S;
     const double lo = s_lo[q], hi = s_hi[q];
