@@ -45,8 +45,11 @@ constexpr int kMaxG = MTG_BASE_LD;  // 22 coefficients: Polynomial::kMaxConvolut
 constexpr int kRootIters = 64;      // Newton iterations per root (bisection fallback inside)
 constexpr int kBernDepth = 30;      // halvings of one interval before it is taken as it is
 constexpr int kExG = 16;            // root problems per warp
-constexpr int kExWarps = 8;         // warps per CTA
-constexpr int kExBr = 64;           // bracket queue of a warp
+#ifndef MTG_EX_WARPS
+#define MTG_EX_WARPS 10
+#endif
+constexpr int kExWarps = MTG_EX_WARPS;  // warps per CTA
+constexpr int kExBr = 32;           // bracket queue of a warp
 #ifndef MTG_EX_MINB
 #define MTG_EX_MINB 2                // resident CTAs the register allocation aims for (shared memory allows 2)
 #endif
@@ -102,20 +105,24 @@ __host__ __device__ inline ExtremaPlan extrema_plan(int N, int D, int derivative
   pl.len = raw ? N : (ndim > 1 ? 2 * pl.nd - 2 : pl.nd - 1);
   if (pl.len < 1) pl.len = 1;
   // every per-problem array holds <= len + 1 doubles (len coefficients; len - 1 roots + 2 end points);
-  // [roots | values] together must also hold the staged derivative coefficients (D * nd) while g is built
+  // [g | roots] together must also hold the staged derivative coefficients (D * nd) while g is built
   int S = (pl.len + 1) | 1;
   const int need = raw ? 0 : ((D * pl.nd + 1) / 2) | 1;
   if (need > S) S = need;
   pl.S = S;
   pl.lpi = pl.len <= 16 ? 16 : 32;
-  // the interval stack also stages the derivative coefficients for the candidate evaluation at the end
+  // the interval stack also stages delta' while g is built, the scaled coefficients while the first intervals are
+  // pushed (at its top end: slot k must not reach the coefficients of problems > k, see the kernel) and the
+  // derivative coefficients for the candidate evaluation at the end
   int qc = 32;
   const int stage = raw ? 0 : (kExG * D * pl.nd + pl.lpi - 1) / pl.lpi;
   if (stage > qc) qc = stage;
+  const int scaled = (kExG * S + (kExG - 1) * (pl.lpi > S ? pl.lpi - S : 0) + pl.lpi - 1) / pl.lpi;
+  if (scaled > qc) qc = scaled;
   pl.qc = qc;
-  // doubles: g, roots, values [G][S]; lo, hi, eps [G]; stack coefficients [qc][lpi], a, b [qc]; brackets a, b, t [kExBr]
+  // doubles: g, roots [G][S]; lo, hi, eps [G]; stack coefficients [qc][lpi], a, b [qc]; brackets a, b, t [kExBr]
   // ints: n, nroot, st, trajectory, segment [G]; stack meta [qc]; bracket meta [kExBr]; top, nbr
-  size_t bytes = (size_t)(3 * kExG * S + 3 * kExG + qc * pl.lpi + 2 * qc + 3 * kExBr) * sizeof(double) +
+  size_t bytes = (size_t)(2 * kExG * S + 3 * kExG + qc * pl.lpi + 2 * qc + 3 * kExBr) * sizeof(double) +
                  (size_t)(5 * kExG + qc + kExBr + 2) * sizeof(int);
   pl.warp_bytes = (bytes + 15) & ~(size_t)15;
   pl.cta_bytes = pl.warp_bytes * kExWarps + (size_t)MTG_BASE_LD * MTG_BASE_LD * sizeof(double);
@@ -164,10 +171,9 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
   auto prob_seg = [&](int q) -> int { return AOS ? (int)((flat0 + q) % K) : seg0; };
 
   unsigned char* base_ptr = smem_raw + pl.warp_bytes * warp;
-  double* s_g = reinterpret_cast<double*>(base_ptr);  // power coefficients of g
+  double* s_g = reinterpret_cast<double*>(base_ptr);  // power coefficients of g; at the end the candidate values
   double* s_root = s_g + G * S;                       // roots found, unsorted until the end
-  double* s_val = s_root + G * S;                     // scratch: scaled coefficients, later candidate values
-  double* s_lo = s_val + G * S;
+  double* s_lo = s_root + G * S;
   double* s_hi = s_lo + G;
   double* s_eps = s_hi + G;                           // coefficients below this count as zero
   double* s_qc = s_eps + G;                           // interval stack: Bernstein coefficients [QC][LPI]
@@ -274,33 +280,47 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
 
   // ---- g: the polynomial whose real roots in [lo, hi] are the candidate times
   {
-    double* s_delta = s_root;  // [roots | values] holds D * nd doubles per problem at this point
-    double* s_dpr = s_qc;      // delta' in the (still empty) interval stack
+    double* s_delta = s_g;  // [g | roots] holds D * nd doubles per problem until g replaces them
+    double* s_dpr = s_qc;   // delta' in the (still empty) interval stack
     const int sd = p.raw ? N : D * nd, sdp = D * (nd - 1);
     stage_delta(s_delta, sd, pl.ndim > 1 ? s_dpr : nullptr, sdp);
     __syncwarp();
-    // lane = (problem q, coefficient m = 2 k + half): 16 problems x 2 lanes, conflict-free odd strides
+    // lane = (problem q, coefficient m = 2 k + half): 16 problems x 2 lanes, conflict-free odd strides; the
+    // coefficients wait in registers until every lane has finished reading delta
     const int q = lane & 15;
+    double acc[kMaxG / 2];
     if (q < np) {
       const double* dl = s_delta + q * sd;
       const double* dp = s_dpr + q * sdp;
-      for (int m = lane >> 4; m < len; m += 2) {
-        double acc = 0.0;
-        if (p.raw) {
-          acc = dl[m];
-        } else if (pl.ndim > 1) {
-          // sum_dim conv(delta, delta'), delta'[j] = (j+1) delta[j+1]   (segment.cpp:93-115)
-          const int i0 = max(0, m - (nd - 2)), i1 = min(m, nd - 1);
-          for (int dim = 0; dim < D; ++dim) {
-            const double* x = dl + dim * nd;
-            const double* y = dp + dim * (nd - 1) + m;
-            for (int i = i0; i <= i1; ++i) acc = fma(x[i], y[-i], acc);
+#pragma unroll
+      for (int k = 0; k < kMaxG / 2; ++k) {
+        const int m = 2 * k + (lane >> 4);
+        double a = 0.0;
+        if (m < len) {
+          if (p.raw) {
+            a = dl[m];
+          } else if (pl.ndim > 1) {
+            // sum_dim conv(delta, delta'), delta'[j] = (j+1) delta[j+1]   (segment.cpp:93-115)
+            const int i0 = max(0, m - (nd - 2)), i1 = min(m, nd - 1);
+            for (int dim = 0; dim < D; ++dim) {
+              const double* x = dl + dim * nd;
+              const double* y = dp + dim * (nd - 1) + m;
+              for (int i = i0; i <= i1; ++i) a = fma(x[i], y[-i], a);
+            }
+          } else {
+            // one dimension: roots of p^(d+1)   (segment.cpp:124-131); the other dimensions are staged as zeros
+            for (int dim = 0; dim < D; ++dim) a += (double)(m + 1) * dl[dim * nd + m + 1];
           }
-        } else {
-          // one dimension: roots of p^(d+1)   (segment.cpp:124-131); the other dimensions are staged as zeros
-          for (int dim = 0; dim < D; ++dim) acc += (double)(m + 1) * dl[dim * nd + m + 1];
         }
-        s_g[q * S + m] = acc;
+        acc[k] = a;
+      }
+    }
+    __syncwarp();
+    if (q < np) {
+#pragma unroll
+      for (int k = 0; k < kMaxG / 2; ++k) {
+        const int m = 2 * k + (lane >> 4);
+        if (m < len) s_g[q * S + m] = acc[k];
       }
     }
     __syncwarp();
@@ -386,6 +406,9 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
   // coefficients stored in reverse so that the interval still runs left to right); pieces outside [lo, hi] are
   // dropped when they are popped and roots outside it at the end. Segment extrema (lo = 0) only have side 0.
   const int nsides = (p.t_lo != nullptr) ? 2 : 1;
+  // scaled power coefficients, at the top end of the (empty) stack: pass q0 pushes slots <= q0 + GP - 1 after it has
+  // read its own problems' coefficients, and extrema_plan() sizes the stack so that slot k ends below problem k + 1
+  double* s_sc = s_qc + QC * LPI - G * S;
   for (int side = 0; side < nsides; ++side) {
     {
       const int q = lane & 15;
@@ -395,7 +418,7 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
         double lp = (lane >> 4) ? E : 1.0;
         const double E2 = E * E;
         for (int j = lane >> 4; j <= n; j += 2) {
-          s_val[q * S + j] = s_g[q * S + j] * lp / s_base[j * MTG_BASE_LD + n];
+          s_sc[q * S + j] = s_g[q * S + j] * lp / s_base[j * MTG_BASE_LD + n];
           lp *= E2;
         }
       }
@@ -407,7 +430,7 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
       if (n >= 1 && !(side == 0 ? s_hi[q] > 0.0 : s_lo[q] < 0.0)) n = -1;
       double c = 0.0;
       if (n >= 1 && li <= n) {
-        const double* aq = s_val + q * S;
+        const double* aq = s_sc + q * S;
         for (int j = 0; j <= li; ++j) c = fma(s_base[j * MTG_BASE_LD + li], aq[j], c);
       }
       // scale of the problem: the largest coefficient
@@ -606,7 +629,7 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
     const int q = lane & 15;
     if (q < np) {
       const double* roots = s_root + q * S;
-      double* vals = s_val + q * S;
+      double* vals = s_g + q * S;
       const double* dl = s_delta + q * sd;
       const int nc = s_nroot[q] + 2;
       for (int c = lane >> 4; c < nc; c += 2) {
@@ -626,7 +649,7 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
     const int q = lane;
     const int b = s_pb[q], seg = s_ps[q], local = b - p.b0;
     const double* roots = s_root + q * S;
-    const double* vals = s_val + q * S;
+    const double* vals = s_g + q * S;
     const double lo = s_lo[q], hi = s_hi[q];
     const int na = s_nroot[q];
     double mn_v = 1.7976931348623157e308, mx_v = -1.7976931348623157e308, mn_t = 0.0, mx_t = 0.0;
