@@ -90,6 +90,7 @@ struct ExtremaPlan {
   int len;     // coefficients of g
   int S;       // stride (doubles) of the per-problem arrays g, roots, values
   int nd;      // coefficients of p^(d)
+  int sd;      // stride (doubles) of the staged derivative coefficients of one problem
   int ndim;    // dimensions taking part
   int lpi;     // lanes per interval (16 or 32)
   int qc;      // interval stack capacity
@@ -107,15 +108,16 @@ __host__ __device__ inline ExtremaPlan extrema_plan(int N, int D, int derivative
   // every per-problem array holds <= len + 1 doubles (len coefficients; len - 1 roots + 2 end points);
   // [g | roots] together must also hold the staged derivative coefficients (D * nd) while g is built
   int S = (pl.len + 1) | 1;
-  const int need = raw ? 0 : ((D * pl.nd + 1) / 2) | 1;
+  pl.sd = (raw ? N : D * pl.nd) | 1;  // odd: the 16 problems of a warp then read 16 different banks
+  const int need = ((pl.sd + 1) / 2) | 1;
   if (need > S) S = need;
   pl.S = S;
   pl.lpi = pl.len <= 16 ? 16 : 32;
-  // the interval stack also stages delta' while g is built, the scaled coefficients while the first intervals are
+  // the interval stack also stages the scaled coefficients while the first intervals are
   // pushed (at its top end: slot k must not reach the coefficients of problems > k, see the kernel) and the
   // derivative coefficients for the candidate evaluation at the end
   int qc = 32;
-  const int stage = raw ? 0 : (kExG * D * pl.nd + pl.lpi - 1) / pl.lpi;
+  const int stage = raw ? 0 : (kExG * pl.sd + pl.lpi - 1) / pl.lpi;
   if (stage > qc) qc = stage;
   const int scaled = (kExG * S + (kExG - 1) * (pl.lpi > S ? pl.lpi - S : 0) + pl.lpi - 1) / pl.lpi;
   if (scaled > qc) qc = scaled;
@@ -220,12 +222,11 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
   }
 
   // Stages the derivative coefficients delta[dim][j] = B(d, j+d) c[j+d] (polynomial.h:99-113) of all problems at
-  // `dst` (stride sd per problem, dims not in dim_mask zeroed) and, if wanted, delta'[dim][j] = (j+1) delta[dim][j+1]
-  // at `dpr` (stride sdp, nd - 1 per dimension). Element e = lane + 32 k walks memory in order in both layouts;
+  // `dst` (stride sd per problem, dims not in dim_mask zeroed). Element e = lane + 32 k walks memory in order in both layouts;
   // the loads of kStageU elements are issued before the first is used (one memory round trip per batch).
   // In raw mode the record is the polynomial itself.
   constexpr int kStageU = 8;
-  auto stage_delta = [&](double* dst, int sd, double* dpr, int sdp) {
+  auto stage_delta = [&](double* dst, int sd) {
     const int n_el = np * rec_one;
     const float inv_a = 1.0f / (float)(AOS ? rec_one : np), inv_N = 1.0f / (float)N;
     for (int e0 = lane; e0 < n_el; e0 += 32 * kStageU) {
@@ -272,7 +273,6 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
           const int dim = rv[u] & 255, jj = rv[u] >> 8, j = jj - d;
           const double dv = ((p.dim_mask >> dim) & 1) ? s_base[d * MTG_BASE_LD + jj] * v[u] : 0.0;
           dst[q * sd + dim * nd + j] = dv;
-          if (dpr && j >= 1) dpr[q * sdp + dim * (nd - 1) + j - 1] = (double)j * dv;
         }
       }
     }
@@ -281,9 +281,8 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
   // ---- g: the polynomial whose real roots in [lo, hi] are the candidate times
   {
     double* s_delta = s_g;  // [g | roots] holds D * nd doubles per problem until g replaces them
-    double* s_dpr = s_qc;   // delta' in the (still empty) interval stack
-    const int sd = p.raw ? N : D * nd, sdp = D * (nd - 1);
-    stage_delta(s_delta, sd, pl.ndim > 1 ? s_dpr : nullptr, sdp);
+    const int sd = pl.sd;
+    stage_delta(s_delta, sd);
     __syncwarp();
     // lane = (problem q, coefficient m = 2 k + half): 16 problems x 2 lanes, conflict-free odd strides; the
     // coefficients wait in registers until every lane has finished reading delta
@@ -291,7 +290,6 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
     double acc[kMaxG / 2];
     if (q < np) {
       const double* dl = s_delta + q * sd;
-      const double* dp = s_dpr + q * sdp;
 #pragma unroll
       for (int k = 0; k < kMaxG / 2; ++k) {
         const int m = 2 * k + (lane >> 4);
@@ -300,13 +298,16 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
           if (p.raw) {
             a = dl[m];
           } else if (pl.ndim > 1) {
-            // sum_dim conv(delta, delta'), delta'[j] = (j+1) delta[j+1]   (segment.cpp:93-115)
-            const int i0 = max(0, m - (nd - 2)), i1 = min(m, nd - 1);
+            // sum_dim conv(delta, delta'), delta'[j] = (j+1) delta[j+1] (segment.cpp:93-115), summed by symmetry:
+            // p p' = (p^2)' / 2, so g[m] = (m+1) (sum_{i < j, i + j = m+1} delta_i delta_j + delta_{(m+1)/2}^2 / 2)
+            const int k2 = m + 1;
+            const int i0 = max(0, k2 - (nd - 1)), i1 = (k2 - 1) >> 1;
             for (int dim = 0; dim < D; ++dim) {
               const double* x = dl + dim * nd;
-              const double* y = dp + dim * (nd - 1) + m;
-              for (int i = i0; i <= i1; ++i) a = fma(x[i], y[-i], a);
+              for (int i = i0; i <= i1; ++i) a = fma(x[i], x[k2 - i], a);
+              if (!(k2 & 1)) a = fma(0.5 * x[k2 >> 1], x[k2 >> 1], a);
             }
+            a *= (double)k2;
           } else {
             // one dimension: roots of p^(d+1)   (segment.cpp:124-131); the other dimensions are staged as zeros
             for (int dim = 0; dim < D; ++dim) a += (double)(m + 1) * dl[dim * nd + m + 1];
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
         double lp = (lane >> 4) ? E : 1.0;
         const double E2 = E * E;
         for (int j = lane >> 4; j <= n; j += 2) {
-          s_sc[q * S + j] = s_g[q * S + j] * lp / s_base[j * MTG_BASE_LD + n];
+          s_sc[q * S + j] = s_g[q * S + j] * lp * (s_base[j * MTG_BASE_LD + j] / s_base[j * MTG_BASE_LD + n]);  // 1 / C(n, j)
           lp *= E2;
         }
       }
@@ -428,10 +429,17 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
       const int q = q0 + gi;
       int n = q < np ? s_n[q] : -1;
       if (n >= 1 && !(side == 0 ? s_hi[q] > 0.0 : s_lo[q] < 0.0)) n = -1;
-      double c = 0.0;
-      if (n >= 1 && li <= n) {
-        const double* aq = s_sc + q * S;
-        for (int j = 0; j <= li; ++j) c = fma(s_base[j * MTG_BASE_LD + li], aq[j], c);
+      // b_i = sum_{j <= i} C(i,j) s_j: the s_j are the forward differences of the b_i at 0, and n rounds of
+      // "add the left neighbour" (round r: lanes i >= r) rebuild the values from them
+      double c = (n >= 1 && li <= n) ? s_sc[q * S + li] : 0.0;
+      {
+        int nmax = n;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, m));
+        for (int r = 1; r <= nmax; ++r) {
+          const double dn = __shfl_up_sync(FULL, c, 1, LPI);
+          if (li >= r && li <= n) c += dn;
+        }
       }
       // scale of the problem: the largest coefficient
       double mx = fabs(c);
@@ -621,8 +629,8 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
 
   // ---- candidates [t_start, t_end, roots...]: |p^(d)(t)| = sqrt(sum_dim evaluate(t, d)^2)  (segment.cpp:135-158)
   double* s_delta = s_qc;  // the interval stack is empty now
-  const int sd = D * nd;
-  stage_delta(s_delta, sd, nullptr, 0);
+  const int sd = pl.sd;
+  stage_delta(s_delta, sd);
   __syncwarp();
   {
     // lane = (problem, candidate parity): 16 problems x 2 lanes
