@@ -17,17 +17,25 @@
 // root) and stopped when |g(t)| falls inside its own rounding-error bound. On min-snap segments one split per
 // problem is typical (0.8-1.0 on average) against 15 levels x 2-5 brackets for a derivative-chain isolator:
 // ~1e3 instead of ~4.5e3 multiply-adds per problem and no level loop. Coefficients below 1e-12 of the largest
-// Bernstein coefficient count as zero: that removes the numerically 7-fold root a rest-to-rest segment has AT its
-// end point (the end points are candidates anyway) and can only hide a root PAIR whose dip of g is below 1e-12
-// of its scale — not an extremum of the magnitude at any tolerance used here. All loops are bounded.
+// Bernstein coefficient count as zero (1e-14 for an explicit input polynomial): that removes the numerically
+// 7-fold root a rest-to-rest segment has AT its end point (the end points are candidates anyway) and can only
+// hide a root PAIR whose dip of g is below 1e-12 of its scale — not an extremum of the magnitude at any tolerance
+// used here. A root that falls ON a split point makes the shared coefficient negligible for both halves; it is
+// recognised by the sign change ACROSS that coefficient and queued directly. An interval that does not start at
+// t = 0 is isolated from the origin (two sides) rather than through a Taylor shift, which would lose
+// ~(1 + |t_start|)^n in the coefficients. All loops are bounded.
 //
 // Mapping (warp-cooperative). One warp owns kExG = 16 root problems ((trajectory, segment) pairs, contiguous in
 // memory in both layouts); g, the roots and the candidate values of a problem live in shared memory (odd
-// strides), nothing in local memory. Intervals wait on a per-warp stack in shared memory; a group of 16 lanes
-// (32 for more than 16 coefficients) takes one interval: lane i holds Bernstein coefficient i, V and the
+// strides), nothing in local memory. The derivative coefficients are staged with batched loads (8 in flight per
+// lane), g is built by the symmetric form of the convolution (p p' = (p^2)'/2: half the multiply-adds) in
+// registers so that the staging area can overlap it, and converted to the Bernstein basis by n rounds of
+// "add the left neighbour" over shuffles. Intervals wait on a per-warp stack in shared memory; a group of 16
+// lanes (32 for more than 16 coefficients) takes one interval: lane i holds Bernstein coefficient i, V and the
 // control-polygon crossing come from ballots, a split is n rounds of shuffles (the left child is the first lane's
 // value after every round, the right child is what the lanes hold at the end). V = 1 pieces queue as brackets and
 // are polished one per lane. The candidates [t_start, t_end, roots...] are then evaluated one per lane.
+// 10.7 kB of shared memory per warp: 20 warps per SM.
 //
 // Candidate order and tie rules follow the reference: per segment [t_start, t_end, roots...]
 // with std::max / std::min (first wins), across segments strict '>' / '<' (earliest wins).

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-end GPU check (run under gpurun from the repo root): full -m gpu suite, smoke, bench (both arms, driver's
-# and default step counts), ncu launch list and --set full capture of the solve kernel into gpurun_out/.
+# and default step counts), ncu launch list and --set full captures of the solve and extrema kernels into gpurun_out/.
 R=r02
 mkdir -p gpurun_out
 python -m pytest tests -q -m gpu > gpurun_out/${R}_pytest_gpu.log 2>&1; tail -3 gpurun_out/${R}_pytest_gpu.log
@@ -11,6 +11,8 @@ python bench.py > gpurun_out/${R}_bench_n1.json 2> gpurun_out/${R}_bench_n1.err;
 CMD="python bench.py --steps 5 --warmup 3 --no-sweep --no-cpu-baseline"
 $CMD > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain_bench2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:solve_canonical -s 3 -c 2 -o gpurun_out/${R}_solve_full $CMD > gpurun_out/ncu_solve.log 2>&1
+ECMD="python tools/bench_extrema.py 262144"
+$ECMD > gpurun_out/${R}_extrema.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:extrema_warp -s 3 -c 1 -o gpurun_out/${R}_extrema_full $ECMD > gpurun_out/ncu_extrema.log 2>&1
 python -c "
 import json
 for f in ('s20',''):
