@@ -102,6 +102,7 @@ struct ExtremaPlan {
   int ndim;    // dimensions taking part
   int lpi;     // lanes per interval (16 or 32)
   int qc;      // interval stack capacity
+  int tld;     // leading dimension of the halving-weight table
   size_t warp_bytes, cta_bytes;
 };
 
@@ -135,7 +136,10 @@ __host__ __device__ inline ExtremaPlan extrema_plan(int N, int D, int derivative
   size_t bytes = (size_t)(2 * kExG * S + 3 * kExG + qc * pl.lpi + 2 * qc + 3 * kExBr) * sizeof(double) +
                  (size_t)(5 * kExG + qc + kExBr + 2) * sizeof(int);
   pl.warp_bytes = (bytes + 15) & ~(size_t)15;
-  pl.cta_bytes = pl.warp_bytes * kExWarps + (size_t)MTG_BASE_LD * MTG_BASE_LD * sizeof(double);
+  // CTA-wide tables: B(k, j) and the halving weights C(i, j) / 2^i (odd leading dimension)
+  pl.tld = pl.lpi == 16 ? 17 : 23;
+  pl.cta_bytes = pl.warp_bytes * kExWarps + (size_t)MTG_BASE_LD * MTG_BASE_LD * sizeof(double) +
+                 (size_t)(pl.tld - 1) * pl.tld * sizeof(double);
   return pl;
 }
 
@@ -156,6 +160,16 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
   // ---- CTA-wide: the base table B(k, j) = j!/(j-k)! in shared memory (lanes read different rows)
   double* s_base = reinterpret_cast<double*>(smem_raw + pl.warp_bytes * kExWarps);
   for (int i = threadIdx.x; i < MTG_BASE_LD * MTG_BASE_LD; i += blockDim.x) s_base[i] = c_base.base[i];
+  // halving weights P[i][j] = C(i, j) / 2^i (exact): de Casteljau at the midpoint in closed form,
+  // left child l_i = sum_{j <= i} P[i][j] c_j, right child r_i = sum_{j >= i} P[n-i][j-i] c_j
+  double* s_pas = s_base + MTG_BASE_LD * MTG_BASE_LD;
+  const int TLD = pl.tld;
+  for (int e = threadIdx.x; e < (TLD - 1) * TLD; e += blockDim.x) {
+    const int i = e / TLD, j = e - i * TLD;
+    double w = 0.0;
+    if (j <= i) w = scalbn(c_base.base[j * MTG_BASE_LD + i] / c_base.base[j * MTG_BASE_LD + j], -i);
+    s_pas[e] = w;
+  }
   __syncthreads();
 
   // ---- this warp's problems
@@ -540,17 +554,18 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
         s_bm[e] = q | (((M >> (__ffs(nz) - 1)) & 1u) << 8);  // sign of g just right of a
       }
       if (__any_sync(FULL, split)) {
-        // de Casteljau at the midpoint: after round r lane i <= n - r holds b_i^(r); the left child is lane 0's value
-        // after every round, the right child is what the lanes hold at the end
-        double cur = c, left = c;
-        int nmax = split ? n : 0;
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, m));
-        for (int r = 1; r <= nmax; ++r) {
-          const double up = __shfl_down_sync(FULL, cur, 1, LPI);
-          if (split && li <= n - r) cur = 0.5 * (cur + up);
-          const double l0 = __shfl_sync(FULL, cur, gi * LPI);
-          if (li == r) left = l0;
+        // de Casteljau at the midpoint in closed form: lane i takes l_i and r_i from the parent's coefficients (still
+        // in its stack slot: pushes come after the ballots below) — n + 2 multiply-adds per lane instead of n rounds
+        double cur = 0.0, left = 0.0;
+        if (split && li <= n) {
+          const double* cs = s_qc + sl * LPI;
+          const double* wl = s_pas + li * TLD;
+          const double* wr = s_pas + (n - li) * TLD - li;
+          for (int j = 0; j <= n; ++j) {
+            const double cj = cs[j];
+            if (j <= li) left = fma(wl[j], cj, left);
+            if (j >= li) cur = fma(wr[j], cj, cur);
+          }
         }
         // A root ON the split point: the shared coefficient g(mid) is then negligible for both children and neither
         // would see the sign change that runs through it. If the nearest non-negligible coefficients on its two sides
