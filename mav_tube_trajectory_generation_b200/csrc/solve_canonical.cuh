@@ -218,8 +218,11 @@ __device__ __forceinline__ void chol_solve(const double (&L)[NF][NF], const doub
   }
 }
 
+#ifndef MTG_SOLVE_THREADS
+#define MTG_SOLVE_THREADS 128  // threads per CTA (2 per trajectory); 2 CTAs per SM
+#endif
 template <int HN, int D, bool AOS, int DT = -1>
-__global__ void __launch_bounds__(128, 2) solve_canonical_kernel(const SolveCanonicalParams p) {
+__global__ void __launch_bounds__(MTG_SOLVE_THREADS, 2) solve_canonical_kernel(const SolveCanonicalParams p) {
   constexpr int N = 2 * HN;
   constexpr int NF = HN - 1;               // free derivatives per interior vertex
   constexpr int SLOTS = NF * NF + NF * D;  // parked G_j and z_j

@@ -18,15 +18,15 @@ int launch_solve_canonical_dt(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, 
   const int n_own_max = std::max(K - 1 - m, m - 1);
   const size_t per_thread = (size_t)std::max(n_own_max - 1, 0) * SLOTS * sizeof(double);
   const size_t optin = ctx->smem_optin;
-  int block = 128;
+  int block = MTG_SOLVE_THREADS;
   if (const char* env = std::getenv("MTG_SOLVE_BLOCK")) {
-    block = std::max(2, std::min(128, std::atoi(env))) & ~1;
+    block = std::max(2, std::min(MTG_SOLVE_THREADS, std::atoi(env))) & ~1;
   } else if (per_thread > 0) {
     const size_t half_sm = (optin + 1024) / 2 - 1024;  // two CTAs per SM, 1 KB reserved each
-    if (per_thread * 128 <= half_sm)
-      block = 128;
+    if (per_thread * MTG_SOLVE_THREADS <= half_sm)
+      block = MTG_SOLVE_THREADS;
     else if (per_thread * 32 <= optin)
-      block = (int)std::min<size_t>(128, (optin / per_thread) / 32 * 32);
+      block = (int)std::min<size_t>(MTG_SOLVE_THREADS, (optin / per_thread) / 32 * 32);
     else
       block = (int)(optin / per_thread) & ~1;
   }
