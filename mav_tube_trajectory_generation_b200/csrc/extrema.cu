@@ -18,7 +18,14 @@ int launch_extrema(mtg_ctx* ctx, bool aos, const ExtremaParams& p_in, cudaStream
   const ExtremaPlan pl = extrema_plan(p.N, p.D, p.derivative, p.dim_mask, p.raw);
   if (pl.len > kMaxG) return fail(ctx, MTG_ERR_UNSUPPORTED, "polynomial too long for the root kernel (22 coefficients)");
   if (pl.cta_bytes > ctx->smem_optin) return fail(ctx, MTG_ERR_UNSUPPORTED, "extrema: shared memory plan exceeds the device limit");
-  auto kern = aos ? extrema_warp_kernel<true> : extrema_warp_kernel<false>;
+  void (*kern)(const ExtremaParams) = aos ? extrema_warp_kernel<true> : extrema_warp_kernel<false>;
+  // the reference's default problem (PolynomialOptimization<10>, 3 dimensions, velocity / acceleration limits)
+  if (!p.raw && p.N == 10 && p.D == 3 && p.dim_mask == 7 && (p.derivative == 1 || p.derivative == 2)) {
+    if (p.derivative == 1)
+      kern = aos ? extrema_warp_kernel<true, 10, 3, 1> : extrema_warp_kernel<false, 10, 3, 1>;
+    else
+      kern = aos ? extrema_warp_kernel<true, 10, 3, 2> : extrema_warp_kernel<false, 10, 3, 2>;
+  }
   MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.cta_bytes));
   const bool reduce = !p.raw && (p.min_value || p.min_time || p.min_seg || p.max_value || p.max_time || p.max_seg ||
                                  p.seg_max_value || p.seg_max_time || p.status || p.soft_cost || p.soft_violation);

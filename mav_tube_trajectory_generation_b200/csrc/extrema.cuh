@@ -106,8 +106,8 @@ struct ExtremaPlan {
   size_t warp_bytes, cta_bytes;
 };
 
-__host__ __device__ inline ExtremaPlan extrema_plan(int N, int D, int derivative, int dim_mask, int raw) {
-  ExtremaPlan pl;
+__host__ __device__ constexpr ExtremaPlan extrema_plan(int N, int D, int derivative, int dim_mask, int raw) {
+  ExtremaPlan pl{};
   int ndim = 0;
   for (int q = 0; q < D; ++q) ndim += (dim_mask >> q) & 1;
   pl.ndim = ndim;
@@ -149,10 +149,22 @@ namespace mtg {
 // extrema.cu: chunked launch of extrema_warp_kernel (+ extrema_reduce_kernel when per-trajectory outputs are wanted)
 int launch_extrema(mtg_ctx* ctx, bool aos, const ExtremaParams& p, cudaStream_t s);
 
-template <bool AOS>
-__global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kernel(const ExtremaParams p) {
+// CN > 0: the instantiation for (N, D, derivative) = (CN, CD, CDER), all dimensions, segment extrema (not raw):
+// every size of the shared-memory plan is a compile-time constant then and the small loops unroll.
+template <bool AOS, int CN = 0, int CD = 0, int CDER = 0>
+__global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kernel(const ExtremaParams p_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const ExtremaPlan pl = extrema_plan(p.N, p.D, p.derivative, p.dim_mask, p.raw);
+  constexpr bool FIX = CN > 0;
+  constexpr ExtremaPlan plc = extrema_plan(FIX ? CN : 2, FIX ? CD : 1, FIX ? CDER : 0, FIX ? (1 << CD) - 1 : 1, 0);
+  ExtremaParams p = p_in;
+  if (FIX) {  // what the launcher has checked; lets the compiler fold every use below
+    p.N = CN;
+    p.D = CD;
+    p.derivative = CDER;
+    p.dim_mask = (1 << CD) - 1;
+    p.raw = 0;
+  }
+  const ExtremaPlan pl = FIX ? plc : extrema_plan(p.N, p.D, p.derivative, p.dim_mask, p.raw);
   const int len = pl.len, S = pl.S, nd = pl.nd, G = kExG, LPI = pl.lpi, QC = pl.qc;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr unsigned FULL = 0xffffffffu;
