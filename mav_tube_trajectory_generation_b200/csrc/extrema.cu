@@ -20,7 +20,7 @@ int launch_extrema(mtg_ctx* ctx, bool aos, const ExtremaParams& p_in, cudaStream
   if (pl.cta_bytes > ctx->smem_optin) return fail(ctx, MTG_ERR_UNSUPPORTED, "extrema: shared memory plan exceeds the device limit");
   void (*kern)(const ExtremaParams) = aos ? extrema_warp_kernel<true> : extrema_warp_kernel<false>;
   // the reference's default problem (PolynomialOptimization<10>, 3 dimensions, velocity / acceleration limits)
-  if (!p.raw && p.N == 10 && p.D == 3 && p.dim_mask == 7 && (p.derivative == 1 || p.derivative == 2)) {
+  if (!p.raw && !p.t_lo && p.N == 10 && p.D == 3 && p.dim_mask == 7 && (p.derivative == 1 || p.derivative == 2)) {
     if (p.derivative == 1)
       kern = aos ? extrema_warp_kernel<true, 10, 3, 1> : extrema_warp_kernel<false, 10, 3, 1>;
     else

@@ -440,16 +440,20 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
   // interval [lo, hi] is covered from the origin instead: side 0 isolates on [0, hi], side 1 on [lo, 0] (E = lo,
   // coefficients stored in reverse so that the interval still runs left to right); pieces outside [lo, hi] are
   // dropped when they are popped and roots outside it at the end. Segment extrema (lo = 0) only have side 0.
-  const int nsides = (p.t_lo != nullptr) ? 2 : 1;
-  // scaled power coefficients, at the top end of the (empty) stack: pass q0 pushes slots <= q0 + GP - 1 after it has
-  // read its own problems' coefficients, and extrema_plan() sizes the stack so that slot k ends below problem k + 1
-  double* s_sc = s_qc + QC * LPI - G * S;
-  for (int side = 0; side < nsides; ++side) {
+  if constexpr (FIX) {
+    // ---- lane = interval (compile-time sizes; t_start = 0). A lane holds the Bernstein coefficients of ITS interval
+    // in registers: counting V, the control-polygon crossing and the halving are serial loops over <= NC
+    // coefficients, 32 intervals at a time. A split keeps the right half in the lane and pushes the left half to the
+    // warp's stack, where the next idle lane picks it up (in the first round lanes 16-31 are idle: they take the
+    // first left halves at once).
+    constexpr int NC = plc.len, NM = NC - 1, SL = NC | 1;
+    const int QS = min(QC, (QC * LPI) / SL);  // stack slots of SL doubles (the meta arrays hold QC)
+    double* s_sc = s_qc;             // scaled power coefficients [problem][S], before the stack is used
     {
       const int q = lane & 15;
       const int n = q < np ? s_n[q] : -1;
-      const double E = side == 0 ? s_hi[q] : s_lo[q];
-      if (n >= 1 && (side == 0 ? E > 0.0 : E < 0.0)) {
+      if (n >= 1) {
+        const double E = s_hi[q];
         double lp = (lane >> 4) ? E : 1.0;
         const double E2 = E * E;
         for (int j = lane >> 4; j <= n; j += 2) {
@@ -459,166 +463,368 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
       }
     }
     __syncwarp();
-    for (int q0 = 0; q0 < np; q0 += GP) {
-      const int q = q0 + gi;
-      int n = q < np ? s_n[q] : -1;
-      if (n >= 1 && !(side == 0 ? s_hi[q] > 0.0 : s_lo[q] < 0.0)) n = -1;
-      // b_i = sum_{j <= i} C(i,j) s_j: the s_j are the forward differences of the b_i at 0, and n rounds of
-      // "add the left neighbour" (round r: lanes i >= r) rebuild the values from them
-      double c = (n >= 1 && li <= n) ? s_sc[q * S + li] : 0.0;
+    double c[NC];
+    bool busy = false;
+    int q = lane & 15, n = 1, depth = 0;
+    double a = 0.0, b = 0.0, eps = 0.0;
+    if (lane < np && s_n[lane] >= 1) {
+      busy = true;
+      n = s_n[lane];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) c[j] = j <= n ? s_sc[lane * S + j] : 0.0;
+      // b_i = sum_{j <= i} C(i,j) s_j: the s_j are the forward differences of the b_i at 0
+#pragma unroll
+      for (int r = 1; r <= NM; ++r)
+#pragma unroll
+        for (int i = NM; i >= r; --i)
+          if (i <= n) c[i] += c[i - 1];
+      double mx = 0.0;
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (j <= n) mx = fmax(mx, fabs(c[j]));
+      eps = 1e-12 * mx;  // "zero" for the sign-variation count (see the header)
+      s_eps[lane] = eps;
+      b = s_hi[lane];
+      if (c[0] == 0.0) s_root[lane * S + atomicAdd(&s_nroot[lane], 1)] = 0.0;  // a root exactly on an end
+#pragma unroll
+      for (int j = 1; j < NC; ++j)
+        if (j == n && c[j] == 0.0) s_root[lane * S + atomicAdd(&s_nroot[lane], 1)] = b;
+    }
+    __syncwarp();  // every row has been read: the area is the stack from here on
+    for (;;) {
+      // ---- idle lanes take intervals off the stack
+      const unsigned idle = __ballot_sync(FULL, !busy);
+      const int top = *s_top;
+      if (idle == FULL && top == 0) break;
       {
-        int nmax = n;
+        const int rank = __popc(idle & ((1u << lane) - 1u));
+        if (!busy && rank < top) {
+          const int sl = top - 1 - rank;
+          const int meta = s_qm[sl];
+          q = meta & 255;
+          depth = meta >> 8;
+          n = s_n[q];
+          eps = s_eps[q];
+          a = s_qa[sl];
+          b = s_qb[sl];
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, m));
-        for (int r = 1; r <= nmax; ++r) {
-          const double dn = __shfl_up_sync(FULL, c, 1, LPI);
-          if (li >= r && li <= n) c += dn;
+          for (int j = 0; j < NC; ++j) c[j] = s_qc[sl * SL + j];
+          busy = true;
         }
       }
-      // scale of the problem: the largest coefficient
-      double mx = fabs(c);
+      __syncwarp();
+      const int top1 = top - min(__popc(idle), top);
+      // ---- sign variations of the non-negligible coefficients; the first crossing of the control polygon
+      int V = 0, i0 = 0, j0 = 1, pidx = 0;
+      double ci = 1.0, cj = -1.0, prev = 0.0;
+      bool seen = false, first_neg = false;
 #pragma unroll
-      for (int m = 8; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, m));
-      if (LPI == 32) mx = fmax(mx, __shfl_xor_sync(FULL, mx, 16));
-      int slot = 0;
-      if (n >= 1 && li == 0) slot = atomicAdd(s_top, 1);  // one slot per interval, drawn by the group's first lane
-      const int sl = __shfl_sync(FULL, slot, gi * LPI);
-      if (n >= 1) {
-        if (li <= n) s_qc[sl * LPI + (side == 0 ? li : n - li)] = c;
-        if (li == 0) {
-          s_qa[sl] = side == 0 ? 0.0 : s_lo[q];
-          s_qb[sl] = side == 0 ? s_hi[q] : 0.0;
-          s_qm[sl] = q;
-          // "zero" for the sign-variation count: solved trajectories carry ~1e-13 of coefficient noise (the
-          // multiple root at a rest-to-rest end is not exact in the data), exact input polynomials only rounding
-          s_eps[q] = (p.raw ? 1e-14 : 1e-12) * mx;
-          // a root exactly at t = 0 (once: side 1 leaves it to side 0 when both run)
-          if (c == 0.0 && (side == 0 || !(s_hi[q] > 0.0))) s_root[q * S + atomicAdd(&s_nroot[q], 1)] = 0.0;
+      for (int j = 0; j < NC; ++j) {
+        const double x = c[j];
+        if (busy && j <= n && fabs(x) > eps) {
+          if (seen && ((x < 0.0) != (prev < 0.0))) {
+            if (V == 0) {
+              i0 = pidx;
+              j0 = j;
+              ci = prev;
+              cj = x;
+            }
+            ++V;
+          }
+          if (!seen) first_neg = x < 0.0;
+          seen = true;
+          prev = x;
+          pidx = j;
         }
-        if (li == n && c == 0.0)  // ... exactly on the far end
-          s_root[q * S + atomicAdd(&s_nroot[q], 1)] = side == 0 ? s_hi[q] : s_lo[q];
       }
+      // ---- V >= 2: halve, if the left half still has a slot on the stack
+      const unsigned want = __ballot_sync(FULL, busy && V >= 2 && depth < kBernDepth);
+      const int srank = __popc(want & ((1u << lane) - 1u));
+      const bool split = ((want >> lane) & 1u) && top1 + srank < QS;
+      const bool leaf = busy && V >= 1 && !split;
+      if (busy && V >= 2 && !split && depth < kBernDepth) atomicOr(&s_st[q], 16);  // no room: taken as it is
+      // ---- V = 1 (or given up): queue the bracket
+      {
+        const unsigned lm = __ballot_sync(FULL, leaf);
+        if (*s_nbr + __popc(lm) > kExBr) drain();
+        if (leaf) {
+          double rc;
+          const double dc = ci - cj;
+          asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(dc));
+          const double u = ((double)i0 + ci * rc * (double)(j0 - i0)) * (double)__frcp_rn((float)n);
+          double t = a + u * (b - a);
+          if (!(t > a && t < b)) t = 0.5 * (a + b);
+          const int e = *s_nbr + __popc(lm & ((1u << lane) - 1u));
+          s_ba[e] = a;
+          s_bb[e] = b;
+          s_bt[e] = t;
+          s_bm[e] = q | ((first_neg ? 1 : 0) << 8);  // sign of g just right of a
+        }
+        __syncwarp();
+        if (lane == 0) *s_nbr += __popc(lm);
+        __syncwarp();
+      }
+      bool midroot = false, mid_neg = false;
+      double mid = 0.0;
+      if (split) {
+        // de Casteljau at the midpoint without the halvings: after round r, c[i] = 2^r b_i^(r); the left half is
+        // c[0] of every round, the right half what is left at the end (index i finished in round n - i)
+        const int sl = top1 + srank;
+        mid = 0.5 * (a + b);
+        s_qa[sl] = a;
+        s_qb[sl] = mid;
+        s_qm[sl] = q | ((depth + 1) << 8);
+        double* ls = s_qc + sl * SL;
+        ls[0] = c[0];
+        bool lseen = fabs(c[0]) > eps, lneg = c[0] < 0.0;  // the last non-negligible coefficient of the left half
+        double shared = 0.0;                                 // b_0^(n) = g(mid): the coefficient both halves share
+        double sc = 0.5;
+#pragma unroll
+        for (int r = 1; r <= NM; ++r) {
+#pragma unroll
+          for (int i = 0; i + r <= NM; ++i)
+            if (i + r <= n) c[i] += c[i + 1];
+          if (r <= n) {
+            const double lv = c[0] * sc;
+            ls[r] = lv;
+            if (r < n) {
+              if (fabs(lv) > eps) {
+                lseen = true;
+                lneg = lv < 0.0;
+              }
+            } else {
+              shared = lv;
+            }
+          }
+          sc *= 0.5;
+        }
+        // right half: c[i] *= 2^-(n - i)
+        const double s0 = __hiloint2double((1023 - n) << 20, 0);
+        double pw = 1.0;
+        bool rseen = false, rneg = false;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          if (i <= n) {
+            c[i] *= s0 * pw;
+            if (i >= 1 && !rseen && fabs(c[i]) > eps) {
+              rseen = true;
+              rneg = c[i] < 0.0;
+            }
+          }
+          pw *= 2.0;
+        }
+        // a root ON the split point: the shared coefficient is negligible for both halves and neither would see the
+        // sign change that runs through it — queued directly, bracketed by one control-point spacing on either side
+        midroot = !(fabs(shared) > eps) && lseen && rseen && (lneg != rneg);
+        mid_neg = lneg;
+      }
+      {
+        const unsigned mm = __ballot_sync(FULL, midroot);
+        if (mm) {
+          if (*s_nbr + __popc(mm) > kExBr) drain();
+          if (midroot) {
+            const double h = (b - a) / (double)(2 * n);
+            const int e = *s_nbr + __popc(mm & ((1u << lane) - 1u));
+            s_ba[e] = mid - h;
+            s_bb[e] = mid + h;
+            s_bt[e] = mid;
+            s_bm[e] = q | ((mid_neg ? 1 : 0) << 8);
+          }
+          __syncwarp();
+          if (lane == 0) *s_nbr += __popc(mm);
+        }
+      }
+      if (split) {  // go on with the right half
+        a = mid;
+        ++depth;
+      } else {
+        busy = false;
+      }
+      __syncwarp();
+      if (lane == 0) *s_top = top1 + min(__popc(want), max(QS - top1, 0));
       __syncwarp();
     }
-
-    // pop intervals, count sign variations, split or queue
-    for (;;) {
-      __syncwarp();
-      const int top = *s_top;
-      if (top == 0) break;
-      const int take = min(GP, top);
-      __syncwarp();
-      if (lane == 0) *s_top = top - take;
-      const bool have = gi < take;
-      const int sl = top - 1 - gi;
-      double c = 0.0, a = 0.0, b = 0.0, eps = 0.0;
-      int q = 0, depth = 0, n = 0;
-      if (have) {
-        const int meta = s_qm[sl];
-        q = meta & 255;
-        depth = meta >> 8;
-        n = s_n[q];
-        a = s_qa[sl];
-        b = s_qb[sl];
-        eps = s_eps[q];
-        if (li <= n) c = s_qc[sl * LPI + li];
-      }
-      const bool live = have && !(b < s_lo[q] || a > s_hi[q]);  // a piece outside [lo, hi] is dropped
-      __syncwarp();  // the popped slots may be overwritten by the pushes below
-      const unsigned shiftg = LPI == 32 ? 0u : 16u * gi;
-      const unsigned lmask = LPI == 32 ? FULL : 0xffffu;
-      const unsigned P = (__ballot_sync(FULL, live && li <= n && c > eps) >> shiftg) & lmask;
-      const unsigned M = (__ballot_sync(FULL, live && li <= n && c < -eps) >> shiftg) & lmask;
-      const unsigned nz = P | M;
-      // a sign change starts at i: i is non-zero and the next non-zero coefficient above it has the other sign
-      int nxt = -1;
-      bool var = false;
-      if ((nz >> li) & 1u) {
-        const unsigned above = li >= 31 ? 0u : (nz & ~((2u << li) - 1u));
-        if (above) {
-          nxt = __ffs(above) - 1;
-          var = ((P >> li) & 1u) != ((P >> nxt) & 1u);
-        }
-      }
-      const unsigned Vm = (__ballot_sync(FULL, var) >> shiftg) & lmask;
-      const int V = __popc(Vm);
-      const bool room = *s_top + 2 * GP <= QC;   // read before anybody pushes (uniform)
-      const bool leaf = have && V >= 1 && (V == 1 || depth >= kBernDepth || !room);
-      const bool split = have && V >= 2 && !leaf;
-      if (have && V >= 2 && leaf && li == 0 && !room) atomicOr(&s_st[q], 16);
-      // the first crossing of the control polygon: between coefficients i0 and j0
-      const int i0 = Vm ? __ffs(Vm) - 1 : 0;
-      const int j0 = __shfl_sync(FULL, nxt, gi * LPI + i0);
-      const double ci = __shfl_sync(FULL, c, gi * LPI + i0);
-      const double cj = __shfl_sync(FULL, c, gi * LPI + max(j0, 0));
-      if (leaf && li == 0) {
-        // a starting point needs no more than a few digits: approximate reciprocals instead of two divisions
-        double rc;
-        const double dc = ci - cj;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(dc));
-        const double u = ((double)i0 + ci * rc * (double)(j0 - i0)) * (double)__frcp_rn((float)n);
-        double t = a + u * (b - a);
-        if (!(t > a && t < b)) t = 0.5 * (a + b);
-        const int e = atomicAdd(s_nbr, 1);
-        s_ba[e] = a;
-        s_bb[e] = b;
-        s_bt[e] = t;
-        s_bm[e] = q | (((M >> (__ffs(nz) - 1)) & 1u) << 8);  // sign of g just right of a
-      }
-      if (__any_sync(FULL, split)) {
-        // de Casteljau at the midpoint in closed form: lane i takes l_i and r_i from the parent's coefficients (still
-        // in its stack slot: pushes come after the ballots below) — n + 2 multiply-adds per lane instead of n rounds
-        double cur = 0.0, left = 0.0;
-        if (split && li <= n) {
-          const double* cs = s_qc + sl * LPI;
-          const double* wl = s_pas + li * TLD;
-          const double* wr = s_pas + (n - li) * TLD - li;
-          for (int j = 0; j <= n; ++j) {
-            const double cj = cs[j];
-            if (j <= li) left = fma(wl[j], cj, left);
-            if (j >= li) cur = fma(wr[j], cj, cur);
+  } else {
+    const int nsides = (p.t_lo != nullptr) ? 2 : 1;
+    // scaled power coefficients, at the top end of the (empty) stack: pass q0 pushes slots <= q0 + GP - 1 after it has
+    // read its own problems' coefficients, and extrema_plan() sizes the stack so that slot k ends below problem k + 1
+    double* s_sc = s_qc + QC * LPI - G * S;
+    for (int side = 0; side < nsides; ++side) {
+      {
+        const int q = lane & 15;
+        const int n = q < np ? s_n[q] : -1;
+        const double E = side == 0 ? s_hi[q] : s_lo[q];
+        if (n >= 1 && (side == 0 ? E > 0.0 : E < 0.0)) {
+          double lp = (lane >> 4) ? E : 1.0;
+          const double E2 = E * E;
+          for (int j = lane >> 4; j <= n; j += 2) {
+            s_sc[q * S + j] = s_g[q * S + j] * lp * (s_base[j * MTG_BASE_LD + j] / s_base[j * MTG_BASE_LD + n]);  // 1 / C(n, j)
+            lp *= E2;
           }
         }
-        // A root ON the split point: the shared coefficient g(mid) is then negligible for both children and neither
-        // would see the sign change that runs through it. If the nearest non-negligible coefficients on its two sides
-        // differ in sign, the root is queued directly, bracketed by one control-point spacing on either side.
-        const unsigned PL = (__ballot_sync(FULL, split && li <= n && left > eps) >> shiftg) & lmask;
-        const unsigned ML = (__ballot_sync(FULL, split && li <= n && left < -eps) >> shiftg) & lmask;
-        const unsigned PR = (__ballot_sync(FULL, split && li <= n && cur > eps) >> shiftg) & lmask;
-        const unsigned MR = (__ballot_sync(FULL, split && li <= n && cur < -eps) >> shiftg) & lmask;
-        int basei = 0;
-        if (split && li == 0) basei = atomicAdd(s_top, 2);
-        basei = __shfl_sync(FULL, basei, gi * LPI);
-        if (split) {
-          const double mid = 0.5 * (a + b);
-          s_qc[basei * LPI + li] = li <= n ? cur : 0.0;         // right child first: the left one is popped first
-          s_qc[(basei + 1) * LPI + li] = li <= n ? left : 0.0;
+      }
+      __syncwarp();
+      for (int q0 = 0; q0 < np; q0 += GP) {
+        const int q = q0 + gi;
+        int n = q < np ? s_n[q] : -1;
+        if (n >= 1 && !(side == 0 ? s_hi[q] > 0.0 : s_lo[q] < 0.0)) n = -1;
+        // b_i = sum_{j <= i} C(i,j) s_j: the s_j are the forward differences of the b_i at 0, and n rounds of
+        // "add the left neighbour" (round r: lanes i >= r) rebuild the values from them
+        double c = (n >= 1 && li <= n) ? s_sc[q * S + li] : 0.0;
+        {
+          int nmax = n;
+  #pragma unroll
+          for (int m = 16; m >= 1; m >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, m));
+          for (int r = 1; r <= nmax; ++r) {
+            const double dn = __shfl_up_sync(FULL, c, 1, LPI);
+            if (li >= r && li <= n) c += dn;
+          }
+        }
+        // scale of the problem: the largest coefficient
+        double mx = fabs(c);
+  #pragma unroll
+        for (int m = 8; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, m));
+        if (LPI == 32) mx = fmax(mx, __shfl_xor_sync(FULL, mx, 16));
+        int slot = 0;
+        if (n >= 1 && li == 0) slot = atomicAdd(s_top, 1);  // one slot per interval, drawn by the group's first lane
+        const int sl = __shfl_sync(FULL, slot, gi * LPI);
+        if (n >= 1) {
+          if (li <= n) s_qc[sl * LPI + (side == 0 ? li : n - li)] = c;
           if (li == 0) {
-            s_qa[basei] = mid;
-            s_qb[basei] = b;
-            s_qm[basei] = q | ((depth + 1) << 8);
-            s_qa[basei + 1] = a;
-            s_qb[basei + 1] = mid;
-            s_qm[basei + 1] = q | ((depth + 1) << 8);
-            const unsigned nzl = (PL | ML) & ((1u << n) - 1u);   // left child without the shared coefficient (index n)
-            const unsigned nzr = (PR | MR) & ~1u;                // right child without it (index 0)
-            if (!(((PL | ML) >> n) & 1u) && nzl && nzr) {
-              const int il = 31 - __clz(nzl), ir = __ffs(nzr) - 1;
-              const bool negl = (ML >> il) & 1u, negr = (MR >> ir) & 1u;
-              if (negl != negr) {
-                const double h = (b - a) / (double)(2 * n);
-                const int e = atomicAdd(s_nbr, 1);
-                s_ba[e] = mid - h;
-                s_bb[e] = mid + h;
-                s_bt[e] = mid;
-                s_bm[e] = q | ((negl ? 1 : 0) << 8);
+            s_qa[sl] = side == 0 ? 0.0 : s_lo[q];
+            s_qb[sl] = side == 0 ? s_hi[q] : 0.0;
+            s_qm[sl] = q;
+            // "zero" for the sign-variation count: solved trajectories carry ~1e-13 of coefficient noise (the
+            // multiple root at a rest-to-rest end is not exact in the data), exact input polynomials only rounding
+            s_eps[q] = (p.raw ? 1e-14 : 1e-12) * mx;
+            // a root exactly at t = 0 (once: side 1 leaves it to side 0 when both run)
+            if (c == 0.0 && (side == 0 || !(s_hi[q] > 0.0))) s_root[q * S + atomicAdd(&s_nroot[q], 1)] = 0.0;
+          }
+          if (li == n && c == 0.0)  // ... exactly on the far end
+            s_root[q * S + atomicAdd(&s_nroot[q], 1)] = side == 0 ? s_hi[q] : s_lo[q];
+        }
+        __syncwarp();
+      }
+
+      // pop intervals, count sign variations, split or queue
+      for (;;) {
+        __syncwarp();
+        const int top = *s_top;
+        if (top == 0) break;
+        const int take = min(GP, top);
+        __syncwarp();
+        if (lane == 0) *s_top = top - take;
+        const bool have = gi < take;
+        const int sl = top - 1 - gi;
+        double c = 0.0, a = 0.0, b = 0.0, eps = 0.0;
+        int q = 0, depth = 0, n = 0;
+        if (have) {
+          const int meta = s_qm[sl];
+          q = meta & 255;
+          depth = meta >> 8;
+          n = s_n[q];
+          a = s_qa[sl];
+          b = s_qb[sl];
+          eps = s_eps[q];
+          if (li <= n) c = s_qc[sl * LPI + li];
+        }
+        const bool live = have && !(b < s_lo[q] || a > s_hi[q]);  // a piece outside [lo, hi] is dropped
+        __syncwarp();  // the popped slots may be overwritten by the pushes below
+        const unsigned shiftg = LPI == 32 ? 0u : 16u * gi;
+        const unsigned lmask = LPI == 32 ? FULL : 0xffffu;
+        const unsigned P = (__ballot_sync(FULL, live && li <= n && c > eps) >> shiftg) & lmask;
+        const unsigned M = (__ballot_sync(FULL, live && li <= n && c < -eps) >> shiftg) & lmask;
+        const unsigned nz = P | M;
+        // a sign change starts at i: i is non-zero and the next non-zero coefficient above it has the other sign
+        int nxt = -1;
+        bool var = false;
+        if ((nz >> li) & 1u) {
+          const unsigned above = li >= 31 ? 0u : (nz & ~((2u << li) - 1u));
+          if (above) {
+            nxt = __ffs(above) - 1;
+            var = ((P >> li) & 1u) != ((P >> nxt) & 1u);
+          }
+        }
+        const unsigned Vm = (__ballot_sync(FULL, var) >> shiftg) & lmask;
+        const int V = __popc(Vm);
+        const bool room = *s_top + 2 * GP <= QC;   // read before anybody pushes (uniform)
+        const bool leaf = have && V >= 1 && (V == 1 || depth >= kBernDepth || !room);
+        const bool split = have && V >= 2 && !leaf;
+        if (have && V >= 2 && leaf && li == 0 && !room) atomicOr(&s_st[q], 16);
+        // the first crossing of the control polygon: between coefficients i0 and j0
+        const int i0 = Vm ? __ffs(Vm) - 1 : 0;
+        const int j0 = __shfl_sync(FULL, nxt, gi * LPI + i0);
+        const double ci = __shfl_sync(FULL, c, gi * LPI + i0);
+        const double cj = __shfl_sync(FULL, c, gi * LPI + max(j0, 0));
+        if (leaf && li == 0) {
+          // a starting point needs no more than a few digits: approximate reciprocals instead of two divisions
+          double rc;
+          const double dc = ci - cj;
+          asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(dc));
+          const double u = ((double)i0 + ci * rc * (double)(j0 - i0)) * (double)__frcp_rn((float)n);
+          double t = a + u * (b - a);
+          if (!(t > a && t < b)) t = 0.5 * (a + b);
+          const int e = atomicAdd(s_nbr, 1);
+          s_ba[e] = a;
+          s_bb[e] = b;
+          s_bt[e] = t;
+          s_bm[e] = q | (((M >> (__ffs(nz) - 1)) & 1u) << 8);  // sign of g just right of a
+        }
+        if (__any_sync(FULL, split)) {
+          // de Casteljau at the midpoint in closed form: lane i takes l_i and r_i from the parent's coefficients (still
+          // in its stack slot: pushes come after the ballots below) — n + 2 multiply-adds per lane instead of n rounds
+          double cur = 0.0, left = 0.0;
+          if (split && li <= n) {
+            const double* cs = s_qc + sl * LPI;
+            const double* wl = s_pas + li * TLD;
+            const double* wr = s_pas + (n - li) * TLD - li;
+            for (int j = 0; j <= n; ++j) {
+              const double cj = cs[j];
+              if (j <= li) left = fma(wl[j], cj, left);
+              if (j >= li) cur = fma(wr[j], cj, cur);
+            }
+          }
+          // A root ON the split point: the shared coefficient g(mid) is then negligible for both children and neither
+          // would see the sign change that runs through it. If the nearest non-negligible coefficients on its two sides
+          // differ in sign, the root is queued directly, bracketed by one control-point spacing on either side.
+          const unsigned PL = (__ballot_sync(FULL, split && li <= n && left > eps) >> shiftg) & lmask;
+          const unsigned ML = (__ballot_sync(FULL, split && li <= n && left < -eps) >> shiftg) & lmask;
+          const unsigned PR = (__ballot_sync(FULL, split && li <= n && cur > eps) >> shiftg) & lmask;
+          const unsigned MR = (__ballot_sync(FULL, split && li <= n && cur < -eps) >> shiftg) & lmask;
+          int basei = 0;
+          if (split && li == 0) basei = atomicAdd(s_top, 2);
+          basei = __shfl_sync(FULL, basei, gi * LPI);
+          if (split) {
+            const double mid = 0.5 * (a + b);
+            s_qc[basei * LPI + li] = li <= n ? cur : 0.0;         // right child first: the left one is popped first
+            s_qc[(basei + 1) * LPI + li] = li <= n ? left : 0.0;
+            if (li == 0) {
+              s_qa[basei] = mid;
+              s_qb[basei] = b;
+              s_qm[basei] = q | ((depth + 1) << 8);
+              s_qa[basei + 1] = a;
+              s_qb[basei + 1] = mid;
+              s_qm[basei + 1] = q | ((depth + 1) << 8);
+              const unsigned nzl = (PL | ML) & ((1u << n) - 1u);   // left child without the shared coefficient (index n)
+              const unsigned nzr = (PR | MR) & ~1u;                // right child without it (index 0)
+              if (!(((PL | ML) >> n) & 1u) && nzl && nzr) {
+                const int il = 31 - __clz(nzl), ir = __ffs(nzr) - 1;
+                const bool negl = (ML >> il) & 1u, negr = (MR >> ir) & 1u;
+                if (negl != negr) {
+                  const double h = (b - a) / (double)(2 * n);
+                  const int e = atomicAdd(s_nbr, 1);
+                  s_ba[e] = mid - h;
+                  s_bb[e] = mid + h;
+                  s_bt[e] = mid;
+                  s_bm[e] = q | ((negl ? 1 : 0) << 8);
+                }
               }
             }
           }
         }
+        __syncwarp();
+        if (*s_nbr > kExBr - 2 * GP) drain();
       }
-      __syncwarp();
-      if (*s_nbr > kExBr - 2 * GP) drain();
     }
   }
   drain();
