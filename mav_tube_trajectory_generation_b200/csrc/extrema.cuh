@@ -450,14 +450,17 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
     const int QS = min(QC, (QC * LPI) / SL);  // stack slots of SL doubles (the meta arrays hold QC)
     double* s_sc = s_qc;             // scaled power coefficients [problem][S], before the stack is used
     {
+      // every problem is taken at the full degree NM (a stripped leading zero is a zero power coefficient: the
+      // Bernstein form of the degree-elevated polynomial, for which the variation count holds just the same)
       const int q = lane & 15;
-      const int n = q < np ? s_n[q] : -1;
-      if (n >= 1) {
+      if (q < np && s_n[q] >= 1) {
         const double E = s_hi[q];
         double lp = (lane >> 4) ? E : 1.0;
         const double E2 = E * E;
-        for (int j = lane >> 4; j <= n; j += 2) {
-          s_sc[q * S + j] = s_g[q * S + j] * lp * (s_base[j * MTG_BASE_LD + j] / s_base[j * MTG_BASE_LD + n]);  // 1 / C(n, j)
+#pragma unroll
+        for (int j2 = 0; j2 < NC; j2 += 2) {
+          const int j = j2 + (lane >> 4);
+          if (j < NC) s_sc[q * S + j] = s_g[q * S + j] * lp * (s_base[j * MTG_BASE_LD + j] / s_base[j * MTG_BASE_LD + NM]);  // 1 / C(NM, j)
           lp *= E2;
         }
       }
@@ -465,30 +468,28 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
     __syncwarp();
     double c[NC];
     bool busy = false;
-    int q = lane & 15, n = 1, depth = 0;
+    int q = lane & 15, depth = 0;
+    constexpr int n = NM;
     double a = 0.0, b = 0.0, eps = 0.0;
     if (lane < np && s_n[lane] >= 1) {
       busy = true;
-      n = s_n[lane];
 #pragma unroll
-      for (int j = 0; j < NC; ++j) c[j] = j <= n ? s_sc[lane * S + j] : 0.0;
+      for (int j = 0; j < NC; ++j) c[j] = s_sc[lane * S + j];
       // b_i = sum_{j <= i} C(i,j) s_j: the s_j are the forward differences of the b_i at 0
 #pragma unroll
       for (int r = 1; r <= NM; ++r)
 #pragma unroll
         for (int i = NM; i >= r; --i)
-          if (i <= n) c[i] += c[i - 1];
+          c[i] += c[i - 1];
       double mx = 0.0;
 #pragma unroll
       for (int j = 0; j < NC; ++j)
-        if (j <= n) mx = fmax(mx, fabs(c[j]));
+        mx = fmax(mx, fabs(c[j]));
       eps = 1e-12 * mx;  // "zero" for the sign-variation count (see the header)
       s_eps[lane] = eps;
       b = s_hi[lane];
       if (c[0] == 0.0) s_root[lane * S + atomicAdd(&s_nroot[lane], 1)] = 0.0;  // a root exactly on an end
-#pragma unroll
-      for (int j = 1; j < NC; ++j)
-        if (j == n && c[j] == 0.0) s_root[lane * S + atomicAdd(&s_nroot[lane], 1)] = b;
+      if (c[NM] == 0.0) s_root[lane * S + atomicAdd(&s_nroot[lane], 1)] = b;
     }
     __syncwarp();  // every row has been read: the area is the stack from here on
     for (;;) {
@@ -503,7 +504,6 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
           const int meta = s_qm[sl];
           q = meta & 255;
           depth = meta >> 8;
-          n = s_n[q];
           eps = s_eps[q];
           a = s_qa[sl];
           b = s_qb[sl];
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         const double x = c[j];
-        if (busy && j <= n && fabs(x) > eps) {
+        if (busy && fabs(x) > eps) {
           if (seen && ((x < 0.0) != (prev < 0.0))) {
             if (V == 0) {
               i0 = pidx;
@@ -582,34 +582,28 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
 #pragma unroll
         for (int r = 1; r <= NM; ++r) {
 #pragma unroll
-          for (int i = 0; i + r <= NM; ++i)
-            if (i + r <= n) c[i] += c[i + 1];
-          if (r <= n) {
-            const double lv = c[0] * sc;
-            ls[r] = lv;
-            if (r < n) {
-              if (fabs(lv) > eps) {
-                lseen = true;
-                lneg = lv < 0.0;
-              }
-            } else {
-              shared = lv;
+          for (int i = 0; i + r <= NM; ++i) c[i] += c[i + 1];
+          const double lv = c[0] * sc;
+          ls[r] = lv;
+          if (r < NM) {
+            if (fabs(lv) > eps) {
+              lseen = true;
+              lneg = lv < 0.0;
             }
+          } else {
+            shared = lv;
           }
           sc *= 0.5;
         }
-        // right half: c[i] *= 2^-(n - i)
-        const double s0 = __hiloint2double((1023 - n) << 20, 0);
-        double pw = 1.0;
+        // right half: c[i] *= 2^-(NM - i)
+        double pw = 1.0 / (double)(1 << NM);
         bool rseen = false, rneg = false;
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-          if (i <= n) {
-            c[i] *= s0 * pw;
-            if (i >= 1 && !rseen && fabs(c[i]) > eps) {
-              rseen = true;
-              rneg = c[i] < 0.0;
-            }
+          c[i] *= pw;
+          if (i >= 1 && !rseen && fabs(c[i]) > eps) {
+            rseen = true;
+            rneg = c[i] < 0.0;
           }
           pw *= 2.0;
         }
