@@ -256,58 +256,90 @@ __global__ void __launch_bounds__(kExWarps * 32, MTG_EX_MINB) extrema_warp_kerne
   }
 
   // Stages the derivative coefficients delta[dim][j] = B(d, j+d) c[j+d] (polynomial.h:99-113) of all problems at
-  // `dst` (stride sd per problem, dims not in dim_mask zeroed). Element e = lane + 32 k walks memory in order in both layouts;
-  // the loads of kStageU elements are issued before the first is used (one memory round trip per batch).
+  // `dst` (stride sd per problem, dims not in dim_mask zeroed). Element e = lane + 32 k walks memory in order in both
+  // layouts — (problem, coefficient) and the source address advance incrementally — and the loads of kStageU
+  // elements are issued before the first is used (one memory round trip per batch).
   // In raw mode the record is the polynomial itself.
   constexpr int kStageU = 8;
   auto stage_delta = [&](double* dst, int sd) {
     const int n_el = np * rec_one;
-    const float inv_a = 1.0f / (float)(AOS ? rec_one : np), inv_N = 1.0f / (float)N;
+    if (p.raw) {
+      const float inv_a = 1.0f / (float)(AOS ? rec_one : np);
+      for (int e = lane; e < n_el; e += 32) {
+        int q, r;
+        if (AOS) {
+          q = (int)(((float)e + 0.5f) * inv_a);
+          r = e - q * rec_one;
+        } else {
+          r = (int)(((float)e + 0.5f) * inv_a);
+          q = e - r * np;
+        }
+        dst[q * sd + r] = p.coeffs[at<AOS>((size_t)r, rec_c, Bsz, (size_t)s_pb[q])];
+      }
+      return;
+    }
+    // AoS: the 16 problems are one contiguous run of memory ((b K + seg) is linear in the problem index);
+    // SoA: coefficient r of problem q sits at (seg0 rec_one + r) B + b
+    int q, r, dq, dr;
+    const double* src;
+    if (AOS) {
+      q = lane / rec_one;
+      r = lane - q * rec_one;
+      dq = 32 / rec_one;
+      dr = 32 - dq * rec_one;
+      src = p.coeffs + ((size_t)p.b0 * K + (size_t)flat0) * rec_one + lane;
+    } else {
+      r = lane / np;
+      q = lane - r * np;
+      dr = 32 / np;
+      dq = 32 - dr * np;
+      src = p.coeffs + ((size_t)seg0 * rec_one + r) * Bsz + (size_t)(p.b0 + local0 + q);
+    }
+    const size_t src_step = AOS ? 32 : (size_t)dr * Bsz + dq;
+    const size_t src_wrap = AOS ? 0 : Bsz - np;  // SoA: q wraps to the next coefficient row
     for (int e0 = lane; e0 < n_el; e0 += 32 * kStageU) {
       double v[kStageU];
-      int qv[kStageU], rv[kStageU];
+      int di[kStageU], rv[kStageU];
 #pragma unroll
       for (int u = 0; u < kStageU; ++u) {
-        const int e = e0 + 32 * u;
         v[u] = 0.0;
-        qv[u] = -1;
+        di[u] = -1;
         rv[u] = 0;
-        if (e < n_el) {
-          int q, r;
-          if (AOS) {
-            q = (int)(((float)e + 0.5f) * inv_a);
-            r = e - q * rec_one;
-          } else {
-            r = (int)(((float)e + 0.5f) * inv_a);
-            q = e - r * np;
+        if (e0 + 32 * u < n_el) {
+          int dim = 0, jj = r;
+          while (jj >= N) {
+            jj -= N;
+            ++dim;
           }
-          const int b = s_pb[q], seg = s_ps[q];
-          if (p.raw) {
-            v[u] = p.coeffs[at<AOS>((size_t)r, rec_c, Bsz, (size_t)b)];
-            qv[u] = q;
-            rv[u] = r;
-          } else {
-            const int dim = (int)(((float)r + 0.5f) * inv_N);
-            const int jj = r - dim * N;
-            if (jj >= d) {
-              v[u] = p.coeffs[at<AOS>((size_t)(seg * D + dim) * N + jj, rec_c, Bsz, (size_t)b)];
-              qv[u] = q;
-              rv[u] = dim | (jj << 8);
-            }
+          if (jj >= d) {
+            v[u] = *src;
+            di[u] = q * sd + dim * nd + jj - d;
+            rv[u] = dim | (jj << 8);
+          }
+        }
+        src += src_step;
+        if (AOS) {
+          q += dq;
+          r += dr;
+          if (r >= rec_one) {
+            r -= rec_one;
+            ++q;
+          }
+        } else {
+          r += dr;
+          q += dq;
+          if (q >= np) {
+            q -= np;
+            ++r;
+            src += src_wrap;
           }
         }
       }
 #pragma unroll
       for (int u = 0; u < kStageU; ++u) {
-        const int q = qv[u];
-        if (q < 0) continue;
-        if (p.raw) {
-          dst[q * sd + rv[u]] = v[u];
-        } else {
-          const int dim = rv[u] & 255, jj = rv[u] >> 8, j = jj - d;
-          const double dv = ((p.dim_mask >> dim) & 1) ? s_base[d * MTG_BASE_LD + jj] * v[u] : 0.0;
-          dst[q * sd + dim * nd + j] = dv;
-        }
+        if (di[u] < 0) continue;
+        const int dim = rv[u] & 255, jj = rv[u] >> 8;
+        dst[di[u]] = ((p.dim_mask >> dim) & 1) ? s_base[d * MTG_BASE_LD + jj] * v[u] : 0.0;
       }
     }
   };
