@@ -255,3 +255,36 @@ def test_soft_constraint(po):
             want += min(cap, np.exp((v - lim) / lim * w))
         # the exponential amplifies the 1e-9 value tolerance by weight / limit
         assert abs(cost[b] - want) <= 1e-6 * want
+
+
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_two_isolators_agree_at_scale(po, layout):
+    """Size-independent property: the kernel has two independent isolators — the compile-time path of the default
+    problem (lane = interval, full degree) when no interval is given, and the generic path (16 lanes per
+    interval, per-problem degree, two-sided) when t_start / t_end are explicit. On 8,192 trajectories x 10
+    segments x {velocity, acceleration} both must produce the same candidate lists: same count on all but a
+    few near-degenerate segments, times to 1e-9 T, maxima to 1e-12."""
+    import torch
+    B, K = 8192, 10
+    c = ctx()
+    pos, t = c.generate_candidates_batch(B, K, 3, seed=77, first_index=0, pos_min=[-10.0] * 3, pos_max=[10.0] * 3,
+                                         v_max=3.0, a_max=5.0, layout=layout)
+    sol = c.solve_batch(pos, t, layout=layout)
+    conv = aos if layout == "soa" else (lambda x: x)
+    for der in (1, 2):
+        fast = c.extrema_candidates_batch(sol["coeffs"], t, der, layout=layout)
+        gen = c.extrema_candidates_batch(sol["coeffs"], t, der, t_start=torch.zeros_like(t), t_end=t, layout=layout)
+        assert int((fast["status"] != 0).sum()) == 0 and int((gen["status"] != 0).sum()) == 0
+        nf, ng = conv(host(fast["n_candidates"])), conv(host(gen["n_candidates"]))
+        tf, tg = conv(host(fast["cand_time"])), conv(host(gen["cand_time"]))
+        vf, vg = conv(host(fast["cand_value"])), conv(host(gen["cand_value"]))
+        T = conv(host(t))
+        same = nf == ng
+        assert same.mean() > 0.999
+        col = np.arange(tf.shape[2])[None, None, :]
+        live = same[:, :, None] & (col < nf[:, :, None])
+        assert np.abs(np.where(live, tf - tg, 0.0)).max() <= 1e-9 * T.max()
+        # the maximum over the list is what computeMaximumOfMagnitude consumes: equal on EVERY segment
+        mf = np.where(col < nf[:, :, None], vf, -np.inf).max(axis=2)
+        mg = np.where(col < ng[:, :, None], vg, -np.inf).max(axis=2)
+        assert np.abs(mf - mg).max() <= 1e-12 * mf.max()
