@@ -19,12 +19,15 @@ int launch_extrema(mtg_ctx* ctx, bool aos, const ExtremaParams& p_in, cudaStream
   if (pl.len > kMaxG) return fail(ctx, MTG_ERR_UNSUPPORTED, "polynomial too long for the root kernel (22 coefficients)");
   if (pl.cta_bytes > ctx->smem_optin) return fail(ctx, MTG_ERR_UNSUPPORTED, "extrema: shared memory plan exceeds the device limit");
   void (*kern)(const ExtremaParams) = aos ? extrema_warp_kernel<true> : extrema_warp_kernel<false>;
-  // the reference's default problem (PolynomialOptimization<10>, 3 dimensions, velocity / acceleration limits)
-  if (!p.raw && !p.t_lo && p.N == 10 && p.D == 3 && p.dim_mask == 7 && (p.derivative == 1 || p.derivative == 2)) {
-    if (p.derivative == 1)
-      kern = aos ? extrema_warp_kernel<true, 10, 3, 1> : extrema_warp_kernel<false, 10, 3, 1>;
-    else
-      kern = aos ? extrema_warp_kernel<true, 10, 3, 2> : extrema_warp_kernel<false, 10, 3, 2>;
+  // the reference's default problem (PolynomialOptimization<10>, 3 dimensions; velocity ... snap): compile-time sizes
+  if (!p.raw && !p.t_lo && p.N == 10 && p.D == 3 && p.dim_mask == 7) {
+    switch (p.derivative) {
+      case 1: kern = aos ? extrema_warp_kernel<true, 10, 3, 1> : extrema_warp_kernel<false, 10, 3, 1>; break;
+      case 2: kern = aos ? extrema_warp_kernel<true, 10, 3, 2> : extrema_warp_kernel<false, 10, 3, 2>; break;
+      case 3: kern = aos ? extrema_warp_kernel<true, 10, 3, 3> : extrema_warp_kernel<false, 10, 3, 3>; break;
+      case 4: kern = aos ? extrema_warp_kernel<true, 10, 3, 4> : extrema_warp_kernel<false, 10, 3, 4>; break;
+      default: break;
+    }
   }
   MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.cta_bytes));
   const bool reduce = !p.raw && (p.min_value || p.min_time || p.min_seg || p.max_value || p.max_time || p.max_seg ||
