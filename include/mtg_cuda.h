@@ -395,13 +395,15 @@ int mtg_control_points_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const d
  * The candidate times of a segment are t = 0, t = T and the real roots in [0, T] of
  * g = sum_dim p_dim^(d) * p_dim^(d+1) (one dimension: of p^(d+1)); candidate order and tie
  * rules are the reference's (first candidate / earliest segment wins). Times are relative to
- * the segment start (extremum.h:41-42). The real roots are isolated by a bounded derivative-
- * chain + bracketed-Newton scheme instead of a port of rpoly: extremum VALUES agree with the
- * reference to rounding; extremum TIMES to the root accuracy of either method, except where
- * a root is (numerically) multiple, e.g. at the rest-to-rest ends.
+ * the segment start (extremum.h:41-42). The real roots are isolated by bounded Bernstein-basis
+ * subdivision (variation-diminishing sign count) + bracketed Newton instead of a port of rpoly:
+ * extremum VALUES agree with the reference to rounding; extremum TIMES to the root accuracy of
+ * either method, except where a root is (numerically) multiple, e.g. at the rest-to-rest ends
+ * (SURVEY.md section 7.4). Coefficients of g below 1e-12 of its scale on the segment count as zero.
  *  min_value, min_time, max_value, max_time [B] double; min_seg, max_seg [B] int32  out or NULL
  *  seg_max_value, seg_max_time [K]   out or NULL, maximum of every segment
- * status: MTG_ST_NO_CONVERGENCE if a bracketed refinement hit its iteration cap. */
+ * status: MTG_ST_NO_CONVERGENCE if a bracketed refinement hit its iteration cap or the interval
+ * stack of a warp was full (an interval with several roots was then taken as one bracket). */
 int mtg_extrema_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* coeffs,
                       const double* seg_times, int derivative, double* min_value, double* min_time,
                       int32_t* min_seg, double* max_value, double* max_time, int32_t* max_seg,
