@@ -72,3 +72,26 @@ def test_bounds_and_free_space(po):
         Jo, _, co, ko = po.collision_cost(coeffs[b], times[b], grid, [0, 0, 0], 0.1, [-1.0] * 3, [1.0] * 3, 0.05)
         assert bool(host(r["in_collision"])[b]) == co and host(r["n_checks"])[b] == ko and host(r["J_c"])[b] == Jo
     assert host(r["in_collision"]).sum() > B // 2
+
+
+@pytest.mark.parametrize("n_coeffs", [6, 12])
+def test_other_polynomial_orders(po, n_coeffs):
+    """The same comparison for N = 6 (2 free derivatives per vertex) and N = 12 (5; 36 moment sums per segment, more
+    than one per lane), AoS records."""
+    B, K = 32, 5
+    pos, times = random_problems(po, B, K, 3, box=5.0, seed0=6800)
+    coeffs, _ = po.solve_canonical_batch(pos, times, N=n_coeffs, derivative=n_coeffs // 2 - 1, n_threads=8)
+    res, dt = 0.25, 0.07
+    lo, hi = [-9.0] * 3, [9.0] * 3
+    rng = np.random.RandomState(11)
+    grid, origin = sphere_field(res, lo, hi, rng.uniform(-5, 5, size=(8, 3)), rng.uniform(0.1, 0.5, size=8))
+    kw = dict(epsilon=2.0, robot_radius=0.2, multiplier=1.5)
+    r = ctx().collision_cost_batch(dev(coeffs), dev(times), dev(grid), origin, res, lo, hi, dt, layout="aos", **kw)
+    J, g, col, chk = host(r["J_c"]), host(r["grad"]), host(r["in_collision"]), host(r["n_checks"])
+    assert np.all(host(r["status"]) == 0)
+    for b in range(B):
+        Jo, go, co, ko = po.collision_cost(coeffs[b], times[b], grid, origin, res, lo, hi, dt, **kw)
+        assert bool(col[b]) == co and chk[b] == ko
+        assert abs(J[b] - Jo) <= 1e-9 * max(Jo, 1e-12)
+        assert np.abs(g[b].reshape(3, -1) - go).max() <= 1e-9 * np.abs(go).max() + 1e-15
+    assert (col == 0).sum() > 3
