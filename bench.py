@@ -7,9 +7,11 @@ Workload (BASELINE.json configs[1]): a batch of 65,536 random 3-D, 10-segment,
 N = 10 min-snap problems per GPU (random vertices in a +-10 m box, Nfabian
 segment times v_max = 3, a_max = 5 — the reference's createRandomVertices +
 estimateSegmentTimes recipe, vectorised with numpy's RNG). One "step" = one
-mtg_solve_batch over that batch (Q/A/R construction, the R_pp solve, all 300
-coefficients and the cost of every trajectory) followed by mtg_argmin_batch, which
-folds the batch into the running best candidate (the sweep of BASELINE configs[4]);
+mtg_solve_argmin_batch over that batch: the solve (Q/A/R construction, the R_pp solve, all
+300 coefficients, the cost and the status of every trajectory written to HBM) with the
+argmin that folds the batch into the running best candidate fused into the kernel's
+epilogue (the sweep of BASELINE configs[4]; --two-launch-step runs it as mtg_solve_batch +
+mtg_argmin_batch, the same results in two launches);
 the timed region ends with the one collective of the sharded sweep: an all-gather of
 one 16-byte {cost, index} pair per rank (torch.distributed / NCCL), also at N = 1.
 
@@ -327,6 +329,7 @@ def workload_config(n_gpus):
     return {"workload": "configs[1]: batch of 65,536 random 3-D 10-segment min-snap (N=10) solves per GPU",
             "batch_per_gpu": BATCH_PER_GPU, "segments": K_SEG, "dims": DIM, "N": NCOEF,
             "derivative_to_optimize": DERIV, "global_batch": BATCH_PER_GPU * n_gpus,
+            "step": "mtg_solve_argmin_batch: solve (coefficients, cost, status written) + running argmin, one launch",
             "parallelism": f"batch sharded over {n_gpus} GPU(s); one 16-byte argmin all-gather per rank at the "
                            "end of the timed region",
             "l2": f"inputs+outputs rotate over {N_ROTATE} buffer sets of 180 MB (> 126 MB L2)"}
@@ -491,6 +494,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-sweep", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--two-launch-step", action="store_true",
+                    help="step = mtg_solve_batch + mtg_argmin_batch (two launches) instead of the fused mtg_solve_argmin_batch")
     ap.add_argument("--sweep-batch", type=int, default=SWEEP_BATCH, help=argparse.SUPPRESS)
     args = ap.parse_args()
     claim_stdout()
@@ -548,10 +553,15 @@ def main():
     def step(i, fresh=False):
         p, t = dev_in[i % N_ROTATE]
         o = dev_out[i % N_ROTATE]
-        ctx.solve_batch(p, t, N=NCOEF, derivative=DERIV, out=o)
         # candidate index = step * global_batch + position in the global batch
-        ctx.argmin_batch(o["cost"], status=o["status"], global_offset=i * B * world + start, best=best,
-                         accumulate=not fresh)
+        off = i * B * world + start
+        if args.two_launch_step:
+            ctx.solve_batch(p, t, N=NCOEF, derivative=DERIV, out=o)
+            ctx.argmin_batch(o["cost"], status=o["status"], global_offset=off, best=best, accumulate=not fresh)
+        else:
+            # the same step in one launch: all outputs written, the argmin folded into the solve kernel's epilogue
+            ctx.solve_argmin_batch(p, t, N=NCOEF, derivative=DERIV, out=o, global_offset=off, best=best,
+                                   accumulate=not fresh)
 
     def barrier():
         torch.cuda.synchronize()

@@ -490,6 +490,20 @@ int mtg_generate_candidates_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, ui
  * caller reads best_global when it needs it. Without an initialised communicator: a copy. */
 int mtg_argmin_batch(mtg_ctx* ctx, const double* cost, const uint32_t* status, int64_t n,
                      int64_t global_offset, int accumulate, void* best, void* stream);
+/* mtg_solve_argmin_batch: one step of a candidate sweep in ONE launch — mtg_solve_batch (same
+ * arguments and meaning; coeffs, cost, free_constraints and status may ALL be NULL) with
+ * mtg_argmin_batch over its costs folded into the solve kernel's epilogue: every CTA publishes the
+ * best {cost, global index} of its trajectories and the last CTA folds them, plus the pair already
+ * in *best when accumulate != 0, into the DEVICE pair *best. Same total order and exclusions as
+ * mtg_argmin_batch (failed solves and NaN costs never win, ties -> lower global index =
+ * global_offset + b). This is the loop body of the reference's restart loop — solveLinear() +
+ * computeCost() + keep the cheapest [NL_I:274-330, LIN_I:113-130, 337-379] — without the cost vector
+ * ever leaving the SMs. Device pointers only. Shapes the fused epilogue does not cover (K = 1,
+ * chains so long that a CTA is not whole warps) run as the two launches it replaces. */
+int mtg_solve_argmin_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* positions,
+                           const double* end_derivatives, const double* seg_times, double* coeffs, double* cost,
+                           double* free_constraints, uint32_t* status, int64_t global_offset, int accumulate,
+                           void* best, void* stream);
 int mtg_nccl_unique_id(mtg_ctx* ctx, uint8_t id[128]);
 int mtg_nccl_init(mtg_ctx* ctx, const uint8_t id[128], int rank, int world);
 int mtg_argmin_allgather(mtg_ctx* ctx, const double* cost, const uint32_t* status, int64_t n_local,

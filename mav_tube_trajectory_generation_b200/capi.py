@@ -93,6 +93,8 @@ def load() -> C.CDLL:
     lib.mtg_generate_candidates_batch.argtypes = [vp, C.POINTER(ProblemDesc), C.c_uint64, C.c_int64, vp, vp, C.c_double,
                                                   C.c_double, C.c_double, dp, dp, vp]
     lib.mtg_argmin_batch.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.c_int, vp, vp]
+    lib.mtg_solve_argmin_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, u32p, C.c_int64, C.c_int,
+                                           vp, vp]
     lib.mtg_nccl_unique_id.argtypes = [vp, C.c_char_p]
     lib.mtg_nccl_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
     lib.mtg_argmin_allgather.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.POINTER(C.c_double),
@@ -362,6 +364,37 @@ class Context:
         rc = self._lib.mtg_argmin_batch(self._h, _ptr(cost), _ptr(status), cost.numel(), int(global_offset),
                                         1 if accumulate else 0, _ptr(best), self._stream(MTG_MEM_DEVICE, stream))
         self._check(rc, "mtg_argmin_batch")
+        return best
+
+    def solve_argmin_batch(self, positions, seg_times, end_derivatives=None, N: int = 10, derivative: int = 4,
+                           layout: str = "soa", global_offset: int = 0, best=None, accumulate=False, out=None,
+                           stream=None):
+        """mtg_solve_argmin_batch on CUDA tensors: the solve with the argmin of its costs fused into the kernel.
+        `out` may hold any of coeffs / cost / free / status tensors to be filled (none is required). Returns
+        `best`, the 2-element int64 CUDA tensor holding the device pair {double cost; int64 idx}."""
+        import torch
+
+        aos = layout == "aos"
+        if aos:
+            B, Kp1, D = positions.shape
+        else:
+            Kp1, D, B = positions.shape
+        K = Kp1 - 1
+        if not (_is_torch(positions) and positions.is_cuda):
+            raise MtgError("solve_argmin_batch takes CUDA tensors")
+        for nm, x in (("positions", positions), ("seg_times", seg_times)):
+            self._contig(x, nm)
+        desc = ProblemDesc(B, K, D, N, derivative, MTG_MEM_DEVICE, LAYOUT_AOS if aos else LAYOUT_SOA)
+        out = out or {}
+        if best is None:
+            best = torch.zeros(2, dtype=torch.int64, device=positions.device)
+            accumulate = False
+        rc = self._lib.mtg_solve_argmin_batch(self._h, C.byref(desc), _ptr(positions), _ptr(end_derivatives),
+                                              _ptr(seg_times), _ptr(out.get("coeffs")), _ptr(out.get("cost")),
+                                              _ptr(out.get("free")), _ptr(out.get("status")), int(global_offset),
+                                              1 if accumulate else 0, _ptr(best),
+                                              self._stream(MTG_MEM_DEVICE, stream))
+        self._check(rc, "mtg_solve_argmin_batch")
         return best
 
     @staticmethod

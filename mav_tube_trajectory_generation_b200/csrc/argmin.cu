@@ -8,37 +8,14 @@
 #include <cmath>
 #include <limits>
 
+#include "argmin.cuh"
 #include "host_common.h"
 
 using namespace mtg;
 
 namespace {
 
-struct Best {
-  double cost;
-  long long idx;
-};
-
-__device__ __forceinline__ bool better(double c, long long i, double bc, long long bi) {
-  // total order: lower cost first, ties -> lower global index (the serial scan of a CPU sweep)
-  return (c < bc) || (c == bc && i < bi);
-}
-
-__device__ __forceinline__ void warp_reduce(double& c, long long& i) {
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    const double oc = __shfl_xor_sync(0xffffffffu, c, m);
-    const long long oi = __shfl_xor_sync(0xffffffffu, i, m);
-    if (better(oc, oi, c, i)) {
-      c = oc;
-      i = oi;
-    }
-  }
-}
-
 constexpr int kArgminBlock = 256;
-
-constexpr long long kInfIdx = 0x7fffffffffffffffLL;  // "nothing yet": ordered last
 
 // block-wide reduction of (c, i); the result is valid in thread 0
 __device__ __forceinline__ void block_reduce(double& c, long long& i, double* sc, long long* si) {

@@ -1,6 +1,7 @@
 // libmtg_cuda.so — P1..P8: mtg_solve_batch (canonical constraint pattern).
 #include "host_common.h"
 #include "solve_canonical.cuh"
+#include "solve_launch.cuh"  // solve_block_size()
 
 
 using namespace mtg;
@@ -76,6 +77,72 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* po
     p.vec_ok = 1;
     return launch_solve_canonical(ctx, N, D, aos, p, st);
   });
+}
+
+// Candidate sweep in ONE launch: the solve with the argmin of its costs folded into the kernel's epilogue.
+int mtg_solve_argmin_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* positions,
+                           const double* end_derivatives, const double* seg_times, double* coeffs, double* cost,
+                           double* free_constraints, uint32_t* status, int64_t global_offset, int accumulate,
+                           void* best, void* stream_) {
+  int rc = validate_desc(ctx, desc);
+  if (rc) return rc;
+  if (desc->memory != MTG_MEM_DEVICE)
+    return fail(ctx, MTG_ERR_UNSUPPORTED, "mtg_solve_argmin_batch takes device pointers (the running best lives on the device)");
+  if (!positions || !seg_times || !best)
+    return fail(ctx, MTG_ERR_INVALID_ARGUMENT, "positions, seg_times and best are required");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int B = desc->B, K = desc->K, D = desc->D, N = desc->N;
+  if (B == 0) return mtg_argmin_batch(ctx, nullptr, nullptr, 0, global_offset, accumulate, best, stream_);
+  MTG_CUDA_TRY(cudaSetDevice(ctx->device));
+  const int block = mtg::solve_launch::solve_block_size(ctx, K, N / 2, D, nullptr);
+  if (K < 2 || block < 32 || block % 32 != 0) {
+    // shapes the fused epilogue does not cover (a single segment; very long chains that run in partial warps):
+    // the two launches it replaces, with scratch for whatever the caller did not ask for
+    double* cost_buf = cost;
+    uint32_t* status_buf = status;
+    if (!cost_buf || !status_buf) {
+      DeviceBuffer* scratch = ctx->scratch_for(stream);
+      const size_t cost_bytes = align256((size_t)B * sizeof(double));
+      if (scratch->ensure(cost_bytes + (size_t)B * sizeof(uint32_t)))
+        return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of the sweep scratch failed");
+      if (!cost_buf) cost_buf = (double*)scratch->ptr;
+      if (!status_buf) status_buf = (uint32_t*)((char*)scratch->ptr + cost_bytes);
+    }
+    rc = mtg_solve_batch(ctx, desc, positions, end_derivatives, seg_times, coeffs, cost_buf, free_constraints,
+                         status_buf, stream_);
+    if (rc) return rc;
+    return mtg_argmin_batch(ctx, cost_buf, status_buf, B, global_offset, accumulate, best, stream_);
+  }
+  TableGuard tables(ctx, N, desc->derivative_to_optimize, stream);
+  if (tables.rc()) return tables.rc();
+  DeviceBuffer* state = ctx->argmin_state_for(stream);  // [ticket, lock | partials]: shared with mtg_argmin_batch
+  if (!state->ptr) {
+    const size_t need = 256 + (size_t)4 * std::max(ctx->sm_count, 1) * sizeof(mtg::Best);
+    if (state->ensure(need)) return fail(ctx, MTG_ERR_CUDA, "cudaMalloc of the argmin state failed");
+    MTG_CUDA_TRY(cudaMemset(state->ptr, 0, 256));  // ticket counter and lock, once: the kernels leave them at zero
+  }
+  if (!accumulate) {  // a fresh sweep: the pair starts as "nothing yet"
+    rc = mtg_argmin_batch(ctx, nullptr, nullptr, 0, 0, 0, best, stream_);
+    if (rc) return rc;
+  }
+  mtg::SolveCanonicalParams p;
+  p.K = K;
+  p.derivative = desc->derivative_to_optimize;
+  p.positions = positions;
+  p.end_derivatives = end_derivatives;
+  p.seg_times = seg_times;
+  p.coeffs = coeffs;
+  p.cost = cost;
+  p.free_constraints = free_constraints;
+  p.status = status;
+  p.B = B;
+  p.b0 = 0;
+  p.nb = B;
+  p.vec_ok = (coeffs && (uintptr_t)coeffs % 16 == 0) ? 1 : 0;
+  p.best_lock = (unsigned*)state->ptr + 1;
+  p.best_out = best;
+  p.best_offset = global_offset;
+  return launch_solve_canonical(ctx, N, D, desc->layout == MTG_LAYOUT_AOS, p, stream);
 }
 
 }  // extern "C"

@@ -37,6 +37,7 @@
 
 #include <stdint.h>
 
+#include "argmin.cuh"
 #include "device_tables.cuh"
 
 namespace mtg {
@@ -55,6 +56,11 @@ struct SolveCanonicalParams {
   int K;
   int derivative;
   int vec_ok;  // AoS only: coeffs is 16-byte aligned -> double2 stores
+  // fused candidate argmin (mtg_solve_argmin_batch; best_out == nullptr: off): every CTA folds the best
+  // {cost, global index} of its trajectories into the running pair *best_out
+  unsigned* best_lock = nullptr;        // zero when free
+  void* best_out = nullptr;             // Best*: the running best, {+inf, -1} = nothing yet
+  long long best_offset = 0;            // global index of trajectory 0 of the batch
 };
 
 // element `elem` of record `b`: SoA = batch innermost, AoS = record-contiguous
@@ -473,6 +479,10 @@ __global__ void __launch_bounds__(MTG_SOLVE_THREADS, 2) solve_canonical_kernel(c
   }
 
   // ---------------------------------------------------------------- backward
+  // fused argmin: the running best cost as of now (any value it has held is a valid filter later); requested here
+  // so that the epilogue does not wait for it
+  const double best_cost_at_start =
+      (p.best_out && tid == 0) ? static_cast<volatile const Best*>(p.best_out)->cost : INFINITY;
   double xs[D][HN];
   double T_back = p.seg_times[at<AOS>((size_t)SG(n_own), rec_t, B, b)];  // requested one step ahead, as above
 #pragma unroll 1
@@ -539,6 +549,55 @@ __global__ void __launch_bounds__(MTG_SOLVE_THREADS, 2) solve_canonical_kernel(c
   if (active && side == 0) {
     if (p.cost) p.cost[b] = 0.5 * cost_acc;
     if (p.status) p.status[b] = st;
+  }
+  if (p.best_out) {
+    // ---- the sweep's argmin, fused: same total order and the same exclusions (failed solves, NaN) as
+    // argmin_kernel; blockDim.x is a multiple of 32 here (the launcher falls back to two launches otherwise).
+    // The running best {cost, idx} in *best_out only ever improves, so a CTA whose best is costlier than ANY value
+    // the pair has held is done (the value read when the kernel started is such a value: no latency here); the
+    // few that might win re-read it and, if still in the race, update it under a lock (whoever waits for the lock
+    // keeps re-reading, so a convoy dissolves as soon as a good candidate is in). No per-CTA fence, no partials, no
+    // last-CTA fold on the kernel's tail.
+    __shared__ double s_bc[32];
+    __shared__ long long s_bi[32];
+    double c = INFINITY;
+    long long i = kInfIdx;
+    {
+      const double cv = 0.5 * cost_acc;
+      if (active && side == 0 && st == 0u && cv == cv) {
+        c = cv;
+        i = p.best_offset + b;
+      }
+    }
+    warp_reduce(c, i);
+    if ((tid & 31) == 0) {
+      s_bc[tid >> 5] = c;
+      s_bi[tid >> 5] = i;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    for (int q = 1; q < (nt >> 5); ++q)
+      if (better(s_bc[q], s_bi[q], c, i)) {
+        c = s_bc[q];
+        i = s_bi[q];
+      }
+    if (i == kInfIdx || c > best_cost_at_start) return;
+    volatile Best* out = static_cast<volatile Best*>(p.best_out);
+    for (;;) {
+      if (c > out->cost) return;  // a fresh look before (and while waiting for) the lock: costs only fall
+      if (atomicCAS(p.best_lock, 0u, 1u) == 0u) break;
+    }
+    __threadfence();
+    {
+      const double bc = out->cost;
+      const long long bi = out->idx;
+      if (bi < 0 || better(c, i, bc, bi)) {
+        out->idx = i;
+        out->cost = c;
+      }
+    }
+    __threadfence();
+    atomicExch(p.best_lock, 0u);
   }
 }
 

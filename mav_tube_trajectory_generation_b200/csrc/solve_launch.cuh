@@ -9,15 +9,15 @@ namespace mtg {
 namespace solve_launch {
 
 // -------------------------------------------------------------- solve launch
-template <int HN, int D, bool AOS, int DT>
-int launch_solve_canonical_dt(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, cudaStream_t stream) {
-  constexpr int NF = HN - 1;
-  constexpr int SLOTS = NF * NF + NF * D;
+// threads per CTA (2 per trajectory) and the parked sweep state per thread; block < 2: K too large
+inline int solve_block_size(const mtg_ctx* ctx, int K, int HN, int D, size_t* per_thread_out) {
+  const int NF = HN - 1;
+  const int SLOTS = NF * NF + NF * D;
   // two lanes per trajectory; each parks (G_j, z_j) of all but the last vertex it eliminates
-  const int K = p.K, m = K / 2;
+  const int m = K / 2;
   const int n_own_max = std::max(K - 1 - m, m - 1);
   const size_t per_thread = (size_t)std::max(n_own_max - 1, 0) * SLOTS * sizeof(double);
-  const size_t optin = ctx->smem_optin;
+  const size_t optin = ctx->smem_optin - 1024;  // the kernel also holds ~0.5 KB of static shared memory
   int block = MTG_SOLVE_THREADS;
   if (const char* env = std::getenv("MTG_SOLVE_BLOCK")) {
     block = std::max(2, std::min(MTG_SOLVE_THREADS, std::atoi(env))) & ~1;
@@ -30,16 +30,27 @@ int launch_solve_canonical_dt(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, 
     else
       block = (int)(optin / per_thread) & ~1;
   }
+  if (per_thread_out) *per_thread_out = per_thread;
+  return block;
+}
+
+template <int HN, int D, bool AOS, int DT>
+int launch_solve_canonical_dt(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, cudaStream_t stream) {
+  size_t per_thread = 0;
+  const int block = solve_block_size(ctx, p.K, HN, D, &per_thread);
+  const size_t optin = ctx->smem_optin - 1024;
   if (block < 2 || per_thread * block > optin)
     return fail(ctx, MTG_ERR_UNSUPPORTED,
                 "solve_canonical: K too large for the shared-memory sweep state; use mtg_solve_generic_batch");
   const size_t smem = per_thread * block;
   auto kern = mtg::solve_canonical_kernel<HN, D, AOS, DT>;
   if (smem > 48 * 1024)  // per device and per instantiation; a cheap host-side call
-    MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
+    MTG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long threads = 2LL * p.nb;
   const int grid = (int)((threads + block - 1) / block);
   if (grid == 0) return MTG_OK;
+  if (p.best_out && (block % 32 != 0 || p.K < 2))
+    return fail(ctx, MTG_ERR_UNSUPPORTED, "solve_canonical: the fused argmin needs whole warps and K >= 2");
   kern<<<grid, block, smem, stream>>>(p);
   ++ctx->launches;
   MTG_CUDA_TRY(cudaGetLastError());

@@ -127,3 +127,52 @@ def test_device_candidate_generator_matches_host_twin(po, layout):
         p4, _ = c.generate_candidates_batch(300, 3, d_, 11, layout=layout)
         w4, _ = po.generate_candidates(300, 3, d_, 11)
         assert np.array_equal(conv(host(p4)), w4)
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_fused_solve_argmin_equals_the_two_launches(po, layout):
+    """mtg_solve_argmin_batch = mtg_solve_batch + mtg_argmin_batch, bit for bit: same outputs, same winner under the
+    same total order (ties -> lower global index, failed solves and NaN costs never win), running best over several
+    batches, outputs optional, and the K = 1 shape that takes the two-launch route inside the library."""
+    import torch
+
+    c = ctx()
+    B, K = 5000, 10                                   # not a multiple of the CTA's 64 trajectories
+    pos, times = c.generate_candidates_batch(B, K, 3, seed=5, layout=layout)
+    def col(x, b):                                    # view of candidate b
+        return x[b] if layout == "aos" else x[..., b]
+    col(times, 17)[0] = -1.0                          # a failed solve ...
+    plain = c.solve_batch(pos, times, layout=layout)
+    cost0 = host(plain["cost"]).copy()
+    st0 = host(plain["status"])
+    assert st0[17] != 0
+    best_b = int(np.flatnonzero((st0 == 0) & (cost0 == cost0[st0 == 0].min()))[0])
+    # ... and an exact tie with the best candidate at a HIGHER index: the lower one must win
+    twin = B - 3 if best_b != B - 3 else B - 4
+    col(pos, twin).copy_(col(pos, best_b))
+    col(times, twin).copy_(col(times, best_b))
+    plain = c.solve_batch(pos, times, layout=layout)
+    want = ref_argmin(host(plain["cost"]), host(plain["status"]), offset=1000)
+    assert want[1] == 1000 + min(best_b, twin)
+    out = {"coeffs": torch.empty_like(plain["coeffs"]), "cost": torch.empty_like(plain["cost"]),
+           "status": torch.empty_like(plain["status"])}
+    best = c.solve_argmin_batch(pos, times, layout=layout, global_offset=1000, out=out)
+    assert c.decode_best(best) == want
+    for k in out:
+        assert torch.equal(out[k], plain[k]), k
+    # no outputs at all, accumulate over three batches with their own offsets (the middle one holds the winner)
+    run = torch.zeros(2, dtype=torch.int64, device="cuda")
+    pos2, times2 = c.generate_candidates_batch(B, K, 3, seed=6, layout=layout)
+    p2 = c.solve_batch(pos2, times2, layout=layout)
+    for n, (p_, t_, off) in enumerate(((pos2, times2, 0), (pos, times, 7000), (pos2, times2, 20000))):
+        c.solve_argmin_batch(p_, t_, layout=layout, global_offset=off, best=run, accumulate=n > 0)
+    a = ref_argmin(host(p2["cost"]), host(p2["status"]), 0)
+    b = ref_argmin(host(plain["cost"]), host(plain["status"]), 7000)
+    assert c.decode_best(run) == min(a, b)
+    # the fused argmin agrees with mtg_argmin_batch itself
+    assert c.decode_best(c.argmin_batch(plain["cost"], plain["status"], global_offset=1000)) == want
+    # K = 1: two launches inside the library, scratch for the cost the caller did not ask for
+    pos1, times1 = c.generate_candidates_batch(300, 1, 3, seed=7, layout=layout)
+    p1 = c.solve_batch(pos1, times1, layout=layout)
+    assert c.decode_best(c.solve_argmin_batch(pos1, times1, layout=layout)) == \
+        ref_argmin(host(p1["cost"]), host(p1["status"]))
