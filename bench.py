@@ -329,7 +329,8 @@ def workload_config(n_gpus):
     return {"workload": "configs[1]: batch of 65,536 random 3-D 10-segment min-snap (N=10) solves per GPU",
             "batch_per_gpu": BATCH_PER_GPU, "segments": K_SEG, "dims": DIM, "N": NCOEF,
             "derivative_to_optimize": DERIV, "global_batch": BATCH_PER_GPU * n_gpus,
-            "step": "mtg_solve_argmin_batch: solve (coefficients, cost, status written) + running argmin, one launch",
+            "step": "mtg_solve_argmin_batch: solve (coefficients, cost, status written) + running argmin, one launch; "
+                    "consecutive steps overlap by programmatic dependent launch (mtg_set_solve_overlap; --no-overlap: off)",
             "parallelism": f"batch sharded over {n_gpus} GPU(s); one 16-byte argmin all-gather per rank at the "
                            "end of the timed region",
             "l2": f"inputs+outputs rotate over {N_ROTATE} buffer sets of 180 MB (> 126 MB L2)"}
@@ -494,6 +495,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-sweep", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="ordinary launches: consecutive steps do not overlap (mtg_set_solve_overlap off)")
     ap.add_argument("--two-launch-step", action="store_true",
                     help="step = mtg_solve_batch + mtg_argmin_batch (two launches) instead of the fused mtg_solve_argmin_batch")
     ap.add_argument("--sweep-batch", type=int, default=SWEEP_BATCH, help=argparse.SUPPRESS)
@@ -549,6 +552,10 @@ def main():
     best = torch.zeros(2, dtype=torch.int64, device="cuda")          # running device pair {cost, global index}
     best_global = torch.zeros(2, dtype=torch.int64, device="cuda")   # the gathered + folded pair
     start, _ = sweep.shard_range(B * world, rank, world)
+
+    # consecutive steps may overlap (programmatic dependent launch): their inputs are resident, i.e. never written
+    # by the stream operation before them, which is what mtg_set_solve_overlap asks for
+    ctx.set_solve_overlap(not args.no_overlap)
 
     def step(i, fresh=False):
         p, t = dev_in[i % N_ROTATE]
@@ -641,16 +648,21 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        # the solve kernel's own duration: CUDA events around it alone, same buffers, on the launch stream
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 50
-        k0.record()
-        for i in range(reps):
-            p, t = dev_in[i % N_ROTATE]
-            ctx.solve_batch(p, t, N=NCOEF, derivative=DERIV, out=dev_out[i % N_ROTATE])
-        k1.record()
-        torch.cuda.synchronize()
-        kernel_s = k0.elapsed_time(k1) / reps * 1e-3
+        # the solve kernel's own duration: CUDA events around a train of launches of it alone, same buffers, on the
+        # launch stream — as in the timed region (consecutive launches may overlap) and with ordinary launches
+        def kernel_train(reps=50):
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            for i in range(reps):
+                p, t = dev_in[i % N_ROTATE]
+                ctx.solve_batch(p, t, N=NCOEF, derivative=DERIV, out=dev_out[i % N_ROTATE])
+            k1.record()
+            torch.cuda.synchronize()
+            return k0.elapsed_time(k1) / reps * 1e-3
+        kernel_train(10)
+        kernel_s = kernel_train()
+        ctx.set_solve_overlap(False)
+        kernel_iso_s = kernel_train()
         achieved = BYTES_PER_TRAJ * B / kernel_s / 1e9
         fp64_peak = ctx.probe_fp64_fma(reps=5)       # measured DFMA roof of this GPU (TFLOP/s)
         ref_tflops = FLOP_PER_TRAJ_REF * B / kernel_s / 1e12
@@ -678,6 +690,12 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
                          "kernel": SOLVE_KERNEL_NAME, "kernel_ms": kernel_s * 1e3,
+                         "kernel_ms_isolated": kernel_iso_s * 1e3,
+                         "frac_isolated": BYTES_PER_TRAJ * B / kernel_iso_s / 1e9 / peak,
+                         "kernel_timing": "average launch duration in a train of 50 launches (CUDA events on the launch "
+                                          "stream): kernel_ms with programmatic dependent launch as in the timed region "
+                                          "(a launch starts on the SMs the previous one's last wave leaves empty), "
+                                          "kernel_ms_isolated with ordinary launches (what ncu's serialised replay sees)",
                          "kernel_share_of_step": kernel_s * 1e3 / ms_per_step,
                          "traffic": TRAFFIC_PER_LAUNCH if B == BATCH_PER_GPU else None,
                          "traffic_source": TRAFFIC_SOURCE,

@@ -490,6 +490,16 @@ int mtg_generate_candidates_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, ui
  * caller reads best_global when it needs it. Without an initialised communicator: a copy. */
 int mtg_argmin_batch(mtg_ctx* ctx, const double* cost, const uint32_t* status, int64_t n,
                      int64_t global_offset, int accumulate, void* best, void* stream);
+/* mtg_set_solve_overlap: lets consecutive DEVICE-memory solves of one stream overlap (programmatic dependent
+ * launch, sm_90+). 65,536 solves are 3.46 waves of CTAs: with the option on, mtg_solve_batch / mtg_solve_argmin_batch
+ * are launched with programmatic stream serialization, so the next solve's CTAs start on the SMs the last, partial
+ * wave of the previous one leaves empty; they run the part that only READS global memory (the forward elimination)
+ * and wait for the previous kernel to finish before their first global store. Outputs may therefore be reused from
+ * call to call as usual. CONTRACT while it is on: the inputs of a solve (positions, end_derivatives, seg_times) must
+ * not be written by the stream operation immediately preceding it (e.g. do not put mtg_generate_candidates_batch
+ * directly before the solve of its own output; generate one batch ahead instead). Off by default. */
+int mtg_set_solve_overlap(mtg_ctx* ctx, int enabled);
+
 /* mtg_solve_argmin_batch: one step of a candidate sweep in ONE launch — mtg_solve_batch (same
  * arguments and meaning; coeffs, cost, free_constraints and status may ALL be NULL) with
  * mtg_argmin_batch over its costs folded into the solve kernel's epilogue: every CTA publishes the

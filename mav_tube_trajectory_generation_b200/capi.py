@@ -93,6 +93,7 @@ def load() -> C.CDLL:
     lib.mtg_generate_candidates_batch.argtypes = [vp, C.POINTER(ProblemDesc), C.c_uint64, C.c_int64, vp, vp, C.c_double,
                                                   C.c_double, C.c_double, dp, dp, vp]
     lib.mtg_argmin_batch.argtypes = [vp, dp, u32p, C.c_int64, C.c_int64, C.c_int, vp, vp]
+    lib.mtg_set_solve_overlap.argtypes = [vp, C.c_int]
     lib.mtg_solve_argmin_batch.argtypes = [vp, C.POINTER(ProblemDesc), dp, dp, dp, dp, dp, dp, u32p, C.c_int64, C.c_int,
                                            vp, vp]
     lib.mtg_nccl_unique_id.argtypes = [vp, C.c_char_p]
@@ -365,6 +366,11 @@ class Context:
                                         1 if accumulate else 0, _ptr(best), self._stream(MTG_MEM_DEVICE, stream))
         self._check(rc, "mtg_argmin_batch")
         return best
+
+    def set_solve_overlap(self, enabled: bool):
+        """mtg_set_solve_overlap: consecutive device-memory solves of a stream may overlap (see include/mtg_cuda.h
+        for the contract on their inputs)."""
+        self._check(self._lib.mtg_set_solve_overlap(self._h, 1 if enabled else 0), "mtg_set_solve_overlap")
 
     def solve_argmin_batch(self, positions, seg_times, end_derivatives=None, N: int = 10, derivative: int = 4,
                            layout: str = "soa", global_offset: int = 0, best=None, accumulate=False, out=None,

@@ -46,6 +46,7 @@ struct mtg_ctx {
   size_t smem_optin = 0;
   std::string err;
   uint64_t launches = 0;
+  int solve_overlap = 0;  // mtg_set_solve_overlap
   cudaStream_t stage_stream[kStageSlots] = {nullptr, nullptr, nullptr};
   DeviceBuffer stage[kStageSlots];  // one staging arena per slot (host-memory mode)
   DeviceBuffer scratch;             // small per-context device scratch

@@ -52,6 +52,7 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* po
     p.b0 = 0;
     p.nb = B;
     p.vec_ok = (coeffs && (uintptr_t)coeffs % 16 == 0) ? 1 : 0;
+    p.overlap = ctx->solve_overlap;
     return launch_solve_canonical(ctx, N, D, aos, p, stream);
   }
 
@@ -77,6 +78,12 @@ int mtg_solve_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const double* po
     p.vec_ok = 1;
     return launch_solve_canonical(ctx, N, D, aos, p, st);
   });
+}
+
+int mtg_set_solve_overlap(mtg_ctx* ctx, int enabled) {
+  if (!ctx) return MTG_ERR_INVALID_ARGUMENT;
+  ctx->solve_overlap = enabled ? 1 : 0;
+  return MTG_OK;
 }
 
 // Candidate sweep in ONE launch: the solve with the argmin of its costs folded into the kernel's epilogue.
@@ -139,6 +146,7 @@ int mtg_solve_argmin_batch(mtg_ctx* ctx, const mtg_problem_desc* desc, const dou
   p.b0 = 0;
   p.nb = B;
   p.vec_ok = (coeffs && (uintptr_t)coeffs % 16 == 0) ? 1 : 0;
+  p.overlap = ctx->solve_overlap;
   p.best_lock = (unsigned*)state->ptr + 1;
   p.best_out = best;
   p.best_offset = global_offset;

@@ -58,6 +58,8 @@ struct SolveCanonicalParams {
   int vec_ok;  // AoS only: coeffs is 16-byte aligned -> double2 stores
   // fused candidate argmin (mtg_solve_argmin_batch; best_out == nullptr: off): every CTA folds the best
   // {cost, global index} of its trajectories into the running pair *best_out
+  int overlap = 0;  // 1: launched with programmatic stream serialization (mtg_set_solve_overlap): the grid may start
+                    // while the previous kernel of the stream drains and waits for it before its first global store
   unsigned* best_lock = nullptr;        // zero when free
   void* best_out = nullptr;             // Best*: the running best, {+inf, -1} = nothing yet
   long long best_offset = 0;            // global index of trajectory 0 of the batch
@@ -244,6 +246,9 @@ __global__ void __launch_bounds__(MTG_SOLVE_THREADS, 2) solve_canonical_kernel(c
   const size_t B = (size_t)p.B;
   const int d = DT >= 0 ? DT : p.derivative;
   uint32_t st = 0;
+  // programmatic dependent launch (no-ops for an ordinary launch): let the next solve of the stream start filling
+  // the SMs this grid's last, partial wave leaves empty
+  if (p.overlap) asm volatile("griddepcontrol.launch_dependents;");
 
   const size_t rec_pos = (size_t)(K + 1) * D, rec_t = (size_t)K, rec_end = (size_t)2 * NF * D;
   auto pos = [&](int v, int dim) { return p.positions[at<AOS>((size_t)v * D + dim, rec_pos, B, b)]; };
@@ -280,6 +285,7 @@ __global__ void __launch_bounds__(MTG_SOLVE_THREADS, 2) solve_canonical_kernel(c
   double cost_acc = 0.0;
 
   if (K == 1) {
+    if (p.overlap) asm volatile("griddepcontrol.wait;" ::: "memory");
     // fully constrained single segment: lane A writes it from both vertices' constraints
     double other[D][HN];
 #pragma unroll
@@ -469,6 +475,8 @@ __global__ void __launch_bounds__(MTG_SOLVE_THREADS, 2) solve_canonical_kernel(c
     }
   }
   const size_t rec_free = (size_t)D * (K - 1) * NF;
+  // everything above only READ global memory; from here on this grid writes its outputs
+  if (p.overlap) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (p.free_constraints && active && side == 0) {
 #pragma unroll
     for (int dim = 0; dim < D; ++dim)

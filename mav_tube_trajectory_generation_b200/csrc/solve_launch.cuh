@@ -51,7 +51,21 @@ int launch_solve_canonical_dt(mtg_ctx* ctx, const mtg::SolveCanonicalParams& p, 
   if (grid == 0) return MTG_OK;
   if (p.best_out && (block % 32 != 0 || p.K < 2))
     return fail(ctx, MTG_ERR_UNSUPPORTED, "solve_canonical: the fused argmin needs whole warps and K >= 2");
-  kern<<<grid, block, smem, stream>>>(p);
+  if (p.overlap) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MTG_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+  } else {
+    kern<<<grid, block, smem, stream>>>(p);
+  }
   ++ctx->launches;
   MTG_CUDA_TRY(cudaGetLastError());
   return MTG_OK;

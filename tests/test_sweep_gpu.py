@@ -176,3 +176,40 @@ def test_fused_solve_argmin_equals_the_two_launches(po, layout):
     p1 = c.solve_batch(pos1, times1, layout=layout)
     assert c.decode_best(c.solve_argmin_batch(pos1, times1, layout=layout)) == \
         ref_argmin(host(p1["cost"]), host(p1["status"]))
+
+
+def test_overlapped_solve_train_is_bit_identical():
+    """mtg_set_solve_overlap: a train of solves launched with programmatic stream serialization (each may start
+    while the previous one drains, and waits for it before its first store) writes the SAME outputs as ordinary
+    launches — also when every call reuses one output buffer — and the fused running argmin is the same."""
+    import torch
+
+    c = ctx()
+    B, K, n = 20000, 10, 6
+    batches = [c.generate_candidates_batch(B, K, 3, seed=40 + i) for i in range(n)]
+    torch.cuda.synchronize()
+    want, want_best = [], torch.zeros(2, dtype=torch.int64, device="cuda")
+    for i, (p, t) in enumerate(batches):
+        want.append(c.solve_batch(p, t))
+        c.argmin_batch(want[-1]["cost"], status=want[-1]["status"], global_offset=i * B, best=want_best,
+                       accumulate=i > 0)
+    torch.cuda.synchronize()
+    try:
+        c.set_solve_overlap(True)
+        for rep in range(3):
+            # one output buffer for the whole train: only the last solve's results may be in it afterwards
+            out = {k: torch.empty_like(v) for k, v in want[0].items() if v is not None}
+            best = torch.zeros(2, dtype=torch.int64, device="cuda")
+            for i, (p, t) in enumerate(batches):
+                c.solve_argmin_batch(p, t, out=out, global_offset=i * B, best=best, accumulate=i > 0)
+            torch.cuda.synchronize()
+            for k in out:
+                assert torch.equal(out[k], want[-1][k]), k
+            assert torch.equal(best, want_best)
+            # separate outputs, plain mtg_solve_batch
+            outs = [c.solve_batch(p, t) for p, t in batches]
+            torch.cuda.synchronize()
+            for a, b in zip(outs, want):
+                assert torch.equal(a["coeffs"], b["coeffs"]) and torch.equal(a["cost"], b["cost"])
+    finally:
+        c.set_solve_overlap(False)
