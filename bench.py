@@ -557,6 +557,11 @@ def main():
     # by the stream operation before them, which is what mtg_set_solve_overlap asks for
     ctx.set_solve_overlap(not args.no_overlap)
 
+    # one prepared call per buffer set: a step is then ONE ctypes call (a few microseconds of host time), so that the
+    # launch train is paced by the GPU and not by the Python binding (rank 0 also runs the rendezvous store)
+    prepared = [ctx.prepare_solve_argmin(dev_in[k][0], dev_in[k][1], N=NCOEF, derivative=DERIV, best=best,
+                                         out=dev_out[k]) for k in range(N_ROTATE)]
+
     def step(i, fresh=False):
         p, t = dev_in[i % N_ROTATE]
         o = dev_out[i % N_ROTATE]
@@ -567,8 +572,7 @@ def main():
             ctx.argmin_batch(o["cost"], status=o["status"], global_offset=off, best=best, accumulate=not fresh)
         else:
             # the same step in one launch: all outputs written, the argmin folded into the solve kernel's epilogue
-            ctx.solve_argmin_batch(p, t, N=NCOEF, derivative=DERIV, out=o, global_offset=off, best=best,
-                                   accumulate=not fresh)
+            prepared[i % N_ROTATE](off, not fresh)
 
     def barrier():
         torch.cuda.synchronize()
@@ -582,7 +586,7 @@ def main():
     sampler = ClockSampler(local_rank)
     ev0, ev_c, ev1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     for i in range(args.warmup):
-        step(i)
+        step(i, fresh=(i == 0))   # the warm-up also takes the fresh-sweep route once (its reset kernel loads lazily)
     ctx.best_allgather(best, out=best_global)   # warm-up of the collective too (NCCL connects lazily)
     barrier()
     n0 = ctx.launch_count

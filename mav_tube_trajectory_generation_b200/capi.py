@@ -367,6 +367,35 @@ class Context:
         self._check(rc, "mtg_argmin_batch")
         return best
 
+    def prepare_solve_argmin(self, positions, seg_times, end_derivatives=None, N: int = 10, derivative: int = 4,
+                             layout: str = "soa", best=None, out=None, stream=None):
+        """A prepared mtg_solve_argmin_batch call on fixed CUDA tensors: returns run(global_offset, accumulate),
+        which is ONE ctypes call (the descriptor and the pointers are built here, once) — a launch loop driven
+        from Python then costs a few microseconds of host time per step, like a C++ host."""
+        aos = layout == "aos"
+        if aos:
+            B, Kp1, D = positions.shape
+        else:
+            Kp1, D, B = positions.shape
+        if not (_is_torch(positions) and positions.is_cuda) or best is None:
+            raise MtgError("prepare_solve_argmin takes CUDA tensors and a `best` pair")
+        for nm, x in (("positions", positions), ("seg_times", seg_times)):
+            self._contig(x, nm)
+        out = out or {}
+        desc = ProblemDesc(B, Kp1 - 1, D, N, derivative, MTG_MEM_DEVICE, LAYOUT_AOS if aos else LAYOUT_SOA)
+        keep = (positions, seg_times, end_derivatives, best, dict(out))   # the tensors outlive the closure's calls
+        fixed = (self._h, C.byref(desc), _ptr(positions), _ptr(end_derivatives), _ptr(seg_times),
+                 _ptr(out.get("coeffs")), _ptr(out.get("cost")), _ptr(out.get("free")), _ptr(out.get("status")))
+        tail = (_ptr(best), self._stream(MTG_MEM_DEVICE, stream))
+        fn = self._lib.mtg_solve_argmin_batch
+
+        def run(global_offset: int, accumulate: bool, _keep=keep, _desc=desc):
+            rc = fn(*fixed, global_offset, 1 if accumulate else 0, *tail)
+            if rc:
+                self._check(rc, "mtg_solve_argmin_batch")
+
+        return run
+
     def set_solve_overlap(self, enabled: bool):
         """mtg_set_solve_overlap: consecutive device-memory solves of a stream may overlap (see include/mtg_cuda.h
         for the contract on their inputs)."""
