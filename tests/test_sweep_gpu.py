@@ -213,3 +213,31 @@ def test_overlapped_solve_train_is_bit_identical():
                 assert torch.equal(a["coeffs"], b["coeffs"]) and torch.equal(a["cost"], b["cost"])
     finally:
         c.set_solve_overlap(False)
+
+
+def test_fused_argmin_corner_cases():
+    """Nothing qualifies (every solve fails): the pair stays {inf, -1}; a later batch still wins; the K = 1 shape
+    with the overlap option on takes the two-launch route and gives the same pair."""
+    import torch
+
+    c = ctx()
+    B, K = 1000, 4
+    pos, times = c.generate_candidates_batch(B, K, 3, seed=90)
+    bad = -times.abs()
+    st = torch.empty((B,), dtype=torch.int32, device="cuda")
+    best = c.solve_argmin_batch(pos, bad, out={"status": st})
+    cost, idx = c.decode_best(best)
+    assert idx == -1 and cost == float("inf") and int((st != 0).sum()) == B
+    c.solve_argmin_batch(pos, times, global_offset=5000, best=best, accumulate=True)
+    plain = c.solve_batch(pos, times)
+    assert c.decode_best(best) == ref_argmin(host(plain["cost"]), host(plain["status"]), 5000)
+    pos1, times1 = c.generate_candidates_batch(500, 1, 3, seed=91)
+    p1 = c.solve_batch(pos1, times1)
+    try:
+        c.set_solve_overlap(True)
+        got = c.decode_best(c.solve_argmin_batch(pos1, times1))
+        again = c.solve_batch(pos1, times1)
+    finally:
+        c.set_solve_overlap(False)
+    assert got == ref_argmin(host(p1["cost"]), host(p1["status"]))
+    assert torch.equal(again["coeffs"], p1["coeffs"]) and torch.equal(again["cost"], p1["cost"])
