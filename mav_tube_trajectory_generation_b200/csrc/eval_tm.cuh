@@ -110,6 +110,12 @@ __global__ void __launch_bounds__(256) tube_setup_kernel(const EvalParams p, dou
 //
 // Shared memory per warp (TmLayout): tau[TPW][33] | staging tile [8][4*(8 D + 1)] | info, offsets,
 // counts | flag rows | acc[TPW][33] (only when sampling_times is requested) | slot pairs [TPW].
+#ifndef MTG_TM_FEAS_MINB
+#define MTG_TM_FEAS_MINB 8  // resident warps per SM the feasibility instantiations are compiled for
+#endif
+#ifndef MTG_TM_FEAS_JB
+#define MTG_TM_FEAS_JB 4    // samples a lane advances together in the feasibility sweep (3 * JB * D FMA chains)
+#endif
 #ifndef MTG_TM_TAUBLK
 #define MTG_TM_TAUBLK 1  // 1: phase 1 parks tau at block starts only, phase-2 lanes replay their 8 adds
 #endif
@@ -128,7 +134,10 @@ struct TmLayout {
 // TPW = trajectories per warp (phase-1 lanes in use): the shared memory of a warp scales with it.
 // 16 doubles the resident warps of the latency-bound position sweep; the fp64-bound feasibility
 // sweep prefers full phase-1 lanes (32).
-__host__ __device__ constexpr int tm_tpw(int mode) { return mode >= 2 ? 16 : 16; }
+#ifndef MTG_TM_FEAS_TPW
+#define MTG_TM_FEAS_TPW 16
+#endif
+__host__ __device__ constexpr int tm_tpw(int mode) { return mode >= 2 ? MTG_TM_FEAS_TPW : 16; }
 __host__ __device__ inline TmLayout tm_layout(int D, int NT, bool want_acc, bool tube, int kTmTPW, int mode) {
   const bool kTmTauBlk = tm_taublk(mode);
   TmLayout L;
@@ -154,7 +163,7 @@ enum TmMode { TM_POSITION = 0, TM_DERIVATIVE = 1, TM_FEAS = 2, TM_FEAS_TUBE = 3 
 // Requirements (checked by the launcher, which otherwise falls back to the one-thread-per-
 // trajectory kernels of eval.cuh): AoS layout, N == NT, coeffs 16-byte aligned.
 template <int NT, int D, int MODE>
-__global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
+__global__ void __launch_bounds__(32, (MODE >= 2 ? MTG_TM_FEAS_MINB : MODE == 1 ? 12 : 13)) eval_tm_kernel(const EvalParams p, const double* __restrict__ geom) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr bool FEAS = MODE >= TM_FEAS;
   constexpr bool tube = MODE == TM_FEAS_TUBE;
@@ -416,7 +425,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? 8 : MODE == 1 ? 12 : 13)) eva
       double* srow = stage + q8 * L.row_ld;
       // JB samples advance together, one Horner step at a time: JB*D (position) or 3*JB*D
       // (feasibility) independent FMA chains cover the fp64 pipe latency from a single warp.
-      constexpr int JB = FEAS ? 4 : R;
+      constexpr int JB = FEAS ? MTG_TM_FEAS_JB : R;
       double tcur = 0.0, dt_r = 0.0;
       if (kTmTauBlk) {
         tcur = tau_s[r * TAU_LD + sb];
