@@ -16,15 +16,21 @@ hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Line No")
 hdr = rows[hdr_i]
 ie, te, sm = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
 lines = []
+n_fun, cur_file = 0, ""
 for r in rows[hdr_i + 1:]:
     if not r or r[0] in ("File Path", "Function Name", "Line No"):
-        if r and r[0] == "Function Name" and lines:
-            break
+        if r and r[0] == "File Path" and len(r) > 1:
+            cur_file = r[1].split("/")[-1]
+        if r and r[0] == "Function Name":
+            n_fun += 1
+            if n_fun > 1 and "--all-files" not in sys.argv:
+                pass  # every source file of the kernel has its own section: all of them are summed
         continue
     if r[0] == "":
         continue
     try:
-        lines.append((int(r[0]), r[1].strip(), int(r[ie] or 0), int(r[te] or 0), int(r[sm] or 0)))
+        lines.append((int(r[0]), (cur_file + ": " if cur_file else "") + r[1].strip(), int(r[ie] or 0),
+                      int(r[te] or 0), int(r[sm] or 0)))
     except ValueError:
         pass
 tot_i = sum(x[2] for x in lines)
