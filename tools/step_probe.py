@@ -6,6 +6,8 @@ import numpy as np, torch, bench
 import mav_tube_trajectory_generation_b200 as m
 
 ctx = m.Context(0)
+if os.environ.get("MTG_PROBE_OVERLAP"):
+    ctx.set_solve_overlap(True)   # inputs are resident: consecutive solves may overlap
 B, R = 65536, 4
 ins, outs = [], []
 for i in range(R):
