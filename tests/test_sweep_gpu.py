@@ -241,3 +241,34 @@ def test_fused_argmin_corner_cases():
         c.set_solve_overlap(False)
     assert got == ref_argmin(host(p1["cost"]), host(p1["status"]))
     assert torch.equal(again["coeffs"], p1["coeffs"]) and torch.equal(again["cost"], p1["cost"])
+
+
+def test_overlapped_sweep_with_device_generator():
+    """The sweep loop of INTEGRATION.md with mtg_set_solve_overlap on: batch it + 1 is generated (into the other
+    buffer pair) BEFORE the solve of batch it is launched, so no solve reads what the operation right before it
+    wrote. Same running best as the plain loop."""
+    import torch
+
+    c = ctx()
+    B, K, n = 30000, 10, 8
+
+    def sweep(overlap):
+        best = torch.zeros(2, dtype=torch.int64, device="cuda")
+        bufs = [c.generate_candidates_batch(B, K, 3, seed=123, first_index=0), None]
+        c.set_solve_overlap(overlap)
+        try:
+            for it in range(n):
+                if it + 1 < n:
+                    if bufs[(it + 1) % 2] is None:
+                        bufs[(it + 1) % 2] = tuple(torch.empty_like(x) for x in bufs[0])
+                    nxt = c.generate_candidates_batch(B, K, 3, seed=123, first_index=(it + 1) * B)
+                    for dst, src in zip(bufs[(it + 1) % 2], nxt):   # generator output lands in the other pair
+                        dst.copy_(src)
+                p, t = bufs[it % 2]
+                c.solve_argmin_batch(p, t, global_offset=it * B, best=best, accumulate=it > 0)
+            torch.cuda.synchronize()
+        finally:
+            c.set_solve_overlap(False)
+        return c.decode_best(best)
+
+    assert sweep(True) == sweep(False)
