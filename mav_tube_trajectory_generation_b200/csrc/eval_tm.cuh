@@ -110,6 +110,16 @@ __global__ void __launch_bounds__(256) tube_setup_kernel(const EvalParams p, dou
 //
 // Shared memory per warp (TmLayout): tau[TPW][33] | staging tile [8][4*(8 D + 1)] | info, offsets,
 // counts | flag rows | acc[TPW][33] (only when sampling_times is requested) | slot pairs [TPW].
+#ifndef MTG_TM_STORE_MODE
+#define MTG_TM_STORE_MODE 0  // sample rows: 0 plain stores, 1 streaming (st.cs), 2 write-through (st.wt); measured, see profiles/r02_experiments
+#endif
+#if MTG_TM_STORE_MODE == 1
+#define MTG_TM_STORE(ptr, v) __stcs((ptr), (v))
+#elif MTG_TM_STORE_MODE == 2
+#define MTG_TM_STORE(ptr, v) __stwt((ptr), (v))
+#else
+#define MTG_TM_STORE(ptr, v) (*(ptr) = (v))
+#endif
 #ifndef MTG_TM_FEAS_MINB
 #define MTG_TM_FEAS_MINB 8  // resident warps per SM the feasibility instantiations are compiled for
 #endif
@@ -560,7 +570,7 @@ __global__ void __launch_bounds__(32, (MODE >= 2 ? MTG_TM_FEAS_MINB : MODE == 1 
           const int total = cnt_t * D;
 #pragma unroll
           for (int q = 0; q < D; ++q)
-            if (lane + 32 * q < total) out[32 * q] = row[skew[q]];
+            if (lane + 32 * q < total) MTG_TM_STORE(out + 32 * q, row[skew[q]]);
         }
         if (FEAS) {
           if (p.flags && lane < cnt_t) p.flags[o + lane] = flag_s[t * 40 + lane];
