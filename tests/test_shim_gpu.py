@@ -8,6 +8,7 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BIN = os.path.join(HERE, "cpp", "shim_check")
+SWEEP_BIN = os.path.join(HERE, "cpp", "sweep_check")
 
 
 def build():
@@ -19,7 +20,7 @@ def test_class_api_compiles_and_links():
 
     m._build.build()
     build()
-    assert os.path.exists(BIN)
+    assert os.path.exists(BIN) and os.path.exists(SWEEP_BIN)
 
 
 @pytest.mark.gpu
@@ -30,3 +31,15 @@ def test_class_api_on_gpu():
     print(r.stdout)
     print(r.stderr)
     assert r.returncode == 0 and "SHIM OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_c_abi_sweep_from_compiled_code():
+    """tests/cpp/sweep_check.cpp: the INTEGRATION.md sweep loop (device generator -> fused solve + argmin with
+    overlapping launches -> one pair) against the C ABI only, compared with a host-memory scan."""
+    if not os.path.exists(SWEEP_BIN):
+        build()
+    r = subprocess.run([SWEEP_BIN], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    print(r.stderr)
+    assert r.returncode == 0 and "SWEEP OK" in r.stdout, r.stdout + r.stderr
