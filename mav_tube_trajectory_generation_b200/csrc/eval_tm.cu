@@ -22,7 +22,7 @@ double sq_limit(double lim) {
   return y;
 }
 
-constexpr int kTmBlock = 32;            // one warp = 32 trajectories per CTA (finest shared-memory packing)
+constexpr int kTmBlock = 32;            // one warp per CTA = tm_tpw() = 16 trajectories (finest shared-memory packing)
 constexpr int kTubeChunk = 65536;       // trajectories per launch pair when a tube scratch is needed
 
 template <int NT, int D, int MODE>

@@ -142,8 +142,8 @@ struct TmLayout {
   int off_stage, off_info, off_off, off_cnt, off_flag, off_acc, off_slots, off_dt, per_warp;
 };
 // TPW = trajectories per warp (phase-1 lanes in use): the shared memory of a warp scales with it.
-// 16 doubles the resident warps of the latency-bound position sweep; the fp64-bound feasibility
-// sweep prefers full phase-1 lanes (32).
+// 16 (half the phase-1 lanes idle) doubles the resident warps against 32 and is what every mode ships with; for the
+// feasibility sweep 8 and 32 were measured and lose (profiles/r02_experiments, profiles/r01_sweep_ab_experiments.log).
 #ifndef MTG_TM_FEAS_TPW
 #define MTG_TM_FEAS_TPW 16
 #endif
