@@ -272,3 +272,18 @@ def test_overlapped_sweep_with_device_generator():
         return c.decode_best(best)
 
     assert sweep(True) == sweep(False)
+
+
+def test_fused_argmin_at_a_million_candidates():
+    """Full size of a sweep step (BASELINE configs[4]): 1,000,000 candidates, 15,625 CTAs folding into one pair."""
+    c = ctx()
+    B = 1_000_000
+    pos, times = c.generate_candidates_batch(B, 10, 3, seed=31337)
+    plain = c.solve_batch(pos, times, want_coeffs=False)
+    want = c.decode_best(c.argmin_batch(plain["cost"], plain["status"], global_offset=10**12))
+    assert c.decode_best(c.solve_argmin_batch(pos, times, global_offset=10**12)) == want
+    try:
+        c.set_solve_overlap(True)
+        assert c.decode_best(c.solve_argmin_batch(pos, times, global_offset=10**12)) == want
+    finally:
+        c.set_solve_overlap(False)
